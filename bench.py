@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- pair-column comparisons/s of the pairwise-identity hot path.
+
+Workload (config.workload): BASELINE.json configs[3], the RepresentativeTrimmer
+identity matrix of a synthetic 50 000 x 1 000 protein MSA (seed 4): the largest
+configuration that is sharded over 1/2/4/8 GPUs and fits one B200.  A "step" is
+one full pass of the hot path over the alignment: bit-plane packing (K0) plus
+the pairwise-identity kernel (K1) for every pair this rank owns.
+
+  value  : whole-job pair-column comparisons/s (P*L*K / max-over-ranks device
+           time), alignment already resident in HBM.
+  e2e    : the same metric through the host-buffer C ABI (tcu_msa_create_strided
+           + tcu_identity_band): pinned host rows -> device, kernels, packed
+           identity rows -> pinned host memory, all inside the timed region.
+  N > 1  : the pair matrix is split into contiguous row-block bands of equal
+           pair count, one band per rank, no data-path collective (strong
+           scaling: the alignment is fixed, every rank holds a replica).
+
+`--impl reference` times the reference's own AVX2 code (oracle/_ref, the
+unmodified vendored trimAl compiled by oracle/Makefile) on the box's host CPU.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pair-column comparisons/s (pairwise identity)"
+UNIT = "pair-col/s"
+OPS_PER_PAIR_COLUMN = 42  # 2*(20 one-hot planes + 1 gap plane) int8 tensor ops
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16_tflops": float(p["bf16_tflops"]), "hbm_gbs": float(p["hbm_gbs"]),
+                "source": "measured (MEASURED_PEAKS.json, burst)"}
+    return {"bf16_tflops": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for nme, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def band_partition(nb, world):
+    """Row-block boundaries with (nearly) equal tile counts per rank."""
+    total = nb * (nb + 1) // 2
+    before = lambda b: b * nb - b * (b - 1) // 2
+    bounds = [0]
+    for g in range(1, world):
+        target = total * g / world
+        b = bounds[-1]
+        while b < nb and before(b) < target:
+            b += 1
+        bounds.append(b)
+    bounds.append(nb)
+    return bounds
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation (AVX2), bounded sample per step."""
+    if rank != 0:
+        return
+    import oracle
+    from pytrimal_b200.synthetic import CONFIGS, synthetic_msa
+    n, L, seed = CONFIGS[args.workload]
+    if args.rows:
+        n = args.rows
+    steps, warmup = args.steps, args.warmup
+    kind = "reference" if oracle.ref_available() else "port"
+    rate = 5.0e9 if kind == "reference" else 0.8e9          # expected pair-col/s per core
+    budget = min(8.0, 150.0 / max(1, steps + warmup))        # seconds per step
+    ns = int(min(n, max(64, math.sqrt(2.0 * rate * budget / L))))
+    m = synthetic_msa(ns, L, seed)
+    pairs = ns * (ns - 1) // 2
+    port = None if kind == "reference" else oracle.Port()
+
+    def one():
+        t0 = time.perf_counter()
+        if kind == "reference":
+            r = oracle.Ref(m, platform=oracle.PLATFORM_AVX2)
+            r.identity(copy=False)
+            del r
+        else:
+            port.identity(m, ord("X"))
+        return time.perf_counter() - t0
+
+    for _ in range(warmup):
+        one()
+    times = [one() for _ in range(steps)]
+    total = sum(times)
+    value = pairs * L * steps / total
+    sample = f"first {ns} of {n} rows x {L} cols of the seeded {args.workload} alignment per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * total / steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload}: pairwise identity {n}x{L} synthetic protein MSA "
+                               f"(RepresentativeTrimmer identity matrix)", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
+                         "note": "trimAl/pytrimal statistics are single-threaded (SURVEY F9); "
+                                 f"host has {os.cpu_count()} logical cores"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(workload, L, seed, n_full):
+    """AVX2 reference (or the port) on a bounded row sample, ~10-20 s of one core."""
+    import oracle
+    from pytrimal_b200.synthetic import synthetic_msa
+    kind = "reference" if oracle.ref_available() else "port"
+    rate = 5.0e9 if kind == "reference" else 0.8e9
+    ns = int(min(n_full, math.sqrt(2.0 * rate * 12.0 / L)))
+    m = synthetic_msa(ns, L, seed)
+    t0 = time.perf_counter()
+    if kind == "reference":
+        r = oracle.Ref(m, platform=oracle.PLATFORM_AVX2)
+        r.identity(copy=False)
+    else:
+        oracle.Port().identity(m, ord("X"))
+    dt = time.perf_counter() - t0
+    return {"value": ns * (ns - 1) // 2 * L / dt, "unit": UNIT, "cores": 1, "kind": kind,
+            "seconds": dt,
+            "sample": f"first {ns} of {n_full} rows x {L} cols of the seeded {workload} alignment, "
+                      "one pass of Identity::calculateSeqIdentity (AVX2)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C4", choices=["C2", "C3", "C4", "C5"])
+    ap.add_argument("--rows", type=int, default=0, help="debug: use only the first ROWS rows")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import pytrimal_b200 as pb
+    from pytrimal_b200 import _lib
+    from pytrimal_b200.synthetic import CONFIGS, synthetic_msa
+
+    if pb.device_count() < 1:
+        raise SystemExit("bench.py needs a B200: libtrimal_cuda has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n, L, seed = CONFIGS[args.workload]
+    m = synthetic_msa(n, L, seed)
+    if args.rows:
+        m = m[: args.rows].copy()
+        n = args.rows
+    pairs_total = n * (n - 1) // 2
+    X = ord("X")
+    lib = pb.load()
+
+    # pinned host copy of the rows (e2e uploads come from pinned memory)
+    host_rows = torch.from_numpy(m).pin_memory()
+    host_np = host_rows.numpy()
+
+    nb = lib.tcu_identity_row_blocks(n)
+    bounds = band_partition(nb, world)
+    b0, b1 = bounds[rank], bounds[rank + 1]
+    off0 = lib.tcu_identity_row_offset(n, 64 * b0)
+    off1 = lib.tcu_identity_row_offset(n, min(64 * b1, n))
+    my_pairs = off1 - off0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident steps ---------------------------------
+    dev = pb.DeviceAlignment(pb.Alignment.from_matrix(host_np), device=local_rank)
+    out = torch.empty(max(my_pairs, 1), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", local_rank))
+
+    def step():
+        dev.identity_prepare(X)                 # K0: pack (1 kernel)
+        dev.identity_device(b0, b1, out.data_ptr())   # K1 (1 kernel)
+
+    for _ in range(args.warmup):
+        step()
+    dev.sync()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k_ms = []
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+        # per-step kernel time from the library's own events on the same stream
+    e1.record(stream)
+    dev.sync()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    # duration of the dominant kernel alone (last step), CUDA events inside the library
+    t = dev.timings
+    kernel_ms, pack_ms = t["kernel_ms"], t["pack_ms"]
+
+    tmax = torch.tensor([ms_total, kernel_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total_max, kernel_ms_max = tmax.tolist()
+    value = pairs_total * L * args.steps / (ms_total_max * 1e-3)
+
+    # ---------------- end-to-end through the host-buffer C ABI ----------------
+    host_out = torch.empty(max(my_pairs, 1), dtype=torch.float32).pin_memory()
+    out_ptr = C.cast(host_out.data_ptr(), C.POINTER(C.c_float))
+
+    def e2e_step():
+        h = C.c_void_p()
+        _lib.check(lib.tcu_msa_create_strided(C.c_void_p(host_rows.data_ptr()), n, L, L, local_rank,
+                                              C.byref(h)))
+        try:
+            _lib.check(lib.tcu_identity_band(h, None, None, X, b0, b1, out_ptr))
+        finally:
+            lib.tcu_msa_destroy(h)
+
+    e2e_step()  # warm-up (pinned pool, allocations)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = pairs_total * L * args.e2e_steps / te.item()
+
+    # spot-check the e2e result against the device-resident one
+    same = bool(torch.equal(host_out[: min(my_pairs, 1 << 20)],
+                            out[: min(my_pairs, 1 << 20)].cpu()))
+
+    if rank == 0:
+        peaks = measured_peaks()
+        peak_tops = 2.0 * peaks["bf16_tflops"]          # int8 dense = 2x bf16 dense
+        my_tiles_pairs = my_pairs if world == 1 else None
+        # rank 0's launch processes its own band: use the max-over-ranks duration with
+        # the per-rank share of the pairs (bands hold equal pair counts)
+        achieved_tops = OPS_PER_PAIR_COLUMN * (pairs_total / world) * L / (kernel_ms_max * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total_max / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {
+                "workload": f"{args.workload}: pairwise identity {n}x{L} synthetic protein MSA "
+                            "(RepresentativeTrimmer identity matrix), K0 pack + K1 identity per step",
+                "pairs": pairs_total, "columns": L, "parallelism": f"row-block bands x{world}",
+                "l2": "no explicit flush: each step writes %.2f GB of identities per GPU, >> 126 MB L2"
+                      % (4.0 * my_pairs / 1e9),
+            },
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n) * int(L),
+                    "d2h_bytes_per_step": int(4 * my_pairs), "steps": args.e2e_steps,
+                    "matches_device_result": same,
+                    "api": "tcu_msa_create_strided + tcu_identity_band (pinned host buffers)"},
+            "gpu_launches": 2 * args.steps,
+            "roofline": {
+                "bound": "tensor", "achieved": achieved_tops, "peak": peak_tops, "unit": "TFLOP/s",
+                "frac": achieved_tops / peak_tops, "traffic": None,
+                "kernel": "tcu::k_identity<5>", "kernel_ms": kernel_ms_max, "pack_ms": pack_ms,
+                "note": "algorithmic int8 tensor ops = 42 per pair-column (SURVEY 8d); peak = 2 x "
+                        "bf16 dense, " + peaks["source"] + "; the kernel itself runs on the "
+                        "LOP3/POPC integer pipes (bit-plane formulation)",
+            },
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.workload, L, seed, n)
+        print(json.dumps(line), flush=True)
+
+    dev.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

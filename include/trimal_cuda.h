@@ -1,0 +1,197 @@
+/*
+ * trimal_cuda.h -- C ABI of libtrimal_cuda.so, the B200 (sm_100a) implementation
+ * of trimAl's per-alignment statistics hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
+ * Each entry point replaces one virtual method that trimAl's SIMD platform
+ * classes override (reference paths relative to /root/reference/vendor/trimal/):
+ *
+ *   tcu_gaps        <- statistics::Gaps::CalculateVectors()
+ *                      include/Platform/x86/AVX2.h:52-58, source/Platform/x86/AVX2.cpp:133-136,
+ *                      kernel include/Platform/template.h:444-502
+ *   tcu_identity    <- statistics::Identity::calculateSeqIdentity()
+ *                      AVX2.h:67-72, AVX2.cpp:138-141, template.h:320-442
+ *   tcu_similarity  <- statistics::Similarity::calculateVectors(bool cutByGap)
+ *                      AVX2.h:44-50, AVX2.cpp:128-131, template.h:69-204
+ *   tcu_spurious    <- statistics::Overlap::calculateSpuriousVector(float, float*)
+ *                      AVX2.h:60-65, AVX2.cpp:143-148, template.h:206-318
+ *
+ * The host shim that binds them behind a new ComputePlatform::CUDA enumerator
+ * is in pytrimal_b200/csrc/shim/ and INTEGRATION.md.
+ *
+ * Conventions
+ *  - Every function returns TCU_OK (0) or a negative tcu_status; the message
+ *    of the last failure on the calling thread is in tcu_last_error().
+ *  - Host pointers are borrowed for the duration of the call.  Outputs are
+ *    caller-owned host buffers (the reference's base classes own them).
+ *  - There is no CPU fallback: without a usable CUDA device every compute
+ *    call fails with TCU_ERR_NO_DEVICE.
+ *  - A handle may be used from one thread at a time; different handles are
+ *    independent (own stream, own buffers), so trim() stays re-entrant.
+ *  - keep-masks follow trimAl: int arrays where -1 marks a removed
+ *    row/column (Alignment::saveSequences / saveResidues); NULL = keep all.
+ */
+#ifndef TRIMAL_CUDA_H
+#define TRIMAL_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum tcu_status {
+    TCU_OK = 0,
+    TCU_ERR_NO_DEVICE = -1,        /* no CUDA driver / no sm_100 device                */
+    TCU_ERR_OOM = -2,              /* host or device allocation failed                 */
+    TCU_ERR_CUDA = -3,             /* any other CUDA runtime failure                   */
+    TCU_ERR_INVALID = -4,          /* bad argument                                     */
+    TCU_ERR_INCORRECT_SYMBOL = -5, /* similarity: byte outside 'A'..'Z' (template.h:135-138) */
+    TCU_ERR_UNDEFINED_SYMBOL = -6, /* similarity: letter without matrix row (:140-144)  */
+    TCU_ERR_STATE = -7             /* call order (e.g. similarity before identity)     */
+} tcu_status;
+
+typedef struct tcu_msa tcu_msa; /* opaque: one alignment resident on one GPU */
+
+/* Number of usable sm_100 devices (0 when there is no driver or no GPU). */
+int tcu_device_count(void);
+
+/* Message of the last error raised on this thread ("" if none). */
+const char *tcu_last_error(void);
+
+/* Library version string. */
+const char *tcu_version(void);
+
+/*
+ * Upload an alignment.  rows: nseq pointers to ncol bytes each (the
+ * std::string::data() of Alignment::sequences).  The bytes are staged through
+ * pinned memory and copied to `device`; nothing is retained on the host.
+ */
+int tcu_msa_create(const char *const *rows, int nseq, int ncol, int device, tcu_msa **out);
+
+/* Same for one contiguous matrix: row r at data + r*stride. */
+int tcu_msa_create_strided(const uint8_t *data, int nseq, int ncol, size_t stride, int device,
+                           tcu_msa **out);
+
+void tcu_msa_destroy(tcu_msa *msa);
+
+int tcu_msa_nseq(const tcu_msa *msa);
+int tcu_msa_ncol(const tcu_msa *msa);
+
+/*
+ * Gap counts per column over kept rows ('-' only; the column mask is ignored,
+ * template.h:460-477).  gaps_in_column: ncol ints.  Optional (may be NULL):
+ * num_cols_with_gaps (nseq+1 ints, INCREMENTED like template.h:496-499) and
+ * max_gaps (raised, never lowered, :499-500).
+ */
+int tcu_gaps(tcu_msa *msa, const int *save_seq, int *gaps_in_column, int *num_cols_with_gaps,
+             int *max_gaps);
+
+/*
+ * Pairwise identity over kept rows i<j and kept columns (template.h:346-437).
+ * identities: kept_pairs floats in the reference's packed order.  hit_out /
+ * dst_out (optional, kept_pairs ints each) receive the integer counts.
+ * identities may be NULL when keep_on_device is set and only the device copy
+ * (for a following tcu_similarity) is wanted.
+ * indet: 'X' for amino-acid alignments else 'N' (template.h:331).
+ */
+int tcu_identity(tcu_msa *msa, const int *save_seq, const int *save_res, uint8_t indet,
+                 float *identities, int *hit_out, int *dst_out, int keep_on_device);
+
+/*
+ * Column similarity accumulators (template.h:120-183) for the unmasked
+ * alignment.  Uses the device-resident identities of the last tcu_identity
+ * (keep_on_device=1, no masks); if `identities` is non-NULL it is uploaded
+ * and used instead.
+ *   dist  : npos*npos floats, row-major distance matrix (similarityMatrix::distMat)
+ *   vhash : 26 ints, letter -> matrix row or -1 (similarityMatrix::vhash)
+ *   gaps  : ncol ints (windowed gap counts) or NULL for cutByGap=false
+ *   gap_threshold : 0.8f * numberOfResidues, computed by the caller (template.h:108)
+ * Outputs (ncol floats each): num, den -- the fp32 accumulators in the
+ * reference's exact summation order; mdk (optional) -- the final statistic
+ * (template.h:186-200; expf evaluated on the host with the C library).
+ * On TCU_ERR_INCORRECT_SYMBOL / TCU_ERR_UNDEFINED_SYMBOL, err_col / err_row /
+ * err_byte (optional) identify the first offender in the reference's scan
+ * order and the outputs are unspecified.
+ */
+int tcu_similarity(tcu_msa *msa, uint8_t indet, const float *dist, int npos, const int *vhash,
+                   const int *gaps, float gap_threshold, const float *identities, float *num,
+                   float *den, float *mdk, int *err_col, int *err_row, int *err_byte);
+
+/*
+ * Spurious / overlap vector (template.h:235-310) over ALL rows and columns.
+ * ovrlap = (uint32_t)ceil(overlap * (float)(nseq - 1)), computed by the caller
+ * (template.h:217-218).  spurious: nseq floats.
+ */
+int tcu_spurious(tcu_msa *msa, uint8_t indet, uint32_t ovrlap, float *spurious);
+
+/*
+ * Row-band variant for drivers that shard the pair matrix across GPUs: only
+ * the rows of row-blocks [block_begin, block_end) (64 kept rows per block;
+ * block_end < 0 = to the end) are computed and copied to `identities`, a HOST
+ * slice whose element 0 is packed offset tcu_identity_row_offset(kept,
+ * 64*block_begin).  Bands of different ranks concatenate to the full array.
+ */
+int tcu_identity_band(tcu_msa *msa, const int *save_seq, const int *save_res, uint8_t indet,
+                      int block_begin, int block_end, float *identities);
+
+/* ---- device-resident variants (benchmarks, multi-GPU drivers) -------------
+ * Same kernels, but results stay in device memory owned by the caller and no
+ * host synchronisation is done beyond what the arguments require.            */
+
+/* Number of 64-row blocks the kept rows are tiled into for tcu_identity_device. */
+int tcu_identity_row_blocks(int kept_rows);
+
+/* Packed-array offset of the first pair whose first row is i (kept-index space). */
+size_t tcu_identity_row_offset(int kept_rows, int i);
+
+/*
+ * Prepare the packed bit-planes for (save_seq, save_res, indet) on the device.
+ * Must precede tcu_identity_device; reusable across calls while the masks do
+ * not change.  kept_rows_out (optional) receives the number of kept rows.
+ */
+int tcu_identity_prepare(tcu_msa *msa, const int *save_seq, const int *save_res, uint8_t indet,
+                         int *kept_rows_out);
+
+/*
+ * Compute the rows of the packed identity array that belong to row-blocks
+ * [block_begin, block_end) (64 kept rows per block) into d_out, a DEVICE
+ * buffer whose element 0 corresponds to packed offset
+ * tcu_identity_row_offset(kept, 64*block_begin).  Asynchronous on the
+ * handle's stream; use tcu_msa_sync() to wait.
+ */
+int tcu_identity_device(tcu_msa *msa, int block_begin, int block_end, float *d_out);
+
+/* Wait for all work queued on the handle's stream. */
+int tcu_msa_sync(tcu_msa *msa);
+
+/* The handle's CUDA stream (cudaStream_t) and device ordinal. */
+void *tcu_msa_stream(tcu_msa *msa);
+int tcu_msa_device(const tcu_msa *msa);
+
+/*
+ * Device-side durations (CUDA events on the handle's stream) of the kernels
+ * launched by the most recent call on this handle, in milliseconds.
+ */
+typedef struct tcu_timings {
+    float h2d_ms;        /* host -> device copies                          */
+    float pack_ms;       /* bit-plane / code packing kernels               */
+    float kernel_ms;     /* the statistic's main kernel(s)                 */
+    float d2h_ms;        /* device -> host copies                          */
+    int kernel_launches; /* number of kernels launched by the call         */
+} tcu_timings;
+
+int tcu_msa_timings(const tcu_msa *msa, tcu_timings *out);
+
+/* ---- test-only -------------------------------------------------------------
+ * Same contract as tcu_identity (without keep_on_device), computed by a slow
+ * byte-wise kernel straight from the raw rows.  Lets the GPU tests tell a
+ * packing / pipeline fault from an arithmetic one.  Not for production use. */
+int tcu_debug_identity_bytes(tcu_msa *msa, const int *save_seq, const int *save_res,
+                             uint8_t indet, float *identities, int *hit_out, int *dst_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRIMAL_CUDA_H */

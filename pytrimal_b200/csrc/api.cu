@@ -1,0 +1,782 @@
+// api.cu -- the C ABI of libtrimal_cuda.so (include/trimal_cuda.h): handle
+// management, host<->device staging, and the call sequences around the kernels.
+// No CPU implementation of any statistic lives here: without a device every
+// compute entry point fails.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "tcu_internal.cuh"
+
+using namespace tcu;
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+static int cuda_fail(cudaError_t e, const char *what)
+{
+    // clear the sticky-free error state so the next call starts clean
+    cudaGetLastError();
+    if (e == cudaErrorMemoryAllocation)
+        return fail(TCU_ERR_OOM, "%s: out of device memory", what);
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver)
+        return fail(TCU_ERR_NO_DEVICE, "%s: %s", what, cudaGetErrorString(e));
+    return fail(TCU_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define CK(call)                                                     \
+    do {                                                             \
+        cudaError_t e__ = (call);                                    \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);        \
+    } while (0)
+
+extern "C" const char *tcu_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char *tcu_version(void) { return "trimal_cuda 0.1 (sm_100a)"; }
+
+// ---------------------------------------------------------------------------
+// devices
+// ---------------------------------------------------------------------------
+static bool device_usable(int dev, int *sms)
+{
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    if (sms) *sms = prop.multiProcessorCount;
+    return prop.major == 10;  // the library carries sm_100a code only
+}
+
+extern "C" int tcu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int usable = 0;
+    for (int d = 0; d < n; d++) usable += device_usable(d, nullptr);
+    return usable;
+}
+
+// ---------------------------------------------------------------------------
+// pinned staging pool (process-wide; buffers are reused across handles because
+// cudaHostAlloc costs milliseconds)
+// ---------------------------------------------------------------------------
+namespace {
+constexpr size_t STAGE_BYTES = 16u << 20;
+std::mutex g_pool_mutex;
+std::vector<void *> g_pool;
+
+void *stage_acquire()
+{
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mutex);
+        if (!g_pool.empty()) {
+            void *p = g_pool.back();
+            g_pool.pop_back();
+            return p;
+        }
+    }
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, STAGE_BYTES, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void stage_release(void *p)
+{
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    g_pool.push_back(p);
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------
+struct tcu_msa {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    int nseq = 0, ncol = 0;
+    size_t pitch = 0;
+    uint8_t *d_raw = nullptr;
+
+    // byte presence (mask independent)
+    bool have_present = false;
+    unsigned int present[256];
+
+    // identity operand
+    bool prepared = false;
+    int np = 0, nk = 0, nb = 0, nchunks = 0;
+    uint32_t *d_planes = nullptr;
+    size_t planes_cap = 0;
+    int *d_kept_rows = nullptr;
+    uint8_t *d_col_drop = nullptr;
+    uint8_t *d_lut = nullptr;
+    uint8_t prepared_indet = 0;
+
+    // identities kept on the device
+    float *d_ident = nullptr;
+    size_t ident_cap = 0;
+    bool ident_full = false;  // unmasked rows: usable by tcu_similarity
+
+    // generic scratch
+    void *d_scratch = nullptr;
+    size_t scratch_cap = 0;
+
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    tcu_timings timings{};
+    bool pending_device_timing = false;  // ev[2]..ev[3] bracket an async tcu_identity_device
+};
+
+static int ensure(void **p, size_t *cap, size_t need)
+{
+    if (*cap >= need && *p) return TCU_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    if (need == 0) need = 16;
+    CK(cudaMalloc(p, need));
+    *cap = need;
+    return TCU_OK;
+}
+
+static float ev_ms(cudaEvent_t a, cudaEvent_t b)
+{
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) {
+        cudaGetLastError();
+        return 0.f;
+    }
+    return ms;
+}
+
+static int msa_alloc(int nseq, int ncol, int device, tcu_msa **out)
+{
+    if (!out) return fail(TCU_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (nseq < 0 || ncol < 0) return fail(TCU_ERR_INVALID, "negative alignment shape");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(TCU_ERR_NO_DEVICE, "no CUDA device available (no CPU fallback exists)");
+    }
+    if (device < 0 || device >= ndev) return fail(TCU_ERR_INVALID, "device %d out of range", device);
+    int sms = 0;
+    if (!device_usable(device, &sms))
+        return fail(TCU_ERR_NO_DEVICE, "device %d is not an sm_100 GPU", device);
+    CK(cudaSetDevice(device));
+    tcu_msa *m = new (std::nothrow) tcu_msa();
+    if (!m) return fail(TCU_ERR_OOM, "host allocation failed");
+    m->device = device;
+    m->num_sms = sms;
+    m->nseq = nseq;
+    m->ncol = ncol;
+    m->pitch = ((size_t)ncol + 127) / 128 * 128;
+    if (m->pitch == 0) m->pitch = 128;
+    cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventCreate(&m->ev[i]);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_raw, std::max<size_t>(1, (size_t)nseq) * m->pitch);
+    if (e != cudaSuccess) {
+        tcu_msa_destroy(m);
+        return cuda_fail(e, "tcu_msa_create");
+    }
+    *out = m;
+    return TCU_OK;
+}
+
+// rows -> pinned staging (row pitch = device pitch, padding zero) -> device
+template <typename RowPtr>
+static int upload_rows(tcu_msa *m, RowPtr row_of)
+{
+    CK(cudaSetDevice(m->device));
+    CK(cudaEventRecord(m->ev[0], m->stream));
+    const size_t pitch = m->pitch;
+    const size_t rows_per_stage = std::max<size_t>(1, STAGE_BYTES / pitch);
+    if (pitch > STAGE_BYTES) {
+        // very long rows: copy row by row straight from caller memory
+        CK(cudaMemsetAsync(m->d_raw, 0, (size_t)m->nseq * pitch, m->stream));
+        for (int r = 0; r < m->nseq; r++)
+            CK(cudaMemcpyAsync(m->d_raw + (size_t)r * pitch, row_of(r), m->ncol,
+                               cudaMemcpyHostToDevice, m->stream));
+    } else {
+        void *stage[2] = {stage_acquire(), stage_acquire()};
+        cudaEvent_t done[2] = {m->ev[4], m->ev[5]};
+        bool used[2] = {false, false};
+        if (!stage[0] || !stage[1]) {
+            stage_release(stage[0]);
+            stage_release(stage[1]);
+            return fail(TCU_ERR_OOM, "pinned staging allocation failed");
+        }
+        int which = 0;
+        int rc = TCU_OK;
+        for (size_t r0 = 0; r0 < (size_t)m->nseq && rc == TCU_OK; r0 += rows_per_stage) {
+            const size_t nr = std::min(rows_per_stage, (size_t)m->nseq - r0);
+            uint8_t *s = (uint8_t *)stage[which];
+            if (used[which] && cudaEventSynchronize(done[which]) != cudaSuccess) {
+                rc = cuda_fail(cudaGetLastError(), "staging wait");
+                break;
+            }
+            for (size_t r = 0; r < nr; r++) {
+                memcpy(s + r * pitch, row_of((int)(r0 + r)), m->ncol);
+                if (pitch > (size_t)m->ncol) memset(s + r * pitch + m->ncol, 0, pitch - m->ncol);
+            }
+            cudaError_t e = cudaMemcpyAsync(m->d_raw + r0 * pitch, s, nr * pitch,
+                                            cudaMemcpyHostToDevice, m->stream);
+            if (e == cudaSuccess) e = cudaEventRecord(done[which], m->stream);
+            if (e != cudaSuccess) rc = cuda_fail(e, "row upload");
+            used[which] = true;
+            which ^= 1;
+        }
+        cudaStreamSynchronize(m->stream);
+        stage_release(stage[0]);
+        stage_release(stage[1]);
+        if (rc != TCU_OK) return rc;
+    }
+    CK(cudaEventRecord(m->ev[1], m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    m->timings = tcu_timings{};
+    m->timings.h2d_ms = ev_ms(m->ev[0], m->ev[1]);
+    return TCU_OK;
+}
+
+extern "C" int tcu_msa_create(const char *const *rows, int nseq, int ncol, int device, tcu_msa **out)
+{
+    if (nseq > 0 && !rows) return fail(TCU_ERR_INVALID, "rows is NULL");
+    tcu_msa *m = nullptr;
+    int rc = msa_alloc(nseq, ncol, device, &m);
+    if (rc != TCU_OK) return rc;
+    rc = upload_rows(m, [&](int r) { return (const void *)rows[r]; });
+    if (rc != TCU_OK) {
+        tcu_msa_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return TCU_OK;
+}
+
+extern "C" int tcu_msa_create_strided(const uint8_t *data, int nseq, int ncol, size_t stride,
+                                      int device, tcu_msa **out)
+{
+    if (nseq > 0 && ncol > 0 && !data) return fail(TCU_ERR_INVALID, "data is NULL");
+    if (stride < (size_t)ncol) return fail(TCU_ERR_INVALID, "stride smaller than ncol");
+    tcu_msa *m = nullptr;
+    int rc = msa_alloc(nseq, ncol, device, &m);
+    if (rc != TCU_OK) return rc;
+    rc = upload_rows(m, [&](int r) { return (const void *)(data + (size_t)r * stride); });
+    if (rc != TCU_OK) {
+        tcu_msa_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return TCU_OK;
+}
+
+extern "C" void tcu_msa_destroy(tcu_msa *m)
+{
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    cudaFree(m->d_raw);
+    cudaFree(m->d_planes);
+    cudaFree(m->d_kept_rows);
+    cudaFree(m->d_col_drop);
+    cudaFree(m->d_lut);
+    cudaFree(m->d_ident);
+    cudaFree(m->d_scratch);
+    for (auto &e : m->ev)
+        if (e) cudaEventDestroy(e);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    cudaGetLastError();
+    delete m;
+}
+
+extern "C" int tcu_msa_nseq(const tcu_msa *m) { return m ? m->nseq : 0; }
+extern "C" int tcu_msa_ncol(const tcu_msa *m) { return m ? m->ncol : 0; }
+extern "C" void *tcu_msa_stream(tcu_msa *m) { return m ? (void *)m->stream : nullptr; }
+extern "C" int tcu_msa_device(const tcu_msa *m) { return m ? m->device : -1; }
+
+extern "C" int tcu_msa_sync(tcu_msa *m)
+{
+    if (!m) return fail(TCU_ERR_INVALID, "msa is NULL");
+    CK(cudaSetDevice(m->device));
+    CK(cudaStreamSynchronize(m->stream));
+    if (m->pending_device_timing) {
+        m->timings.pack_ms = ev_ms(m->ev[1], m->ev[2]);
+        m->timings.kernel_ms = ev_ms(m->ev[2], m->ev[3]);
+        m->pending_device_timing = false;
+    }
+    return TCU_OK;
+}
+
+extern "C" int tcu_msa_timings(const tcu_msa *m, tcu_timings *out)
+{
+    if (!m || !out) return fail(TCU_ERR_INVALID, "NULL argument");
+    *out = m->timings;
+    return TCU_OK;
+}
+
+// device -> host copy of a possibly multi-GB result
+static int download(tcu_msa *m, void *dst, const void *d_src, size_t bytes)
+{
+    if (bytes == 0) return TCU_OK;
+    CK(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, m->stream));
+    return TCU_OK;
+}
+
+// ---------------------------------------------------------------------------
+// K3 gaps
+// ---------------------------------------------------------------------------
+extern "C" int tcu_gaps(tcu_msa *m, const int *save_seq, int *gaps_in_column,
+                        int *num_cols_with_gaps, int *max_gaps)
+{
+    if (!m || !gaps_in_column) return fail(TCU_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(m->device));
+    m->timings = tcu_timings{};
+    const int n = m->nseq, L = m->ncol;
+    if (L == 0) return TCU_OK;
+    const size_t cnt_bytes = ((size_t)L * sizeof(int) + 255) / 256 * 256;
+    int rc = ensure(&m->d_scratch, &m->scratch_cap, cnt_bytes + (size_t)n + 256);
+    if (rc != TCU_OK) return rc;
+    int *d_cnt = (int *)m->d_scratch;
+    uint8_t *d_drop = nullptr;
+    CK(cudaEventRecord(m->ev[0], m->stream));
+    std::vector<uint8_t> drop;
+    if (save_seq) {
+        drop.resize(n);
+        for (int i = 0; i < n; i++) drop[i] = save_seq[i] == -1;
+        d_drop = (uint8_t *)m->d_scratch + cnt_bytes;
+        CK(cudaMemcpyAsync(d_drop, drop.data(), n, cudaMemcpyHostToDevice, m->stream));
+    }
+    CK(cudaMemsetAsync(d_cnt, 0, (size_t)L * sizeof(int), m->stream));
+    CK(cudaEventRecord(m->ev[1], m->stream));
+    CK(launch_column_counts(m->d_raw, n, L, m->pitch, d_drop, '-', '-', d_cnt, nullptr,
+                            m->num_sms, m->stream));
+    CK(cudaEventRecord(m->ev[2], m->stream));
+    CK(cudaMemcpyAsync(gaps_in_column, d_cnt, (size_t)L * sizeof(int), cudaMemcpyDeviceToHost,
+                       m->stream));
+    CK(cudaEventRecord(m->ev[3], m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    m->timings.h2d_ms = ev_ms(m->ev[0], m->ev[1]);
+    m->timings.kernel_ms = ev_ms(m->ev[1], m->ev[2]);
+    m->timings.d2h_ms = ev_ms(m->ev[2], m->ev[3]);
+    m->timings.kernel_launches = n > 0 ? 1 : 0;
+    // histogram and maximum (template.h:496-501)
+    for (int k = 0; k < L; k++) {
+        if (num_cols_with_gaps) num_cols_with_gaps[gaps_in_column[k]]++;
+        if (max_gaps && gaps_in_column[k] > *max_gaps) *max_gaps = gaps_in_column[k];
+    }
+    return TCU_OK;
+}
+
+// ---------------------------------------------------------------------------
+// K0 + K1 identity
+// ---------------------------------------------------------------------------
+extern "C" int tcu_identity_row_blocks(int kept_rows) { return (kept_rows + RB - 1) / RB; }
+
+extern "C" size_t tcu_identity_row_offset(int kept_rows, int i)
+{
+    const size_t n = (size_t)std::max(kept_rows, 0);
+    size_t r = (size_t)std::max(i, 0);
+    if (n < 2) return 0;
+    if (r > n - 1) r = n - 1;
+    return r * n - r * (r + 1) / 2;
+}
+
+static long long tiles_before(int b, int nb) { return (long long)b * nb - (long long)b * (b - 1) / 2; }
+
+extern "C" int tcu_identity_prepare(tcu_msa *m, const int *save_seq, const int *save_res,
+                                    uint8_t indet, int *kept_rows_out)
+{
+    if (!m) return fail(TCU_ERR_INVALID, "msa is NULL");
+    CK(cudaSetDevice(m->device));
+    m->prepared = false;
+    const int n = m->nseq, L = m->ncol;
+
+    std::vector<int> kept;
+    kept.reserve(n);
+    for (int i = 0; i < n; i++)
+        if (!save_seq || save_seq[i] != -1) kept.push_back(i);
+    std::vector<uint8_t> drop((size_t)std::max(L, 1), 0);
+    if (save_res)
+        for (int k = 0; k < L; k++) drop[k] = save_res[k] == -1;
+
+    CK(cudaEventRecord(m->ev[0], m->stream));
+    if (!m->have_present) {
+        unsigned int *d_present = nullptr;
+        int rc = ensure(&m->d_scratch, &m->scratch_cap, 256 * sizeof(unsigned int));
+        if (rc != TCU_OK) return rc;
+        d_present = (unsigned int *)m->d_scratch;
+        CK(cudaMemsetAsync(d_present, 0, 256 * sizeof(unsigned int), m->stream));
+        CK(launch_byte_presence(m->d_raw, n, L, m->pitch, d_present, m->stream));
+        CK(cudaMemcpyAsync(m->present, d_present, sizeof m->present, cudaMemcpyDeviceToHost,
+                           m->stream));
+        CK(cudaStreamSynchronize(m->stream));
+        m->have_present = true;
+        m->timings.kernel_launches++;
+    }
+
+    // dense residue codes for the bytes that occur; the gap class shares one code
+    uint8_t lut[256];
+    int count = 0;
+    for (int b = 0; b < 256; b++) {
+        if (b == '-' || b == indet) lut[b] = CODE_GAP;
+        else if (m->present[b]) lut[b] = (uint8_t)std::min(count++, 254);
+        else lut[b] = 0;
+    }
+    int np = MIN_PLANES;
+    while (np <= MAX_PLANES && (1 << np) - 2 < count) np++;
+    if (np > MAX_PLANES)
+        return fail(TCU_ERR_INVALID, "alignment uses %d distinct symbols (max %d)", count,
+                    (1 << MAX_PLANES) - 2);
+
+    m->np = np;
+    m->nk = (int)kept.size();
+    m->nb = (m->nk + RB - 1) / RB;
+    m->nchunks = (L + KC * 32 - 1) / (KC * 32);
+    m->prepared_indet = indet;
+
+    if (!m->d_lut) CK(cudaMalloc((void **)&m->d_lut, 256));
+    if (!m->d_kept_rows) CK(cudaMalloc((void **)&m->d_kept_rows, std::max<size_t>(1, (size_t)n) * sizeof(int)));
+    if (!m->d_col_drop) CK(cudaMalloc((void **)&m->d_col_drop, m->pitch));
+    CK(cudaMemcpyAsync(m->d_lut, lut, 256, cudaMemcpyHostToDevice, m->stream));
+    if (m->nk)
+        CK(cudaMemcpyAsync(m->d_kept_rows, kept.data(), (size_t)m->nk * sizeof(int),
+                           cudaMemcpyHostToDevice, m->stream));
+    if (L) CK(cudaMemcpyAsync(m->d_col_drop, drop.data(), L, cudaMemcpyHostToDevice, m->stream));
+    CK(cudaStreamSynchronize(m->stream));  // the host vectors go out of scope
+
+    const size_t need = (size_t)m->nb * m->nchunks * tile_bytes(np);
+    int rc = ensure((void **)&m->d_planes, &m->planes_cap, need);
+    if (rc != TCU_OK) return rc;
+    CK(cudaEventRecord(m->ev[1], m->stream));
+    CK(launch_pack_planes(m->d_raw, m->pitch, L, m->d_kept_rows, m->nk, m->d_col_drop, m->d_lut, np,
+                          m->nb, m->nchunks, m->d_planes, m->stream));
+    CK(cudaEventRecord(m->ev[2], m->stream));
+    if (m->nb && m->nchunks) m->timings.kernel_launches++;
+    m->prepared = true;
+    if (kept_rows_out) *kept_rows_out = m->nk;
+    return TCU_OK;
+}
+
+static int identity_launch(tcu_msa *m, int block_begin, int block_end, float *d_out, int *d_hit,
+                           int *d_dst)
+{
+    IdentityParams p{};
+    p.planes = m->d_planes;
+    p.out = d_out;
+    p.hit_out = d_hit;
+    p.dst_out = d_dst;
+    p.nb = m->nb;
+    p.nchunks = m->nchunks;
+    p.nk = m->nk;
+    p.total_bits = m->nchunks * KC * 32;
+    p.tile_begin = tiles_before(block_begin, m->nb);
+    p.tile_end = tiles_before(block_end, m->nb);
+    p.out_base = tcu_identity_row_offset(m->nk, block_begin * RB);
+    if (p.tile_end <= p.tile_begin || m->nchunks == 0) return TCU_OK;
+    CK(launch_identity(m->np, p, m->num_sms, m->stream));
+    m->timings.kernel_launches++;
+    return TCU_OK;
+}
+
+extern "C" int tcu_identity_device(tcu_msa *m, int block_begin, int block_end, float *d_out)
+{
+    if (!m || !d_out) return fail(TCU_ERR_INVALID, "NULL argument");
+    if (!m->prepared) return fail(TCU_ERR_STATE, "tcu_identity_prepare has not been called");
+    if (block_begin < 0 || block_end > m->nb || block_begin > block_end)
+        return fail(TCU_ERR_INVALID, "row-block range [%d,%d) outside [0,%d)", block_begin,
+                    block_end, m->nb);
+    CK(cudaSetDevice(m->device));
+    m->timings.kernel_launches = 0;
+    int rc = identity_launch(m, block_begin, block_end, d_out, nullptr, nullptr);
+    if (rc != TCU_OK) return rc;
+    CK(cudaEventRecord(m->ev[3], m->stream));
+    m->pending_device_timing = true;
+    return TCU_OK;
+}
+
+// Host-facing band variant: row-blocks [block_begin, block_end) of the packed
+// array into a host slice whose element 0 is packed offset
+// tcu_identity_row_offset(kept, 64*block_begin).  block_end < 0 = all blocks.
+extern "C" int tcu_identity_band(tcu_msa *m, const int *save_seq, const int *save_res,
+                                 uint8_t indet, int block_begin, int block_end, float *identities)
+{
+    if (!m || !identities) return fail(TCU_ERR_INVALID, "NULL argument");
+    m->timings = tcu_timings{};
+    m->ident_full = false;
+    int rc = tcu_identity_prepare(m, save_seq, save_res, indet, nullptr);
+    if (rc != TCU_OK) return rc;
+    if (block_end < 0) block_end = m->nb;
+    if (block_begin < 0 || block_end > m->nb || block_begin > block_end)
+        return fail(TCU_ERR_INVALID, "row-block range [%d,%d) outside [0,%d)", block_begin,
+                    block_end, m->nb);
+    const size_t lo = tcu_identity_row_offset(m->nk, block_begin * RB);
+    const size_t hi = tcu_identity_row_offset(m->nk, std::min(block_end * RB, m->nk));
+    const size_t count = hi - lo;
+    if (count == 0) {
+        CK(cudaStreamSynchronize(m->stream));
+        return TCU_OK;
+    }
+    rc = ensure((void **)&m->d_ident, &m->ident_cap, count * sizeof(float));
+    if (rc != TCU_OK) return rc;
+    rc = identity_launch(m, block_begin, block_end, m->d_ident, nullptr, nullptr);
+    if (rc != TCU_OK) return rc;
+    CK(cudaEventRecord(m->ev[3], m->stream));
+    rc = download(m, identities, m->d_ident, count * sizeof(float));
+    if (rc != TCU_OK) return rc;
+    CK(cudaEventRecord(m->ev[4], m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    m->timings.h2d_ms = ev_ms(m->ev[0], m->ev[1]);
+    m->timings.pack_ms = ev_ms(m->ev[1], m->ev[2]);
+    m->timings.kernel_ms = ev_ms(m->ev[2], m->ev[3]);
+    m->timings.d2h_ms = ev_ms(m->ev[3], m->ev[4]);
+    return TCU_OK;
+}
+
+static int identity_host(tcu_msa *m, const int *save_seq, const int *save_res, uint8_t indet,
+                         float *identities, int *hit_out, int *dst_out, int keep_on_device,
+                         bool bytes_kernel)
+{
+    if (!m) return fail(TCU_ERR_INVALID, "msa is NULL");
+    if (!identities && !keep_on_device)
+        return fail(TCU_ERR_INVALID, "identities is NULL and keep_on_device is 0");
+    m->timings = tcu_timings{};
+    m->ident_full = false;
+    int rc = tcu_identity_prepare(m, save_seq, save_res, indet, nullptr);
+    if (rc != TCU_OK) return rc;
+    const size_t npairs = (size_t)m->nk * (size_t)std::max(m->nk - 1, 0) / 2;
+    if (npairs == 0) {
+        CK(cudaStreamSynchronize(m->stream));
+        return TCU_OK;
+    }
+    rc = ensure((void **)&m->d_ident, &m->ident_cap, npairs * sizeof(float));
+    if (rc != TCU_OK) return rc;
+    int *d_hit = nullptr, *d_dst = nullptr;
+    if (hit_out || dst_out) {
+        // the kernel writes both or neither
+        rc = ensure(&m->d_scratch, &m->scratch_cap, 2 * npairs * sizeof(int));
+        if (rc != TCU_OK) return rc;
+        d_hit = (int *)m->d_scratch;
+        d_dst = d_hit + npairs;
+    }
+    if (bytes_kernel) {
+        CK(launch_identity_bytes(m->d_raw, m->pitch, m->ncol, m->d_kept_rows, m->nk, m->d_col_drop,
+                                 indet, m->d_ident, d_hit, d_dst, m->stream));
+        m->timings.kernel_launches++;
+    } else {
+        rc = identity_launch(m, 0, m->nb, m->d_ident, d_hit, d_dst);
+        if (rc != TCU_OK) return rc;
+    }
+    CK(cudaEventRecord(m->ev[3], m->stream));
+    if (identities) rc = download(m, identities, m->d_ident, npairs * sizeof(float));
+    if (rc == TCU_OK && hit_out) rc = download(m, hit_out, d_hit, npairs * sizeof(int));
+    if (rc == TCU_OK && dst_out) rc = download(m, dst_out, d_dst, npairs * sizeof(int));
+    if (rc != TCU_OK) return rc;
+    CK(cudaEventRecord(m->ev[4], m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    m->timings.h2d_ms = ev_ms(m->ev[0], m->ev[1]);
+    m->timings.pack_ms = ev_ms(m->ev[1], m->ev[2]);
+    m->timings.kernel_ms = ev_ms(m->ev[2], m->ev[3]);
+    m->timings.d2h_ms = ev_ms(m->ev[3], m->ev[4]);
+    m->ident_full = (m->nk == m->nseq);
+    if (!keep_on_device) {
+        cudaFree(m->d_ident);
+        m->d_ident = nullptr;
+        m->ident_cap = 0;
+        m->ident_full = false;
+    }
+    return TCU_OK;
+}
+
+extern "C" int tcu_identity(tcu_msa *m, const int *save_seq, const int *save_res, uint8_t indet,
+                            float *identities, int *hit_out, int *dst_out, int keep_on_device)
+{
+    return identity_host(m, save_seq, save_res, indet, identities, hit_out, dst_out,
+                         keep_on_device, false);
+}
+
+// test-only: same contract as tcu_identity, computed by the byte-wise kernel
+extern "C" int tcu_debug_identity_bytes(tcu_msa *m, const int *save_seq, const int *save_res,
+                                        uint8_t indet, float *identities, int *hit_out,
+                                        int *dst_out)
+{
+    return identity_host(m, save_seq, save_res, indet, identities, hit_out, dst_out, 0, true);
+}
+
+// ---------------------------------------------------------------------------
+// K2 spurious
+// ---------------------------------------------------------------------------
+extern "C" int tcu_spurious(tcu_msa *m, uint8_t indet, uint32_t ovrlap, float *spurious)
+{
+    if (!m || !spurious) return fail(TCU_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(m->device));
+    m->timings = tcu_timings{};
+    const int n = m->nseq, L = m->ncol;
+    if (n == 0) return TCU_OK;
+    if (L == 0) {
+        // 0/0 in the reference's final division (template.h:309)
+        for (int i = 0; i < n; i++) spurious[i] = NAN;
+        return TCU_OK;
+    }
+    const size_t cnt_bytes = ((size_t)L * sizeof(int) + 255) / 256 * 256;
+    const size_t out_bytes = ((size_t)n * sizeof(float) + 255) / 256 * 256;
+    int rc = ensure(&m->d_scratch, &m->scratch_cap, 2 * cnt_bytes + out_bytes + m->pitch);
+    if (rc != TCU_OK) return rc;
+    int *d_cg = (int *)m->d_scratch;
+    int *d_cx = (int *)((uint8_t *)m->d_scratch + cnt_bytes);
+    float *d_out = (float *)((uint8_t *)m->d_scratch + 2 * cnt_bytes);
+    uint8_t *d_flags = (uint8_t *)m->d_scratch + 2 * cnt_bytes + out_bytes;
+    CK(cudaMemsetAsync(d_cg, 0, 2 * cnt_bytes, m->stream));
+    CK(cudaMemsetAsync(d_flags, 0, m->pitch, m->stream));
+    CK(cudaEventRecord(m->ev[1], m->stream));
+    CK(launch_column_counts(m->d_raw, n, L, m->pitch, nullptr, '-', indet, d_cg, d_cx, m->num_sms,
+                            m->stream));
+    CK(launch_spurious_rows(m->d_raw, n, L, m->pitch, indet, d_cg, d_cx, ovrlap, d_flags, d_out,
+                            m->stream));
+    CK(cudaEventRecord(m->ev[2], m->stream));
+    CK(cudaMemcpyAsync(spurious, d_out, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost,
+                       m->stream));
+    CK(cudaEventRecord(m->ev[3], m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    m->timings.kernel_ms = ev_ms(m->ev[1], m->ev[2]);
+    m->timings.d2h_ms = ev_ms(m->ev[2], m->ev[3]);
+    m->timings.kernel_launches = 3;
+    return TCU_OK;
+}
+
+// ---------------------------------------------------------------------------
+// K4 similarity
+// ---------------------------------------------------------------------------
+extern "C" int tcu_similarity(tcu_msa *m, uint8_t indet, const float *dist, int npos,
+                              const int *vhash, const int *gaps, float gap_threshold,
+                              const float *identities, float *num, float *den, float *mdk,
+                              int *err_col, int *err_row, int *err_byte)
+{
+    if (!m || !dist || !vhash || !num || !den) return fail(TCU_ERR_INVALID, "NULL argument");
+    if (npos < 1 || npos > SIM_MAX_POS)
+        return fail(TCU_ERR_INVALID, "similarity matrix order %d outside [1,%d]", npos, SIM_MAX_POS);
+    CK(cudaSetDevice(m->device));
+    const int n = m->nseq, L = m->ncol;
+    const size_t npairs = (size_t)n * (size_t)std::max(n - 1, 0) / 2;
+    tcu_timings t{};
+    if (L == 0) return TCU_OK;
+
+    if (identities) {
+        int rc = ensure((void **)&m->d_ident, &m->ident_cap, std::max<size_t>(npairs, 1) * sizeof(float));
+        if (rc != TCU_OK) return rc;
+        CK(cudaMemcpyAsync(m->d_ident, identities, npairs * sizeof(float), cudaMemcpyHostToDevice,
+                           m->stream));
+        m->ident_full = true;
+    } else if (npairs && (!m->d_ident || !m->ident_full)) {
+        return fail(TCU_ERR_STATE,
+                    "tcu_similarity needs the identities of the unmasked alignment: call "
+                    "tcu_identity(..., keep_on_device=1) first or pass them");
+    }
+
+    // byte -> code table (template.h:130-147) and skipped columns (:122-125)
+    uint8_t lut[256];
+    for (int b = 0; b < 256; b++) {
+        int up = (b >= 'a' && b <= 'z') ? b - 32 : b;
+        if (up == indet || up == '-') lut[b] = SIM_GAP;
+        else if (up < 'A' || up > 'Z') lut[b] = SIM_INCORRECT;
+        else if (vhash[up - 'A'] < 0 || vhash[up - 'A'] >= npos) lut[b] = SIM_UNDEFINED;
+        else lut[b] = (uint8_t)vhash[up - 'A'];
+    }
+    std::vector<uint8_t> skip((size_t)m->pitch, 0);
+    if (gaps)
+        for (int k = 0; k < L; k++) skip[k] = (float)gaps[k] >= gap_threshold;
+
+    const size_t codes_bytes = (size_t)n * m->pitch;
+    const size_t vec_bytes = ((size_t)L * sizeof(float) + 255) / 256 * 256;
+    const size_t dist_bytes = 4096;
+    const size_t need = codes_bytes + 2 * vec_bytes + dist_bytes + m->pitch + 256 + 64;
+    int rc = ensure(&m->d_scratch, &m->scratch_cap, need);
+    if (rc != TCU_OK) return rc;
+    uint8_t *base = (uint8_t *)m->d_scratch;
+    float *d_num = (float *)base;
+    float *d_den = (float *)(base + vec_bytes);
+    float *d_dist = (float *)(base + 2 * vec_bytes);
+    uint8_t *d_skip = base + 2 * vec_bytes + dist_bytes;
+    uint8_t *d_lut = d_skip + m->pitch;
+    unsigned long long *d_err = (unsigned long long *)(d_lut + 256);
+    uint8_t *d_codes = (uint8_t *)(d_err + 8);
+
+    const unsigned long long no_err = ~0ull;
+    unsigned long long first_err = no_err;
+    CK(cudaEventRecord(m->ev[0], m->stream));
+    CK(cudaMemsetAsync(d_num, 0, 2 * vec_bytes, m->stream));
+    CK(cudaMemcpyAsync(d_dist, dist, (size_t)npos * npos * sizeof(float), cudaMemcpyHostToDevice,
+                       m->stream));
+    CK(cudaMemcpyAsync(d_skip, skip.data(), m->pitch, cudaMemcpyHostToDevice, m->stream));
+    CK(cudaMemcpyAsync(d_lut, lut, 256, cudaMemcpyHostToDevice, m->stream));
+    CK(cudaMemcpyAsync(d_err, &no_err, sizeof no_err, cudaMemcpyHostToDevice, m->stream));
+    CK(cudaEventRecord(m->ev[1], m->stream));
+    CK(launch_sim_codes(m->d_raw, n, L, m->pitch, d_lut, d_skip, d_codes, d_err, m->stream));
+    CK(cudaEventRecord(m->ev[2], m->stream));
+    CK(cudaMemcpyAsync(&first_err, d_err, sizeof first_err, cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    t.h2d_ms = ev_ms(m->ev[0], m->ev[1]);
+    t.pack_ms = ev_ms(m->ev[1], m->ev[2]);
+    t.kernel_launches = n > 0 ? 1 : 0;
+    if (first_err != no_err) {
+        const int byte = (int)(first_err & 0xFF);
+        const unsigned long long cell = first_err >> 8;
+        const int col = (int)(cell / (unsigned long long)n), row = (int)(cell % (unsigned long long)n);
+        if (err_col) *err_col = col;
+        if (err_row) *err_row = row;
+        if (err_byte) *err_byte = byte;
+        m->timings = t;
+        const bool incorrect = byte < 'A' || byte > 'Z';
+        return fail(incorrect ? TCU_ERR_INCORRECT_SYMBOL : TCU_ERR_UNDEFINED_SYMBOL,
+                    "symbol '%c' at column %d, row %d cannot be scored", byte, col, row);
+    }
+
+    CK(cudaEventRecord(m->ev[2], m->stream));
+    CK(launch_similarity(d_codes, n, L, m->pitch, m->d_ident, d_dist, npos, d_skip, d_num, d_den,
+                         m->num_sms, m->stream));
+    CK(cudaEventRecord(m->ev[3], m->stream));
+    CK(cudaMemcpyAsync(num, d_num, (size_t)L * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaMemcpyAsync(den, d_den, (size_t)L * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaEventRecord(m->ev[4], m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    t.kernel_ms = ev_ms(m->ev[2], m->ev[3]);
+    t.d2h_ms = ev_ms(m->ev[3], m->ev[4]);
+    t.kernel_launches += n > 0 ? 1 : 0;
+    m->timings = t;
+
+    if (mdk) {
+        // template.h:186-200, glibc expf on the host so the last bit matches
+        for (int k = 0; k < L; k++) {
+            if (den[k] == 0) mdk[k] = 0.0f;
+            else {
+                const float q = num[k] / den[k];
+                mdk[k] = q < 0 ? 1.0f : expf(-q);
+            }
+        }
+    }
+    return TCU_OK;
+}

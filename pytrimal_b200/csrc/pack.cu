@@ -1,0 +1,141 @@
+// pack.cu -- K0: turn the raw byte matrix into the packed identity operand.
+//
+// The reference kernels read std::string rows directly (template.h:352-361);
+// there is no packing step to mirror.  Layout: see tcu_internal.cuh.
+#include <algorithm>
+
+#include "tcu_internal.cuh"
+
+namespace tcu {
+
+// ---------------------------------------------------------------------------
+// Which of the 256 byte values occur in columns [0, ncol)?  One pass over the
+// matrix, 16 bytes per thread per row, flags collected in shared memory.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_byte_presence(const uint8_t *__restrict__ raw, int nseq,
+                                                       int ncol, size_t pitch,
+                                                       unsigned int *__restrict__ present256)
+{
+    __shared__ unsigned int flags[256];
+    flags[threadIdx.x] = 0;
+    __syncthreads();
+
+    const int groups = (ncol + 15) >> 4;  // 16-byte groups per row
+    const long long total = (long long)nseq * groups;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(idx / groups);
+        const int g = (int)(idx - (long long)r * groups);
+        const uint4 v = *reinterpret_cast<const uint4 *>(raw + (size_t)r * pitch + (size_t)g * 16);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        const int valid = min(16, ncol - g * 16);
+#pragma unroll
+        for (int b = 0; b < 16; b++)
+            if (b < valid) flags[(w[b >> 2] >> ((b & 3) * 8)) & 0xFF] = 1;
+    }
+    __syncthreads();
+    if (flags[threadIdx.x]) present256[threadIdx.x] = 1;
+}
+
+cudaError_t launch_byte_presence(const uint8_t *raw, int nseq, int ncol, size_t pitch,
+                                 unsigned int *present256, cudaStream_t stream)
+{
+    if (nseq == 0 || ncol == 0) return cudaSuccess;
+    const long long total = (long long)nseq * ((ncol + 15) >> 4);
+    int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+    k_byte_presence<<<blocks, 256, 0, stream>>>(raw, nseq, ncol, pitch, present256);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// One CTA per (chunk, row-block) tile.  A warp takes one (row, 32-column word)
+// at a time: each lane maps one byte through the code LUT and the W plane
+// words are formed with warp ballots, so the 32 bytes are read coalesced and
+// no thread ever shifts bits one by one.
+// ---------------------------------------------------------------------------
+template <int NP>
+__global__ void __launch_bounds__(256) k_pack_planes(const uint8_t *__restrict__ raw, size_t pitch,
+                                                     int ncol, const int *__restrict__ kept_rows,
+                                                     int nk, const uint8_t *__restrict__ col_drop,
+                                                     const uint8_t *__restrict__ lut256,
+                                                     int nchunks, uint32_t *__restrict__ planes)
+{
+    constexpr int W = NP + 1;
+    constexpr int G1 = group1_words(NP);
+    constexpr int WS = words_stored(NP);
+    constexpr int TW = tile_words(NP);
+    constexpr uint32_t GAP_BITS = (1u << NP) - 2u;  // p0 = 0, p1.. = 1
+
+    __shared__ __align__(16) uint32_t tile[TW];
+    __shared__ uint8_t lut[256];
+
+    const int chunk = blockIdx.x;
+    const int block = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    lut[threadIdx.x] = lut256[threadIdx.x];
+    if (G1 + 4 > W) {  // the padding word of group 1 must be defined
+        for (int i = threadIdx.x; i < TW; i += 256) tile[i] = 0;
+    }
+    __syncthreads();
+
+    for (int r = warp; r < RB; r += 8) {
+        const int ki = block * RB + r;
+        const bool row_ok = ki < nk;
+        const uint8_t *src = row_ok ? raw + (size_t)kept_rows[ki] * pitch : nullptr;
+#pragma unroll 2
+        for (int kw = 0; kw < KC; kw++) {
+            const int col = (chunk * KC + kw) * 32 + lane;
+            uint32_t code = GAP_BITS;
+            uint32_t gap = 1;
+            if (row_ok && col < ncol && !col_drop[col]) {
+                const uint8_t c = lut[src[col]];
+                if (c != CODE_GAP) {
+                    code = c;
+                    gap = 0;
+                }
+            }
+            uint32_t mine = __ballot_sync(0xffffffffu, gap);
+#pragma unroll
+            for (int p = 0; p < NP; p++) {
+                const uint32_t w = __ballot_sync(0xffffffffu, (code >> p) & 1u);
+                if (lane == p + 1) mine = w;
+            }
+            if (lane < W) {
+                const int base = kw * RB * WS;
+                const int off = lane < 4 ? base + r * 4 + lane : base + RB * 4 + r * G1 + (lane - 4);
+                tile[off] = mine;
+            }
+        }
+    }
+    __syncthreads();
+
+    uint4 *dst = reinterpret_cast<uint4 *>(planes + ((size_t)block * nchunks + chunk) * TW);
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(tile);
+    for (int i = threadIdx.x; i < TW / 4; i += 256) dst[i] = s4[i];
+}
+
+cudaError_t launch_pack_planes(const uint8_t *raw, size_t pitch, int ncol, const int *kept_rows,
+                               int nk, const uint8_t *col_drop, const uint8_t *lut256, int np,
+                               int nb, int nchunks, uint32_t *planes, cudaStream_t stream)
+{
+    if (nb == 0 || nchunks == 0) return cudaSuccess;
+    dim3 grid(nchunks, nb);
+#define TCU_PACK_CASE(N)                                                                         \
+    case N:                                                                                      \
+        k_pack_planes<N><<<grid, 256, 0, stream>>>(raw, pitch, ncol, kept_rows, nk, col_drop,    \
+                                                   lut256, nchunks, planes);                     \
+        break;
+    switch (np) {
+        TCU_PACK_CASE(3)
+        TCU_PACK_CASE(4)
+        TCU_PACK_CASE(5)
+        TCU_PACK_CASE(6)
+        TCU_PACK_CASE(7)
+    default: return cudaErrorInvalidValue;
+    }
+#undef TCU_PACK_CASE
+    return cudaGetLastError();
+}
+
+}  // namespace tcu

@@ -1,0 +1,148 @@
+// tcu_internal.cuh -- shared declarations of libtrimal_cuda (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "trimal_cuda.h"
+
+namespace tcu {
+
+// ---------------------------------------------------------------------------
+// Packed layout of the identity operand ("bit-planes")
+//
+// The kept rows are renumbered 0..nk-1 and grouped into row-blocks of RB rows;
+// the columns are grouped into words of 32 and the words into chunks of KC.
+// One (row-block, chunk) TILE is stored contiguously so that a single 1-D
+// bulk async copy (cp.async.bulk, TMA unit) brings it into shared memory:
+//
+//     tile[kw][group][row][word]      kw < KC, row < RB
+//
+// For every (row, 32-column word) there are W = NP+1 words: word 0 is the
+// identity-gap mask g ('-' or indet, masked-out and padding columns, padding
+// rows); words 1..NP are the bits of a dense residue code (bit p of the code
+// of column c sits at bit c%32 of word 1+p).  Gap-class positions carry the
+// code 2^NP-2, residues use codes < 2^NP-2, so in the kernel
+//     differ = (a.p0 ^ (b.p0 | b.g)) | (a.p1 ^ b.p1) | ...
+// is 1 wherever either side is a gap or the bytes differ -- hits need no
+// separate gap test.  Words are split into group 0 (g,p0,p1,p2: one 16-byte
+// shared load) and group 1 (the rest, padded to 1, 2 or 4 words).
+// Tiles are ordered block-major: tile(b, c) at ((b * nchunks) + c) * TILE_BYTES.
+// ---------------------------------------------------------------------------
+constexpr int RB = 64;  // rows per row-block
+constexpr int KC = 8;   // 32-column words per chunk (256 columns)
+
+__host__ __device__ constexpr int group1_words(int np) { return np + 1 - 4 == 3 ? 4 : np + 1 - 4; }
+__host__ __device__ constexpr int words_stored(int np) { return 4 + group1_words(np); }
+__host__ __device__ constexpr int tile_words(int np) { return KC * RB * words_stored(np); }
+__host__ __device__ constexpr int tile_bytes(int np) { return tile_words(np) * 4; }
+
+constexpr int MIN_PLANES = 3;
+constexpr int MAX_PLANES = 7;
+constexpr uint8_t CODE_GAP = 0xFF;  // LUT value for the identity gap class
+
+// similarity codes (per byte, after upper-casing)
+constexpr uint8_t SIM_GAP = 0xFF;
+constexpr uint8_t SIM_INCORRECT = 0xFE;
+constexpr uint8_t SIM_UNDEFINED = 0xFD;
+constexpr int SIM_MAX_POS = 28;
+
+struct IdentityParams {
+    const uint32_t *planes;  // packed tiles
+    float *out;              // identities, element 0 = packed offset out_base
+    int *hit_out;            // optional, absolute packed offsets
+    int *dst_out;            // optional
+    unsigned long long out_base;
+    long long tile_begin;    // linear upper-triangular tile range [begin, end)
+    long long tile_end;
+    int nb;                  // number of row-blocks
+    int nchunks;             // chunks per row-block
+    int nk;                  // kept rows
+    int total_bits;          // nchunks * KC * 32
+};
+
+// launchers (each enqueues on `stream` and returns the launch status)
+cudaError_t launch_byte_presence(const uint8_t *raw, int nseq, int ncol, size_t pitch,
+                                 unsigned int *present256, cudaStream_t stream);
+cudaError_t launch_pack_planes(const uint8_t *raw, size_t pitch, int ncol, const int *kept_rows,
+                               int nk, const uint8_t *col_drop, const uint8_t *lut256, int np,
+                               int nb, int nchunks, uint32_t *planes, cudaStream_t stream);
+cudaError_t launch_identity(int np, const IdentityParams &p, int num_sms, cudaStream_t stream);
+cudaError_t launch_identity_bytes(const uint8_t *raw, size_t pitch, int ncol, const int *kept_rows,
+                                  int nk, const uint8_t *col_drop, uint8_t indet, float *out,
+                                  int *hit_out, int *dst_out, cudaStream_t stream);
+cudaError_t launch_column_counts(const uint8_t *raw, int nseq, int ncol, size_t pitch,
+                                 const uint8_t *row_drop, uint8_t sym_a, uint8_t sym_b,
+                                 int *count_a, int *count_b, int num_sms, cudaStream_t stream);
+cudaError_t launch_spurious_rows(const uint8_t *raw, int nseq, int ncol, size_t pitch,
+                                 uint8_t indet, const int *cnt_gap, const int *cnt_indet,
+                                 uint32_t ovrlap, uint8_t *col_flags, float *out,
+                                 cudaStream_t stream);
+cudaError_t launch_sim_codes(const uint8_t *raw, int nseq, int ncol, size_t pitch,
+                             const uint8_t *lut256, const uint8_t *col_skip, uint8_t *codes,
+                             unsigned long long *first_error, cudaStream_t stream);
+cudaError_t launch_similarity(const uint8_t *codes, int nseq, int ncol, size_t pitch,
+                              const float *identities, const float *dist, int npos,
+                              const uint8_t *col_skip, float *num, float *den, int num_sms,
+                              cudaStream_t stream);
+
+// ---------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D bulk async copy (TMA unit, SASS: UBLKCP)
+// ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "TCU_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra TCU_DONE;\n"
+        "bra TCU_WAIT;\n"
+        "TCU_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes,
+                                              uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return d;
+}
+#endif
+
+}  // namespace tcu

@@ -1,0 +1,193 @@
+"""The four per-alignment statistics, computed on a B200 through the C ABI.
+
+Host mirror of ``statistics::Manager`` for the CUDA platform
+(vendor/trimal/source/Statistics/Manager.cpp:61-114, 228-370): lazy, cached
+gap / identity / similarity / overlap statistics of one alignment, with the
+non-kernel parts the reference's base classes keep on the host (gap and
+similarity windows, Gaps.cpp:93-153, Similarity.cpp:212-269).
+
+Every number comes from libtrimal_cuda.so; nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from .alignment import Alignment
+from .matrix import SimilarityMatrix
+
+_i32p = C.POINTER(C.c_int)
+_f32p = C.POINTER(C.c_float)
+
+
+def _p(a, ty):
+    return None if a is None else a.ctypes.data_as(ty)
+
+
+def _mask(m, n):
+    if m is None:
+        return None
+    m = np.ascontiguousarray(m, np.int32)
+    if m.shape != (n,):
+        raise ValueError("keep-mask has the wrong length")
+    return m
+
+
+class DeviceAlignment:
+    """One alignment uploaded to one GPU (wraps a ``tcu_msa`` handle)."""
+
+    def __init__(self, alignment, device=0):
+        if not isinstance(alignment, Alignment):
+            alignment = Alignment.from_matrix(np.asarray(alignment, np.uint8))
+        self.alignment = alignment
+        self.lib = _lib.load()
+        m = np.ascontiguousarray(alignment.matrix)
+        self._h = C.c_void_p()
+        _lib.check(self.lib.tcu_msa_create_strided(
+            m.ctypes.data_as(C.c_void_p), m.shape[0], m.shape[1],
+            m.strides[0] if m.shape[0] else max(m.shape[1], 1), device, C.byref(self._h)))
+        self.nseq, self.ncol = m.shape
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.tcu_msa_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def timings(self):
+        t = _lib.Timings()
+        _lib.check(self.lib.tcu_msa_timings(self._h, C.byref(t)))
+        return {"h2d_ms": t.h2d_ms, "pack_ms": t.pack_ms, "kernel_ms": t.kernel_ms,
+                "d2h_ms": t.d2h_ms, "kernel_launches": t.kernel_launches}
+
+    # -- K3 -------------------------------------------------------------------
+    def gaps(self, save_seq=None):
+        """(gapsInColumn, numColumnsWithGaps, maxGaps) -- template.h:444-502."""
+        ss = _mask(save_seq, self.nseq)
+        g = np.zeros(self.ncol, np.int32)
+        hist = np.zeros(self.nseq + 1, np.int32)
+        mx = C.c_int(0)
+        _lib.check(self.lib.tcu_gaps(self._h, _p(ss, _i32p), _p(g, _i32p), _p(hist, _i32p),
+                                     C.byref(mx)))
+        return g, hist, mx.value
+
+    # -- K1 -------------------------------------------------------------------
+    def identity(self, indet=None, save_seq=None, save_res=None, counts=False,
+                 keep_on_device=False, out=None, _debug_bytes=False):
+        """Packed identity array over kept pairs -- template.h:320-442."""
+        indet = self.alignment.indet if indet is None else indet
+        ss, sr = _mask(save_seq, self.nseq), _mask(save_res, self.ncol)
+        nk = self.nseq if ss is None else int((ss != -1).sum())
+        npairs = nk * (nk - 1) // 2
+        ident = np.empty(npairs, np.float32) if out is None else out
+        assert ident.dtype == np.float32 and ident.size >= npairs and ident.flags.c_contiguous
+        hit = np.zeros(npairs, np.int32) if counts else None
+        dst = np.zeros(npairs, np.int32) if counts else None
+        if _debug_bytes:
+            rc = self.lib.tcu_debug_identity_bytes(self._h, _p(ss, _i32p), _p(sr, _i32p), indet,
+                                                   _p(ident, _f32p), _p(hit, _i32p), _p(dst, _i32p))
+        else:
+            rc = self.lib.tcu_identity(self._h, _p(ss, _i32p), _p(sr, _i32p), indet,
+                                       _p(ident, _f32p), _p(hit, _i32p), _p(dst, _i32p),
+                                       1 if keep_on_device else 0)
+        _lib.check(rc)
+        ident = ident[:npairs]
+        return (ident, hit, dst) if counts else ident
+
+    # -- K4 -------------------------------------------------------------------
+    def similarity(self, matrix: SimilarityMatrix, gaps=None, number_of_residues=None,
+                   identities=None, indet=None):
+        """(mdk, num, den) -- template.h:69-204.  ``gaps=None`` is cutByGap=False.
+        Needs the device identities of a previous ``identity(keep_on_device=True)``
+        unless ``identities`` is given."""
+        indet = self.alignment.indet if indet is None else indet
+        nres = self.ncol if number_of_residues is None else number_of_residues
+        thr = np.float32(0.8) * np.float32(nres)           # template.h:108
+        dist = np.ascontiguousarray(matrix.distances, np.float32)
+        vhash = np.ascontiguousarray(matrix.vhash, np.int32)
+        g = None if gaps is None else np.ascontiguousarray(gaps, np.int32)
+        ids = None if identities is None else np.ascontiguousarray(identities, np.float32)
+        num, den, mdk = (np.zeros(self.ncol, np.float32) for _ in range(3))
+        ec, er, eb = C.c_int(-1), C.c_int(-1), C.c_int(0)
+        rc = self.lib.tcu_similarity(self._h, indet, _p(dist, _f32p), dist.shape[0],
+                                     _p(vhash, _i32p), _p(g, _i32p), C.c_float(thr),
+                                     _p(ids, _f32p), _p(num, _f32p), _p(den, _f32p),
+                                     _p(mdk, _f32p), C.byref(ec), C.byref(er), C.byref(eb))
+        _lib.check(rc, (ec.value, er.value, eb.value))
+        return mdk, num, den
+
+    # -- K2 -------------------------------------------------------------------
+    def spurious(self, overlap, indet=None):
+        """spuriousVector -- template.h:206-318."""
+        indet = self.alignment.indet if indet is None else indet
+        # template.h:217-218: fp32 product, then ceil
+        ovrlap = int(math.ceil(float(np.float32(overlap) * np.float32(self.nseq - 1))))
+        out = np.zeros(self.nseq, np.float32)
+        _lib.check(self.lib.tcu_spurious(self._h, indet, max(ovrlap, 0), _p(out, _f32p)))
+        return out
+
+    # -- device-resident identity (benchmarks / multi-GPU) ---------------------
+    def identity_prepare(self, indet=None, save_seq=None, save_res=None):
+        indet = self.alignment.indet if indet is None else indet
+        ss, sr = _mask(save_seq, self.nseq), _mask(save_res, self.ncol)
+        nk = C.c_int(0)
+        _lib.check(self.lib.tcu_identity_prepare(self._h, _p(ss, _i32p), _p(sr, _i32p), indet,
+                                                 C.byref(nk)))
+        return nk.value
+
+    def identity_device(self, block_begin, block_end, device_ptr):
+        _lib.check(self.lib.tcu_identity_device(self._h, block_begin, block_end,
+                                                C.c_void_p(device_ptr)))
+
+    def sync(self):
+        _lib.check(self.lib.tcu_msa_sync(self._h))
+
+    @property
+    def stream(self):
+        return self.lib.tcu_msa_stream(self._h)
+
+
+def gaps_window(gaps_in_column, half_window):
+    """``Gaps::applyWindow`` (Gaps.cpp:93-153): mirrored integer mean with
+    ``utils::roundInt`` (utils.cpp:68-72).  Host side, O(L*w)."""
+    g = np.asarray(gaps_in_column, np.int64)
+    L = len(g)
+    if half_window > L // 4:
+        raise ValueError("gap window too big")            # ErrorCode::GapWindowTooBig
+    if half_window < 1:
+        return np.asarray(gaps_in_column, np.int32).copy()
+    idx = np.arange(-half_window, half_window + 1)[None, :] + np.arange(L)[:, None]
+    idx = np.where(idx < 0, -idx, idx)
+    idx = np.where(idx >= L, 2 * L - idx - 2, idx)
+    s = g[idx].sum(axis=1)
+    return (s.astype(np.float64) / (2 * half_window + 1) + 0.5).astype(np.int32)
+
+
+def similarity_window(mdk, half_window):
+    """``Similarity::applyWindow`` (Similarity.cpp:212-269): fp32 running sum in
+    ascending j, divided by (float)(2h+1)."""
+    mdk = np.asarray(mdk, np.float32)
+    L = len(mdk)
+    if half_window > L // 4:
+        raise ValueError("similarity window too big")     # ErrorCode::SimilarityWindowTooBig
+    if half_window < 1:
+        return mdk.copy()
+    idx = np.arange(-half_window, half_window + 1)[None, :] + np.arange(L)[:, None]
+    idx = np.where(idx < 0, -idx, idx)
+    idx = np.where(idx >= L, 2 * L - idx - 2, idx)
+    acc = np.zeros(L, np.float32)
+    for j in range(2 * half_window + 1):                   # sequential fp32 adds, same order
+        acc = (acc + mdk[idx[:, j]]).astype(np.float32)
+    return (acc / np.float32(2 * half_window + 1)).astype(np.float32)

@@ -1,0 +1,235 @@
+"""GPU parity: the CUDA library (through its C ABI) against the oracle.
+
+Integer counts and identity ratios must be bit-exact; similarity accumulators
+are compared bit-for-bit as well (the kernel replays the reference's fp32
+order), with the 1e-5 relative bound of BASELINE.json as the hard limit.
+"""
+import numpy as np
+import pytest
+
+from conftest import random_msa
+
+pytestmark = pytest.mark.gpu
+
+X = ord("X")
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+SHAPES = [(2, 1), (2, 31), (3, 32), (5, 33), (6, 46), (17, 255), (64, 256), (65, 257),
+          (130, 300), (200, 1000), (257, 513)]
+
+
+@pytest.mark.parametrize("n,L", SHAPES)
+def test_gaps(gpu, port, n, L):
+    rng = np.random.default_rng(n * 1000 + L)
+    m = random_msa(rng, n, L)
+    with gpu.DeviceAlignment(m) as d:
+        g, hist, mx = d.gaps()
+    og, ohist, omx = port.gaps(m)
+    assert (g == og).all() and (hist == ohist).all() and mx == omx
+
+
+def test_gaps_masked_rows_true_counts(gpu, port):
+    """Masked rows: true counts (generic path), not the SIMD u8 wrap."""
+    rng = np.random.default_rng(5)
+    m = random_msa(rng, 700, 100, gap=0.9)
+    ss = np.arange(700, dtype=np.int32)
+    ss[rng.random(700) < 0.3] = -1
+    with gpu.DeviceAlignment(m) as d:
+        g, _, _ = d.gaps(save_seq=ss)
+    assert (g == port.gaps(m, ss)[0]).all()
+
+
+def test_gaps_many_rows(gpu, port):
+    rng = np.random.default_rng(6)
+    m = random_msa(rng, 5000, 333, gap=0.5)
+    with gpu.DeviceAlignment(m) as d:
+        g, hist, mx = d.gaps()
+    og, ohist, omx = port.gaps(m)
+    assert (g == og).all() and (hist == ohist).all() and mx == omx
+
+
+@pytest.mark.parametrize("n,L", SHAPES)
+def test_identity_counts_and_ratio(gpu, port, n, L):
+    rng = np.random.default_rng(n * 7919 + L)
+    m = random_msa(rng, n, L)
+    with gpu.DeviceAlignment(m) as d:
+        ident, hit, dst = d.identity(X, counts=True)
+    oi, oh, od = port.identity(m, X, counts=True)
+    assert (hit == oh).all()
+    assert (dst == od).all()
+    assert (bits(ident) == bits(oi)).all()
+
+
+@pytest.mark.parametrize("n,L", [(6, 46), (65, 257), (130, 300)])
+def test_identity_debug_kernel_agrees(gpu, port, n, L):
+    rng = np.random.default_rng(n + L)
+    m = random_msa(rng, n, L)
+    with gpu.DeviceAlignment(m) as d:
+        ident, hit, dst = d.identity(X, counts=True, _debug_bytes=True)
+    oi, oh, od = port.identity(m, X, counts=True)
+    assert (hit == oh).all() and (dst == od).all() and (bits(ident) == bits(oi)).all()
+
+
+def test_identity_masks(gpu, port):
+    rng = np.random.default_rng(11)
+    m = random_msa(rng, 150, 400)
+    ss = np.arange(150, dtype=np.int32)
+    ss[rng.random(150) < 0.25] = -1
+    sr = np.arange(400, dtype=np.int32)
+    sr[rng.random(400) < 0.4] = -1
+    with gpu.DeviceAlignment(m) as d:
+        ident, hit, dst = d.identity(X, save_seq=ss, save_res=sr, counts=True)
+    oi, oh, od = port.identity(m, X, ss, sr, counts=True)
+    assert (hit == oh).all() and (dst == od).all() and (bits(ident) == bits(oi)).all()
+
+
+def test_identity_raw_bytes_case_sensitive(gpu, port):
+    """Lower case, punctuation and >30 distinct symbols (6-7 planes); 'x' is a
+    residue, 'X' a gap."""
+    rng = np.random.default_rng(12)
+    m = random_msa(rng, 90, 500, lower=0.3, extra=b"BZJUO*.?~!#")
+    m[rng.random(m.shape) < 0.02] = ord("x")
+    with gpu.DeviceAlignment(m) as d:
+        ident, hit, dst = d.identity(X, counts=True)
+    oi, oh, od = port.identity(m, X, counts=True)
+    assert (hit == oh).all() and (dst == od).all() and (bits(ident) == bits(oi)).all()
+
+
+@pytest.mark.parametrize("alphabet,indet", [(b"ACGT", ord("N")), (b"AC", ord("N"))])
+def test_identity_small_alphabets(gpu, port, alphabet, indet):
+    rng = np.random.default_rng(13)
+    m = random_msa(rng, 70, 200, alphabet=alphabet, indet=0.0)
+    m[rng.random(m.shape) < 0.03] = indet
+    with gpu.DeviceAlignment(m) as d:
+        ident, hit, dst = d.identity(indet, counts=True)
+    oi, oh, od = port.identity(m, indet, counts=True)
+    assert (hit == oh).all() and (dst == od).all() and (bits(ident) == bits(oi)).all()
+
+
+def test_identity_all_gap_pairs(gpu, port):
+    """dst == 0 -> identity 0 (template.h:427-428)."""
+    m = np.full((5, 70), ord("-"), np.uint8)
+    m[0, :10] = ord("A")
+    m[3, 5:20] = X
+    with gpu.DeviceAlignment(m) as d:
+        ident, hit, dst = d.identity(X, counts=True)
+    oi, oh, od = port.identity(m, X, counts=True)
+    assert (hit == oh).all() and (dst == od).all() and (bits(ident) == bits(oi)).all()
+    assert (ident[od == 0] == 0).all()
+
+
+def test_identity_medium_vs_oracle(gpu, port):
+    from pytrimal_b200.synthetic import synthetic_msa
+    m = synthetic_msa(700, 1300, 21)
+    with gpu.DeviceAlignment(m) as d:
+        ident, hit, dst = d.identity(X, counts=True)
+    oi, oh, od = port.identity(m, X, counts=True)
+    assert (hit == oh).all() and (dst == od).all() and (bits(ident) == bits(oi)).all()
+
+
+@pytest.mark.parametrize("n,L", SHAPES)
+@pytest.mark.parametrize("overlap", [0.0, 0.5, 0.8, 1.0])
+def test_spurious(gpu, port, n, L, overlap):
+    rng = np.random.default_rng(n * 31 + L)
+    m = random_msa(rng, n, L, gap=0.4, indet=0.1)
+    with gpu.DeviceAlignment(m) as d:
+        s = d.spurious(overlap, indet=X)
+    o = port.spurious_pairwise(m, X, overlap)
+    assert (bits(s) == bits(o)).all()
+
+
+@pytest.mark.parametrize("n,L", [(2, 5), (6, 46), (40, 130), (150, 257), (300, 96)])
+@pytest.mark.parametrize("cut", [False, True])
+def test_similarity(gpu, port, n, L, cut):
+    rng = np.random.default_rng(n * 17 + L)
+    m = random_msa(rng, n, L, gap=0.3, lower=0.2)
+    smx = gpu.SimilarityMatrix.aa()
+    og = port.gaps(m)[0]
+    oi = port.identity(m, X)
+    gaps = og if cut else None
+    omdk, onum, oden = port.similarity(m, X, oi, gaps, L, smx.distances, smx.vhash)
+    with gpu.DeviceAlignment(m) as d:
+        d.identity(X, keep_on_device=True)
+        mdk, num, den = d.similarity(smx, gaps=gaps, indet=X)
+    assert (bits(num) == bits(onum)).all()
+    assert (bits(den) == bits(oden)).all()
+    assert (bits(mdk) == bits(omdk)).all()
+    np.testing.assert_allclose(mdk, omdk, rtol=1e-5, atol=0)   # BASELINE.json tolerance
+
+
+def test_similarity_gap_cut_uses_residue_count(gpu, port):
+    """threshold = 0.8 * numberOfResidues (columns!), SURVEY F4."""
+    rng = np.random.default_rng(3)
+    n, L = 300, 100                      # 0.8*L = 80 < n: columns with >= 80 gaps are cut
+    m = random_msa(rng, n, L, gap=0.3)
+    smx = gpu.SimilarityMatrix.aa()
+    og = port.gaps(m)[0]
+    assert (og >= 80).any() and (og < 80).any()
+    oi = port.identity(m, X)
+    omdk, onum, oden = port.similarity(m, X, oi, og, L, smx.distances, smx.vhash)
+    with gpu.DeviceAlignment(m) as d:
+        d.identity(X, keep_on_device=True)
+        mdk, num, den = d.similarity(smx, gaps=og, indet=X)
+    assert (mdk[og >= 80] == 0).all()
+    assert (bits(mdk) == bits(omdk)).all()
+
+
+def test_similarity_symbol_errors(gpu, port):
+    """First offender in column-major scan order; error class as template.h:135-145."""
+    import oracle
+    rng = np.random.default_rng(4)
+    m = random_msa(rng, 20, 60, gap=0.1)
+    smx = gpu.SimilarityMatrix.aa()
+    m[7, 30] = ord("B")      # undefined in BLOSUM62's 20 letters
+    m[3, 41] = ord("*")      # incorrect symbol
+    m[15, 30] = ord("O")
+    oi = port.identity(m, X)
+    with pytest.raises(oracle.SymbolError) as oe:
+        port.similarity(m, X, oi, None, 60, smx.distances, smx.vhash)
+    with gpu.DeviceAlignment(m) as d:
+        d.identity(X, keep_on_device=True)
+        with pytest.raises(gpu.SymbolError) as ge:
+            d.similarity(smx, indet=X)
+    assert (ge.value.col, ge.value.row, ge.value.byte) == (oe.value.col, oe.value.row, oe.value.byte)
+    assert ge.value.code == -6 and oe.value.code == 2
+    m[2, 5] = ord("?")
+    with pytest.raises(oracle.SymbolError) as oe:
+        port.similarity(m, X, oi, None, 60, smx.distances, smx.vhash)
+    with gpu.DeviceAlignment(m) as d:
+        d.identity(X, keep_on_device=True)
+        with pytest.raises(gpu.SymbolError) as ge:
+            d.similarity(smx, indet=X)
+    assert (ge.value.col, ge.value.row, ge.value.byte) == (5, 2, ord("?")) == \
+        (oe.value.col, oe.value.row, oe.value.byte)
+    assert ge.value.code == -5 and oe.value.code == 1
+
+
+def test_similarity_requires_identity(gpu):
+    m = random_msa(np.random.default_rng(1), 10, 40)
+    with gpu.DeviceAlignment(m) as d:
+        with pytest.raises(gpu.TrimalCudaError):
+            d.similarity(gpu.SimilarityMatrix.aa(), indet=X)
+
+
+def test_identity_row_band_matches_full(gpu, port):
+    """Row-block bands written by tcu_identity_device tile the packed array."""
+    import ctypes as C
+    import torch
+    from pytrimal_b200.synthetic import synthetic_msa
+    m = synthetic_msa(300, 700, 5)
+    oi = port.identity(m, X)
+    lib = gpu.load()
+    with gpu.DeviceAlignment(m) as d:
+        nk = d.identity_prepare(X)
+        nb = lib.tcu_identity_row_blocks(nk)
+        out = torch.full((nk * (nk - 1) // 2,), -1.0, dtype=torch.float32, device="cuda:0")
+        for b0, b1 in [(0, 2), (2, 3), (3, nb)]:
+            off = lib.tcu_identity_row_offset(nk, 64 * b0)
+            d.identity_device(b0, b1, out.data_ptr() + 4 * off)
+        d.sync()
+        got = out.cpu().numpy()
+    assert (bits(got) == bits(oi)).all()
