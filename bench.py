@@ -92,21 +92,6 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def band_partition(nb, world):
-    """Row-block boundaries with (nearly) equal tile counts per rank."""
-    total = nb * (nb + 1) // 2
-    before = lambda b: b * nb - b * (b - 1) // 2
-    bounds = [0]
-    for g in range(1, world):
-        target = total * g / world
-        b = bounds[-1]
-        while b < nb and before(b) < target:
-            b += 1
-        bounds.append(b)
-    bounds.append(nb)
-    return bounds
-
-
 def run_reference(args, rank, world):
     """The reference's own CPU implementation (AVX2), bounded sample per step."""
     if rank != 0:
@@ -203,6 +188,7 @@ def main():
     import torch.distributed as dist
     import pytrimal_b200 as pb
     from pytrimal_b200 import _lib
+    from pytrimal_b200.sharding import band_partition
     from pytrimal_b200.synthetic import CONFIGS, synthetic_msa
 
     if pb.device_count() < 1:

@@ -48,10 +48,12 @@ def read_alignment(path):
     with open(path, "rb") as f:
         lines = f.readlines()
     first = next((l for l in lines if l.strip()), b"")
-    if first.startswith(b">"):
-        return _parse_fasta(lines)
     if first.upper().startswith(b"CLUSTAL") or first.upper().startswith(b"MUSCLE"):
         return _parse_clustal(lines)
+    # FASTA; like trimAl's reader, tolerate junk before the first '>' record
+    start = next((i for i, l in enumerate(lines) if l.startswith(b">")), None)
+    if start is not None:
+        return _parse_fasta(lines[start:])
     raise ValueError(f"unsupported alignment format: {path}")
 
 

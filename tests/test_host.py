@@ -1,0 +1,150 @@
+"""Host-side logic and the C-ABI surface, CPU only (no compute calls)."""
+import ctypes
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, random_msa
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "trimal_cuda.h")).read()
+    declared = set(re.findall(r"\b(tcu_[a-z_0-9]+)\s*\(", header))
+    assert len(declared) >= 20
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in trimal_cuda.h but not exported"
+    from pytrimal_b200 import _lib
+    assert declared == set(_lib.PROTOTYPES), "ctypes prototypes out of sync with the header"
+
+
+def test_library_links_no_torch_and_no_oracle():
+    import subprocess
+    import pytrimal_b200
+    out = subprocess.run(["ldd", pytrimal_b200.LIB_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in out and "oracle" not in out and "trimal_ref" not in out
+
+
+def test_product_sources_do_not_reference_the_oracle():
+    for path in glob.glob(os.path.join(ROOT, "pytrimal_b200", "**", "*"), recursive=True):
+        if os.path.isfile(path) and path.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+            text = open(path, errors="replace").read()
+            assert "import oracle" not in text and "liboracle" not in text and \
+                "trimal_ref" not in text, path
+
+
+def test_no_device_fails_loudly(lib):
+    import pytrimal_b200 as pb
+    if pb.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(pb.NoDeviceError):
+        pb.DeviceAlignment(np.full((3, 5), 65, np.uint8))
+    assert "no CPU fallback" in lib.tcu_last_error().decode() or "CUDA" in lib.tcu_last_error().decode()
+
+
+def test_row_offset_and_blocks_match_python(lib):
+    from pytrimal_b200 import sharding
+    for n in [0, 1, 2, 63, 64, 65, 1000, 50000, 100000]:
+        assert lib.tcu_identity_row_blocks(n) == sharding.row_blocks(n)
+        for i in [0, 1, 63, 64, n // 2, n - 2, n - 1, n, n + 5]:
+            assert lib.tcu_identity_row_offset(n, i) == sharding.row_offset(n, i), (n, i)
+    n = 1000
+    pos = 0
+    for i in range(n - 1):
+        assert sharding.row_offset(n, i) == pos
+        pos += n - 1 - i
+    assert sharding.row_offset(n, n - 1) == n * (n - 1) // 2
+
+
+def test_band_partition_balanced_and_covering():
+    from pytrimal_b200.sharding import band_partition, band_slice, row_blocks, tiles_before
+    for n in [100, 4097, 50000, 100000]:
+        nb = row_blocks(n)
+        for world in [1, 2, 3, 4, 8]:
+            b = band_partition(nb, world)
+            assert b[0] == 0 and b[-1] == nb and all(x <= y for x, y in zip(b, b[1:]))
+            counts = [tiles_before(b[g + 1], nb) - tiles_before(b[g], nb) for g in range(world)]
+            assert sum(counts) == nb * (nb + 1) // 2
+            if nb >= 16 * world:
+                assert max(counts) <= 1.05 * sum(counts) / world + nb
+            total = 0
+            for g in range(world):
+                off, cnt = band_slice(n, b, g)
+                assert off == total
+                total += cnt
+            assert total == n * (n - 1) // 2
+
+
+def test_alignment_type_detection_matches_fixtures():
+    import pytrimal_b200 as pb
+    for path in glob.glob(os.path.join(GOLDEN, "*.npz")):
+        g = np.load(path)
+        a = pb.Alignment.from_matrix(g["matrix"])
+        assert a.alignment_type == int(g["alignment_type"]), path
+
+
+def test_default_matrices_match_fixtures():
+    import pytrimal_b200 as pb
+    for path in glob.glob(os.path.join(GOLDEN, "*.npz")):
+        g = np.load(path)
+        t = int(g["alignment_type"])
+        if t in (8, 24, 0):
+            smx = pb.SimilarityMatrix.aa()
+        elif t in (2, 4):
+            smx = pb.SimilarityMatrix.nt()
+        else:
+            smx = pb.SimilarityMatrix.nt(degenerated=True)
+        assert (smx.distances.view(np.uint32) == g["dist"].view(np.uint32)).all(), path
+        assert (smx.vhash == g["vhash"]).all()
+
+
+def test_windows_match_oracle(port):
+    from pytrimal_b200 import gaps_window, similarity_window
+    rng = np.random.default_rng(1)
+    for L in [8, 46, 200]:
+        g = rng.integers(0, 50, L).astype(np.int32)
+        mdk = rng.random(L).astype(np.float32)
+        for h in [0, 1, 2, L // 4]:
+            assert (gaps_window(g, h) == port.gaps_window(g, h)).all()
+            assert (similarity_window(mdk, h).view(np.uint32) ==
+                    port.similarity_window(mdk, h).view(np.uint32)).all()
+        with pytest.raises(ValueError):
+            gaps_window(g, L // 4 + 1)      # test_manual_trimmer.py:49-52 (window too large)
+        with pytest.raises(ValueError):
+            similarity_window(mdk, L // 4 + 1)
+
+
+def test_alignment_constructor_errors():
+    import pytrimal_b200 as pb
+    with pytest.raises(ValueError):
+        pb.Alignment([b"a"], [b"MKK", b"MKA"])
+    with pytest.raises(ValueError):
+        pb.Alignment([b"a", b"b"], [b"MKK", b"MK"])
+    with pytest.raises(ValueError):
+        pb.Alignment([b"a", b"b"], [b"MK1", b"MKA"])     # digit: Alignment.cpp:659-664
+    with pytest.raises(ValueError):
+        pb.Alignment([b"a"], [b"MKK"], sequence_type="nope")
+    a = pb.Alignment([b"a", b"b"], ["MKKBO", "MKKAY"])
+    assert a.alignment_type & 8 and chr(a.indet) == "X"
+
+
+def test_readers(tmp_path):
+    from pytrimal_b200 import io as tio
+    p = tmp_path / "a.fasta"
+    p.write_bytes(b"[junk line]\n>s1 desc\nAC-\nGT\n>s2\nACCGT\n")
+    names, seqs = tio.read_alignment(str(p))
+    assert names == [b"s1", b"s2"] and seqs == [b"AC-GT", b"ACCGT"]
+    q = tmp_path / "a.clw"
+    q.write_bytes(b"CLUSTAL W\n\ns1   AC-\ns2   ACC\n     ** \n\ns1   GT\ns2   GT\n")
+    names, seqs = tio.read_alignment(str(q))
+    assert names == [b"s1", b"s2"] and seqs == [b"AC-GT", b"ACCGT"]
+
+
+def test_synthetic_generator_is_deterministic():
+    from pytrimal_b200.synthetic import synthetic_msa
+    a = synthetic_msa(300, 200, 7)
+    b = synthetic_msa(300, 200, 7)
+    assert (a == b).all() and a.shape == (300, 200)
+    assert 0.1 < (a == ord("-")).mean() < 0.5
