@@ -29,7 +29,7 @@ REF_PATH = os.path.join(_HERE, "_ref", "libtrimal_ref.so")
 ERR_INCORRECT_SYMBOL = 1
 ERR_UNDEFINED_SYMBOL = 2
 
-PLATFORM_NONE, PLATFORM_SSE2, PLATFORM_AVX2 = 0, 1, 2
+PLATFORM_NONE, PLATFORM_SSE2, PLATFORM_AVX2, PLATFORM_CUDA = 0, 1, 2, 3
 
 _u8p = C.POINTER(C.c_uint8)
 _i32p = C.POINTER(C.c_int)
@@ -229,13 +229,14 @@ class Ref:
     """One reference ``Alignment`` (real trimAl code) built from a byte matrix."""
 
     _lib = None
+    PATH = REF_PATH
 
     @classmethod
     def lib(cls):
-        if cls._lib is None:
-            if not ref_available():
-                raise RuntimeError(f"{REF_PATH} not built (make -C oracle ref needs /root/reference)")
-            L = C.CDLL(REF_PATH)
+        if cls.__dict__.get("_lib") is None:
+            if not os.path.exists(cls.PATH):
+                raise RuntimeError(f"{cls.PATH} not built (needs /root/reference)")
+            L = C.CDLL(cls.PATH)
             L.ref_alignment_new.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int]
             L.ref_alignment_new.restype = C.c_void_p
             L.ref_alignment_free.argtypes = [C.c_void_p]

@@ -55,6 +55,9 @@ statistics::ComputePlatform to_platform(int p)
     switch (p) {
     case 1: return statistics::ComputePlatform::SSE2;
     case 2: return statistics::ComputePlatform::AVX2;
+#ifdef HAVE_CUDA  /* only in the integration build (integration/Makefile) */
+    case 3: return statistics::ComputePlatform::CUDA;
+#endif
     default: return statistics::ComputePlatform::NONE;
     }
 }
@@ -119,7 +122,8 @@ void ref_alignment_free(void *hv)
 
 int ref_alignment_type(void *hv) { return ((RefAlignment *)hv)->ali->getAlignmentType(); }
 
-/* 0 = generic, 1 = SSE2, 2 = AVX2.  Must be called before any statistic. */
+/* 0 = generic, 1 = SSE2, 2 = AVX2, 3 = CUDA (integration build only).
+ * Must be called before any statistic. */
 void ref_set_platform(void *hv, int platform)
 {
     ((RefAlignment *)hv)->ali->Statistics->platform = to_platform(platform);

@@ -1,0 +1,122 @@
+"""Drop-in test: the REFERENCE's own trimAl (Alignment, Cleaner, Manager -- all
+trimming logic) built with the CUDA compute platform patched in
+(integration/Makefile), driven exactly like the AVX2 oracle.  Trimmed
+alignments must be byte-identical to the AVX2 platform's: same kept rows, same
+kept columns."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, random_msa
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+DROPIN = os.path.join(ROOT, "integration", "_build", "libtrimal_cuda_platform.so")
+
+
+class DropIn(oracle.Ref):
+    PATH = DROPIN
+    _lib = None
+
+
+@pytest.fixture(scope="module")
+def dropin(gpu):
+    if not os.path.exists(DROPIN):
+        pytest.skip("integration/_build not present (built where /root/reference exists)")
+    return DropIn
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "*.npz")))
+IDS = [os.path.basename(f)[:-4] for f in FIXTURES]
+AUTO = ["gappyout", "strict", "strictplus", "automated1", "automated2", "nogaps", "noallgaps"]
+PYTRIMAL = {
+    "cons60.gt90": ("manual", [1 - 0.9, -1, 60, -1, -1, -1]),
+    "cons40.gt40": ("manual", [1 - 0.4, -1, 40, -1, -1, -1]),
+    "seq80.res80": ("overlap", [0.8, 80]),
+    "seq40.res60": ("overlap", [0.6, 40]),
+    "clusters5": ("representative", [5, -1]),
+    "clusters10": ("representative", [10, -1]),
+    "maxidentity75": ("representative", [-1, 0.75]),
+    "noduplicateseqs": ("noduplicateseqs", []),
+}
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=IDS)
+def test_cuda_platform_reproduces_reference_trims(dropin, path):
+    g = np.load(path)
+    m = g["matrix"]
+    for method in AUTO:
+        key = f"trim_{method}_seq"
+        if key in g:
+            ks, kr = dropin(m, platform=oracle.PLATFORM_CUDA).trim(method)
+            assert (ks == g[key]).all(), method
+            assert (kr == g[f"trim_{method}_res"]).all(), method
+        else:  # the reference reported an error: the CUDA platform must too
+            with pytest.raises(ValueError):
+                dropin(m, platform=oracle.PLATFORM_CUDA).trim(method)
+    for suffix, (method, params) in PYTRIMAL.items():
+        key = f"pytrimal_{suffix}_seq"
+        if key in g:
+            ks, kr = dropin(m, platform=oracle.PLATFORM_CUDA).trim(method, params)
+            assert (ks == g[key]).all() and (kr == g[f"pytrimal_{suffix}_res"]).all(), suffix
+    if "pytrimal_gt90w3_seq" in g:
+        ks, kr = dropin(m, platform=oracle.PLATFORM_CUDA).trim("manual", [1 - 0.9, -1, -1, 3, -1, -1])
+        assert (ks == g["pytrimal_gt90w3_seq"]).all() and (kr == g["pytrimal_gt90w3_res"]).all()
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=IDS)
+def test_cuda_platform_statistics_through_manager(dropin, path):
+    g = np.load(path)
+    m = g["matrix"]
+    r = dropin(m, platform=oracle.PLATFORM_CUDA)
+    gaps, _, hist, mx = r.gaps()
+    assert (gaps == g["gaps"]).all() and (hist == g["gaps_hist"]).all() and mx == int(g["gaps_max"])
+    assert (bits(r.identity()) == bits(g["identity"])).all()
+    assert (bits(dropin(m, platform=oracle.PLATFORM_CUDA).spurious(0.5)) == bits(g["spurious_50"])).all()
+    if "similarity_error" in g:
+        with pytest.raises(ValueError):
+            r.similarity()
+    else:
+        assert (bits(r.similarity()[0]) == bits(g["mdk"])).all()
+
+
+TRIMS = [("strict", []), ("strictplus", []), ("gappyout", []), ("automated1", []),
+         ("manual", [1 - 0.9, 0.1, -1, 3, -1, -1]),      # BASELINE config 2
+         ("manual", [1 - 0.7, -1, 40, -1, -1, -1]),
+         ("overlap", [0.5, 50]), ("overlap", [0.5, 0.5]),  # BASELINE config 5 (both readings)
+         ("representative", [-1, 0.8]),                   # BASELINE config 4
+         ("representative", [7, -1])]
+
+
+@pytest.mark.parametrize("shape,seed", [((400, 600), 1), ((1000, 300), 2), ((150, 2000), 3)])
+def test_cuda_vs_avx2_platform_synthetic(dropin, shape, seed):
+    from pytrimal_b200.synthetic import synthetic_msa
+    m = synthetic_msa(shape[0], shape[1], seed)
+    for method, params in TRIMS:
+        a = dropin(m, platform=oracle.PLATFORM_AVX2).trim(method, params)
+        c = dropin(m, platform=oracle.PLATFORM_CUDA).trim(method, params)
+        assert (a[0] == c[0]).all() and (a[1] == c[1]).all(), (method, params)
+
+
+def test_cuda_platform_symbol_error_is_reported(dropin):
+    """test_automatic_trimmer.py:74-79: Alignment(["MKKBO","MKKAY"]) + strict -> error."""
+    m = np.frombuffer(b"MKKBOMKKAY", np.uint8).reshape(2, 5)
+    with pytest.raises(ValueError):
+        dropin(m, platform=oracle.PLATFORM_AVX2).trim("strict")
+    with pytest.raises(ValueError):
+        dropin(m, platform=oracle.PLATFORM_CUDA).trim("strict")
+
+
+def test_cuda_platform_large_window_is_reported(dropin):
+    """test_manual_trimmer.py:49-52: window > L/4 fails (Gaps.cpp:98-101)."""
+    g = np.load(os.path.join(GOLDEN, "example.001.AA.npz"))
+    with pytest.raises(ValueError):
+        dropin(g["matrix"], platform=oracle.PLATFORM_CUDA).trim("manual", [1 - 0.9, -1, -1, 100, -1, -1])
