@@ -210,11 +210,11 @@ def main():
     host_rows = torch.from_numpy(m).pin_memory()
     host_np = host_rows.numpy()
 
-    nb = lib.tcu_identity_row_blocks(n)
-    bounds = band_partition(nb, world)
+    band_rows = lib.tcu_identity_band_rows()
+    bounds = band_partition(n, world)
     b0, b1 = bounds[rank], bounds[rank + 1]
-    off0 = lib.tcu_identity_row_offset(n, 64 * b0)
-    off1 = lib.tcu_identity_row_offset(n, min(64 * b1, n))
+    off0 = lib.tcu_identity_row_offset(n, band_rows * b0)
+    off1 = lib.tcu_identity_row_offset(n, min(band_rows * b1, n))
     my_pairs = off1 - off0
 
     def barrier():

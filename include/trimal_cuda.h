@@ -128,10 +128,11 @@ int tcu_spurious(tcu_msa *msa, uint8_t indet, uint32_t ovrlap, float *spurious);
 
 /*
  * Row-band variant for drivers that shard the pair matrix across GPUs: only
- * the rows of row-blocks [block_begin, block_end) (64 kept rows per block;
- * block_end < 0 = to the end) are computed and copied to `identities`, a HOST
- * slice whose element 0 is packed offset tcu_identity_row_offset(kept,
- * 64*block_begin).  Bands of different ranks concatenate to the full array.
+ * the rows of row-blocks [block_begin, block_end) (tcu_identity_band_rows() =
+ * 128 kept rows per block; block_end < 0 = to the end) are computed and copied
+ * to `identities`, a HOST slice whose element 0 is packed offset
+ * tcu_identity_row_offset(kept, 128*block_begin).  Bands of different ranks
+ * concatenate to the full array.
  */
 int tcu_identity_band(tcu_msa *msa, const int *save_seq, const int *save_res, uint8_t indet,
                       int block_begin, int block_end, float *identities);
@@ -140,8 +141,14 @@ int tcu_identity_band(tcu_msa *msa, const int *save_seq, const int *save_res, ui
  * Same kernels, but results stay in device memory owned by the caller and no
  * host synchronisation is done beyond what the arguments require.            */
 
-/* Number of 64-row blocks the kept rows are tiled into for tcu_identity_device. */
+/* Rows per row-block of the band interface (the kernel's tile height, 128). */
+int tcu_identity_band_rows(void);
+
+/* Number of row-blocks the kept rows are tiled into for tcu_identity_device / _band. */
 int tcu_identity_row_blocks(int kept_rows);
+
+/* Work (pair-matrix tiles) in row-blocks < block: lets a driver cut bands of equal work. */
+long long tcu_identity_tiles_before(int kept_rows, int block);
 
 /* Packed-array offset of the first pair whose first row is i (kept-index space). */
 size_t tcu_identity_row_offset(int kept_rows, int i);
@@ -156,9 +163,9 @@ int tcu_identity_prepare(tcu_msa *msa, const int *save_seq, const int *save_res,
 
 /*
  * Compute the rows of the packed identity array that belong to row-blocks
- * [block_begin, block_end) (64 kept rows per block) into d_out, a DEVICE
- * buffer whose element 0 corresponds to packed offset
- * tcu_identity_row_offset(kept, 64*block_begin).  Asynchronous on the
+ * [block_begin, block_end) (tcu_identity_band_rows() kept rows per block) into
+ * d_out, a DEVICE buffer whose element 0 corresponds to packed offset
+ * tcu_identity_row_offset(kept, 128*block_begin).  Asynchronous on the
  * handle's stream; use tcu_msa_sync() to wait.
  */
 int tcu_identity_device(tcu_msa *msa, int block_begin, int block_end, float *d_out);

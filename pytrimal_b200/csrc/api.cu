@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -131,8 +132,12 @@ struct tcu_msa {
     // identity operand
     bool prepared = false;
     int np = 0, nk = 0, nb = 0, nchunks = 0;
+    int nsb = 0, nb2 = 0;     // v2: 128-row super-blocks, allocated 64-row blocks (even)
+    bool use_v1 = false;      // TCU_IDENTITY_IMPL=v1: the integer-pipe-only kernel (A/B timing)
     uint32_t *d_planes = nullptr;
     size_t planes_cap = 0;
+    uint8_t *d_gbytes = nullptr;
+    size_t gbytes_cap = 0;
     int *d_kept_rows = nullptr;
     uint8_t *d_col_drop = nullptr;
     uint8_t *d_lut = nullptr;
@@ -302,6 +307,7 @@ extern "C" void tcu_msa_destroy(tcu_msa *m)
     if (m->stream) cudaStreamSynchronize(m->stream);
     cudaFree(m->d_raw);
     cudaFree(m->d_planes);
+    cudaFree(m->d_gbytes);
     cudaFree(m->d_kept_rows);
     cudaFree(m->d_col_drop);
     cudaFree(m->d_lut);
@@ -395,7 +401,14 @@ extern "C" int tcu_gaps(tcu_msa *m, const int *save_seq, int *gaps_in_column,
 // ---------------------------------------------------------------------------
 // K0 + K1 identity
 // ---------------------------------------------------------------------------
-extern "C" int tcu_identity_row_blocks(int kept_rows) { return (kept_rows + RB - 1) / RB; }
+extern "C" int tcu_identity_band_rows(void) { return IB; }
+extern "C" int tcu_identity_row_blocks(int kept_rows) { return (kept_rows + IB - 1) / IB; }
+
+extern "C" long long tcu_identity_tiles_before(int kept_rows, int block)
+{
+    const int nb = (kept_rows + RB - 1) / RB, nsb = (kept_rows + IB - 1) / IB;
+    return tiles_before2(std::max(0, std::min(block, nsb)), nb);
+}
 
 extern "C" size_t tcu_identity_row_offset(int kept_rows, int i)
 {
@@ -456,7 +469,13 @@ extern "C" int tcu_identity_prepare(tcu_msa *m, const int *save_seq, const int *
     m->np = np;
     m->nk = (int)kept.size();
     m->nb = (m->nk + RB - 1) / RB;
-    m->nchunks = (L + KC * 32 - 1) / (KC * 32);
+    m->nsb = (m->nk + IB - 1) / IB;
+    m->nb2 = 2 * m->nsb;
+    {
+        const char *impl = getenv("TCU_IDENTITY_IMPL");
+        m->use_v1 = impl && strcmp(impl, "v1") == 0;
+    }
+    m->nchunks = m->use_v1 ? (L + KC * 32 - 1) / (KC * 32) : (L + KC2 * 32 - 1) / (KC2 * 32);
     m->prepared_indet = indet;
 
     if (!m->d_lut) CK(cudaMalloc((void **)&m->d_lut, 256));
@@ -469,12 +488,23 @@ extern "C" int tcu_identity_prepare(tcu_msa *m, const int *save_seq, const int *
     if (L) CK(cudaMemcpyAsync(m->d_col_drop, drop.data(), L, cudaMemcpyHostToDevice, m->stream));
     CK(cudaStreamSynchronize(m->stream));  // the host vectors go out of scope
 
-    const size_t need = (size_t)m->nb * m->nchunks * tile_bytes(np);
-    int rc = ensure((void **)&m->d_planes, &m->planes_cap, need);
-    if (rc != TCU_OK) return rc;
-    CK(cudaEventRecord(m->ev[1], m->stream));
-    CK(launch_pack_planes(m->d_raw, m->pitch, L, m->d_kept_rows, m->nk, m->d_col_drop, m->d_lut, np,
-                          m->nb, m->nchunks, m->d_planes, m->stream));
+    int rc;
+    if (m->use_v1) {
+        rc = ensure((void **)&m->d_planes, &m->planes_cap, (size_t)m->nb * m->nchunks * tile_bytes(np));
+        if (rc != TCU_OK) return rc;
+        CK(cudaEventRecord(m->ev[1], m->stream));
+        CK(launch_pack_planes(m->d_raw, m->pitch, L, m->d_kept_rows, m->nk, m->d_col_drop, m->d_lut,
+                              np, m->nb, m->nchunks, m->d_planes, m->stream));
+    } else {
+        rc = ensure((void **)&m->d_planes, &m->planes_cap, (size_t)m->nb2 * m->nchunks * tile2_bytes(np));
+        if (rc != TCU_OK) return rc;
+        rc = ensure((void **)&m->d_gbytes, &m->gbytes_cap,
+                    (size_t)m->nb2 * m->nchunks * G_STAGES_PER_CHUNK * G_BLOCK_BYTES);
+        if (rc != TCU_OK) return rc;
+        CK(cudaEventRecord(m->ev[1], m->stream));
+        CK(launch_pack_planes2(m->d_raw, m->pitch, L, m->d_kept_rows, m->nk, m->d_col_drop, m->d_lut,
+                               np, m->nb2, m->nchunks, m->d_planes, m->d_gbytes, m->stream));
+    }
     CK(cudaEventRecord(m->ev[2], m->stream));
     if (m->nb && m->nchunks) m->timings.kernel_launches++;
     m->prepared = true;
@@ -482,23 +512,44 @@ extern "C" int tcu_identity_prepare(tcu_msa *m, const int *save_seq, const int *
     return TCU_OK;
 }
 
-static int identity_launch(tcu_msa *m, int block_begin, int block_end, float *d_out, int *d_hit,
+// super-blocks [sb_begin, sb_end) of IB = 128 kept rows each
+static int identity_launch(tcu_msa *m, int sb_begin, int sb_end, float *d_out, int *d_hit,
                            int *d_dst)
 {
-    IdentityParams p{};
-    p.planes = m->d_planes;
-    p.out = d_out;
-    p.hit_out = d_hit;
-    p.dst_out = d_dst;
-    p.nb = m->nb;
-    p.nchunks = m->nchunks;
-    p.nk = m->nk;
-    p.total_bits = m->nchunks * KC * 32;
-    p.tile_begin = tiles_before(block_begin, m->nb);
-    p.tile_end = tiles_before(block_end, m->nb);
-    p.out_base = tcu_identity_row_offset(m->nk, block_begin * RB);
-    if (p.tile_end <= p.tile_begin || m->nchunks == 0) return TCU_OK;
-    CK(launch_identity(m->np, p, m->num_sms, m->stream));
+    if (m->nchunks == 0 || sb_end <= sb_begin) return TCU_OK;
+    if (m->use_v1) {
+        IdentityParams p{};
+        p.planes = m->d_planes;
+        p.out = d_out;
+        p.hit_out = d_hit;
+        p.dst_out = d_dst;
+        p.nb = m->nb;
+        p.nchunks = m->nchunks;
+        p.nk = m->nk;
+        p.total_bits = m->nchunks * KC * 32;
+        p.tile_begin = tiles_before(std::min(2 * sb_begin, m->nb), m->nb);
+        p.tile_end = tiles_before(std::min(2 * sb_end, m->nb), m->nb);
+        p.out_base = tcu_identity_row_offset(m->nk, sb_begin * IB);
+        if (p.tile_end <= p.tile_begin) return TCU_OK;
+        CK(launch_identity(m->np, p, m->num_sms, m->stream));
+    } else {
+        Identity2Params p{};
+        p.planes = m->d_planes;
+        p.gbytes = m->d_gbytes;
+        p.out = d_out;
+        p.hit_out = d_hit;
+        p.dst_out = d_dst;
+        p.nb = m->nb;
+        p.nb2 = m->nb2;
+        p.nchunks = m->nchunks;
+        p.nk = m->nk;
+        p.total_bits = m->nchunks * KC2 * 32;
+        p.tile_begin = tiles_before2(sb_begin, m->nb);
+        p.tile_end = tiles_before2(sb_end, m->nb);
+        p.out_base = tcu_identity_row_offset(m->nk, sb_begin * IB);
+        if (p.tile_end <= p.tile_begin) return TCU_OK;
+        CK(launch_identity2(m->np, p, m->num_sms, m->stream));
+    }
     m->timings.kernel_launches++;
     return TCU_OK;
 }
@@ -507,9 +558,9 @@ extern "C" int tcu_identity_device(tcu_msa *m, int block_begin, int block_end, f
 {
     if (!m || !d_out) return fail(TCU_ERR_INVALID, "NULL argument");
     if (!m->prepared) return fail(TCU_ERR_STATE, "tcu_identity_prepare has not been called");
-    if (block_begin < 0 || block_end > m->nb || block_begin > block_end)
+    if (block_begin < 0 || block_end > m->nsb || block_begin > block_end)
         return fail(TCU_ERR_INVALID, "row-block range [%d,%d) outside [0,%d)", block_begin,
-                    block_end, m->nb);
+                    block_end, m->nsb);
     CK(cudaSetDevice(m->device));
     m->timings.kernel_launches = 0;
     int rc = identity_launch(m, block_begin, block_end, d_out, nullptr, nullptr);
@@ -530,12 +581,12 @@ extern "C" int tcu_identity_band(tcu_msa *m, const int *save_seq, const int *sav
     m->ident_full = false;
     int rc = tcu_identity_prepare(m, save_seq, save_res, indet, nullptr);
     if (rc != TCU_OK) return rc;
-    if (block_end < 0) block_end = m->nb;
-    if (block_begin < 0 || block_end > m->nb || block_begin > block_end)
+    if (block_end < 0) block_end = m->nsb;
+    if (block_begin < 0 || block_end > m->nsb || block_begin > block_end)
         return fail(TCU_ERR_INVALID, "row-block range [%d,%d) outside [0,%d)", block_begin,
-                    block_end, m->nb);
-    const size_t lo = tcu_identity_row_offset(m->nk, block_begin * RB);
-    const size_t hi = tcu_identity_row_offset(m->nk, std::min(block_end * RB, m->nk));
+                    block_end, m->nsb);
+    const size_t lo = tcu_identity_row_offset(m->nk, block_begin * IB);
+    const size_t hi = tcu_identity_row_offset(m->nk, std::min(block_end * IB, m->nk));
     const size_t count = hi - lo;
     if (count == 0) {
         CK(cudaStreamSynchronize(m->stream));
@@ -588,7 +639,7 @@ static int identity_host(tcu_msa *m, const int *save_seq, const int *save_res, u
                                  indet, m->d_ident, d_hit, d_dst, m->stream));
         m->timings.kernel_launches++;
     } else {
-        rc = identity_launch(m, 0, m->nb, m->d_ident, d_hit, d_dst);
+        rc = identity_launch(m, 0, m->nsb, m->d_ident, d_hit, d_dst);
         if (rc != TCU_OK) return rc;
     }
     CK(cudaEventRecord(m->ev[3], m->stream));

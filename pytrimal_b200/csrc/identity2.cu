@@ -1,0 +1,439 @@
+// identity2.cu -- K1: pairwise sequence identity, integer pipes + tensor cores.
+//
+// Replaces simd::calculateSeqIdentity<V> (vendor/trimal/include/Platform/
+// template.h:320-442).  Per kept pair i<j:
+//     dst = #{kept columns : not (gap_i and gap_j)}      (template.h:422)
+//     hit = #{those columns : byte_i == byte_j}          (template.h:423-424)
+//     identity = dst ? (float)hit / (float)dst : 0       (template.h:427-434)
+// written at the packed upper-triangular offset of (i, j) (template.h:436).
+//
+// The two counts run on different units of the SM, concurrently:
+//   hit    integer pipes.  Residues are dense codes stored as NP bit-planes; for
+//          one 32-column word of one pair
+//              differ = (a.p0A ^ b.p0B) | (a.r1 ^ b.r1) | ... | (a.rN ^ b.rN)
+//              hit   += popc(~differ)
+//          i.e. NP LOP3 + 1 POPC + 1 add per 32 pair-columns (the gap class is
+//          encoded so that it never compares equal, see tcu_internal.cuh).
+//   both   = #{columns : gap_i and gap_j} = G Gt, a binary matrix product: one
+//          tcgen05.mma kind::i8 (M = 128 I rows, N = 64 J rows, K = 32 columns)
+//          per 32 columns of a tile, accumulated in TMEM as int32;
+//          dst = total_bits - both because padding/masked columns are gaps in
+//          every row.
+// Everything is integer until the single IEEE fp32 division of the epilogue, so
+// the results are bit-identical to the reference for any input bytes.
+//
+// One CTA (two per SM) walks 128 x 64 tiles of the pair matrix:
+//   warps 0-7  math: 32 x 32 pairs per warp, 8 x 4 per thread, plane chunks of
+//              128 columns from a 3-stage ring; epilogue: TMEM -> registers ->
+//              shared-memory transpose -> divide -> store
+//   warp 8     producer: 1-D bulk async copies (TMA unit) of plane chunks and of
+//              the 64-column gap-byte stages, mbarrier complete_tx
+//   warp 9     MMA issuer: one thread, two UMMAs per gap-byte stage, tcgen05.commit
+//              frees the stage / publishes the accumulator (two TMEM buffers)
+#include <algorithm>
+
+#include "tcu_internal.cuh"
+
+namespace tcu {
+
+constexpr int ID2_MATH_WARPS = 8;
+constexpr int ID2_MATH_THREADS = ID2_MATH_WARPS * 32;
+constexpr int ID2_THREADS = ID2_MATH_THREADS + 64;
+constexpr int ID2_PSTAGES = 3;                               // plane-chunk ring
+constexpr int ID2_GSTAGES = 2;                               // gap-byte ring
+constexpr int ID2_GSTAGE_BYTES = (IB + RB) * GS_COLS;         // 12288
+constexpr int ID2_XS = 68;                                   // exchange row stride (words)
+constexpr int ID2_XCH_BYTES = IB * ID2_XS * 4;
+constexpr int ID2_TMEM_COLS = 2 * RB;                         // two int32 accumulators of N = 64
+constexpr int ID2_NBARS = 2 * ID2_PSTAGES + 2 * ID2_GSTAGES + 4;
+
+__host__ __device__ constexpr int id2_pstage_bytes(int np) { return 3 * role_bytes(np); }
+__host__ __device__ constexpr size_t id2_smem_bytes(int np)
+{
+    return (size_t)ID2_PSTAGES * id2_pstage_bytes(np) + ID2_GSTAGES * ID2_GSTAGE_BYTES +
+           ID2_XCH_BYTES + ID2_NBARS * sizeof(uint64_t) + 16;
+}
+
+// ------------------------------ tcgen05 helpers ------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, no swizzle: 8 x 16-byte core matrices; LBO between the two 16-byte K
+// halves of one MMA, SBO between 8-row groups (cute::UMMA::SmemDescriptor:
+// start >> 4 at [0,14), LBO >> 4 at [16,30), SBO >> 4 at [32,46), version 1 at [46,48))
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo)
+{
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+
+// cute::UMMA::InstrDescriptor: D = s32 (2 at [4,6)), A = B = u8 (0), both K-major,
+// N >> 3 at [17,23), M >> 4 at [24,29)
+constexpr uint32_t ID2_IDESC = (2u << 4) | ((uint32_t)(RB >> 3) << 17) | ((uint32_t)(IB >> 4) << 24);
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(ID2_IDESC), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+          "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+          "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void math_bar_sync()
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(ID2_MATH_THREADS) : "memory");
+}
+
+// linear tile index -> (I super-block, J block): super-block BI owns the tiles
+// (BI, 2*BI .. nb-1), tiles_before2(BI, nb) of them precede it
+__device__ __forceinline__ void tile_to_blocks2(long long t, int nb, int &BI, int &bj)
+{
+    const double m = (double)nb + 1.0;
+    int b = (int)((m - sqrt(fmax(m * m - 4.0 * (double)t, 0.0))) * 0.5);
+    const int nsb = (nb + 1) >> 1;
+    b = max(0, min(b, nsb - 1));
+    while (b > 0 && tiles_before2(b, nb) > t) b--;
+    while (b + 1 < nsb && tiles_before2(b + 1, nb) <= t) b++;
+    BI = b;
+    bj = 2 * b + (int)(t - tiles_before2(b, nb));
+}
+
+template <int NP>
+struct Rest {
+    uint32_t r[NP - 1];
+};
+
+template <int NP>
+__device__ __forceinline__ void load_rest(const uint32_t *rest, int cell, Rest<NP> &o)
+{
+    constexpr int R = NP - 1;
+    constexpr int RP = rest_words(NP);
+    const uint32_t *q = rest + cell * RP;
+    if constexpr (RP == 2) {
+        const uint2 v = *reinterpret_cast<const uint2 *>(q);
+        o.r[0] = v.x;
+        o.r[1] = v.y;
+    } else {
+        const uint4 v = *reinterpret_cast<const uint4 *>(q);
+        o.r[0] = v.x;
+        o.r[1] = v.y;
+        o.r[2] = v.z;
+        if constexpr (R >= 4) o.r[3] = v.w;
+        if constexpr (RP == 8) {
+            const uint4 u = *reinterpret_cast<const uint4 *>(q + 4);
+            o.r[4] = u.x;
+            if constexpr (R >= 6) o.r[5] = u.y;
+        }
+    }
+}
+
+template <int NP>
+__global__ void __launch_bounds__(ID2_THREADS, NP <= 5 ? 2 : 1) k_identity2(const Identity2Params p)
+{
+    constexpr int RP = rest_words(NP);
+    constexpr int ROLE_W = role_words(NP);
+    constexpr int ROLE_B = role_bytes(NP);
+    constexpr int PST_B = id2_pstage_bytes(NP);
+    constexpr int TILE_B = tile2_bytes(NP);
+
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *s_planes = smem;
+    uint8_t *s_g = s_planes + ID2_PSTAGES * PST_B;
+    uint32_t *s_xch = reinterpret_cast<uint32_t *>(s_g + ID2_GSTAGES * ID2_GSTAGE_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(s_xch) + ID2_XCH_BYTES);
+    uint64_t *pfull = bars, *pempty = bars + ID2_PSTAGES;
+    uint64_t *gfull = pempty + ID2_PSTAGES, *gempty = gfull + ID2_GSTAGES;
+    uint64_t *accfull = gempty + ID2_GSTAGES, *accempty = accfull + 2;
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + ID2_NBARS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < ID2_PSTAGES; s++) {
+            mbar_init(&pfull[s], 1);
+            mbar_init(&pempty[s], ID2_MATH_WARPS);
+        }
+        for (int s = 0; s < ID2_GSTAGES; s++) {
+            mbar_init(&gfull[s], 1);
+            mbar_init(&gempty[s], 1);
+        }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&accfull[s], 1);
+            mbar_init(&accempty[s], ID2_MATH_WARPS);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 9) {  // TMEM: two 64-column int32 accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(s_tmem)),
+                     "r"((uint32_t)ID2_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    const int ngs = p.nchunks * G_STAGES_PER_CHUNK;
+
+    if (warp == 8) {
+        // ------------------------------ producer ------------------------------
+        if (lane == 0) {
+            int ps = 0, gs = 0;
+            uint32_t pph = 0, gph = 0;
+            const uint8_t *planes = reinterpret_cast<const uint8_t *>(p.planes);
+            for (long long t = p.tile_begin + blockIdx.x; t < p.tile_end; t += gridDim.x) {
+                int BI, bj;
+                tile_to_blocks2(t, p.nb, BI, bj);
+                const uint8_t *srcA0 = planes + (size_t)(2 * BI) * p.nchunks * TILE_B + p0_words() * 4;
+                const uint8_t *srcA1 = srcA0 + (size_t)p.nchunks * TILE_B;
+                const uint8_t *srcB = planes + (size_t)bj * p.nchunks * TILE_B;
+                for (int c = 0; c < p.nchunks; c++) {
+#pragma unroll
+                    for (int h = 0; h < G_STAGES_PER_CHUNK; h++) {
+                        const int s = c * G_STAGES_PER_CHUNK + h;
+                        const uint8_t *gsrc = p.gbytes + (size_t)s * p.nb2 * G_BLOCK_BYTES;
+                        mbar_wait(&gempty[gs], gph ^ 1u);
+                        mbar_arrive_expect_tx(&gfull[gs], ID2_GSTAGE_BYTES);
+                        uint8_t *gd = s_g + gs * ID2_GSTAGE_BYTES;
+                        bulk_copy_g2s(gd, gsrc + (size_t)(2 * BI) * G_BLOCK_BYTES, 2 * G_BLOCK_BYTES,
+                                      &gfull[gs]);
+                        bulk_copy_g2s(gd + 2 * G_BLOCK_BYTES, gsrc + (size_t)bj * G_BLOCK_BYTES,
+                                      G_BLOCK_BYTES, &gfull[gs]);
+                        if (++gs == ID2_GSTAGES) {
+                            gs = 0;
+                            gph ^= 1u;
+                        }
+                    }
+                    mbar_wait(&pempty[ps], pph ^ 1u);
+                    mbar_arrive_expect_tx(&pfull[ps], 3u * ROLE_B);
+                    uint8_t *pd = s_planes + ps * PST_B;
+                    bulk_copy_g2s(pd, srcA0 + (size_t)c * TILE_B, ROLE_B, &pfull[ps]);
+                    bulk_copy_g2s(pd + ROLE_B, srcA1 + (size_t)c * TILE_B, ROLE_B, &pfull[ps]);
+                    bulk_copy_g2s(pd + 2 * ROLE_B, srcB + (size_t)c * TILE_B, ROLE_B, &pfull[ps]);
+                    if (++ps == ID2_PSTAGES) {
+                        ps = 0;
+                        pph ^= 1u;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 9) {
+        // ------------------------------ MMA issuer ----------------------------
+        if (lane == 0) {
+            int gs = 0;
+            uint32_t gph = 0;
+            long long k = 0;
+            for (long long t = p.tile_begin + blockIdx.x; t < p.tile_end; t += gridDim.x, k++) {
+                const int buf = (int)(k & 1);
+                const uint32_t use_parity = (uint32_t)((k >> 1) & 1);
+                mbar_wait(&accempty[buf], use_parity ^ 1u);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(buf * RB);
+                for (int s = 0; s < ngs; s++) {
+                    mbar_wait(&gfull[gs], gph);
+                    tc_fence_after();
+                    const uint32_t a = smem_u32(s_g + gs * ID2_GSTAGE_BYTES);
+                    const uint32_t b = a + 2 * G_BLOCK_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < GS_COLS / 32; kk++) {
+                        umma_i8(d, umma_desc(a + kk * 256, 128, 512), umma_desc(b + kk * 256, 128, 512),
+                                (s | kk) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&gempty[gs]);
+                    if (++gs == ID2_GSTAGES) {
+                        gs = 0;
+                        gph ^= 1u;
+                    }
+                }
+                umma_commit(&accfull[buf]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------ math warps ----------------------------
+        const int wi = warp >> 1, wj = warp & 1;  // 4 (I) x 2 (J) warps of 32 x 32 pairs
+        const int li = lane & 3, lj = lane >> 2;
+        const int half = wi >> 1;                     // which block of the super-block
+        const int rowA0 = 32 * (wi & 1) + li;         // + 4*a, row inside that block
+        const int rowB0 = 32 * wj + lj;               // + 8*b
+        const unsigned long long n = (unsigned long long)p.nk;
+
+        int stage = 0;
+        uint32_t phase = 0;
+        long long k = 0;
+        for (long long t = p.tile_begin + blockIdx.x; t < p.tile_end; t += gridDim.x, k++) {
+            int BI, bj;
+            tile_to_blocks2(t, p.nb, BI, bj);
+
+            uint32_t hit[8][4];
+#pragma unroll
+            for (int a = 0; a < 8; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) hit[a][b] = 0;
+
+            for (int c = 0; c < p.nchunks; c++) {
+                mbar_wait(&pfull[stage], phase);
+                const uint32_t *sA = reinterpret_cast<const uint32_t *>(s_planes + stage * PST_B) +
+                                     half * ROLE_W;           // {rest, p0A}
+                const uint32_t *sB = reinterpret_cast<const uint32_t *>(s_planes + stage * PST_B) +
+                                     2 * ROLE_W;              // {p0B, rest}
+                const uint32_t *a_rest = sA, *a_p0 = sA + KC2 * RB * RP;
+                const uint32_t *b_p0 = sB, *b_rest = sB + p0_words();
+#pragma unroll 1
+                for (int kw = 0; kw < KC2; kw++) {
+                    Rest<NP> B[4];
+                    uint32_t B0[4];
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const int cell = kw * RB + rowB0 + 8 * b;
+                        load_rest<NP>(b_rest, cell, B[b]);
+                        B0[b] = b_p0[cell];
+                    }
+#pragma unroll
+                    for (int a = 0; a < 8; a++) {
+                        const int cell = kw * RB + rowA0 + 4 * a;
+                        Rest<NP> A;
+                        load_rest<NP>(a_rest, cell, A);
+                        const uint32_t A0 = a_p0[cell];
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            uint32_t d = A0 ^ B0[b];
+#pragma unroll
+                            for (int q = 0; q < NP - 2; q++)  // differ |= a.rq ^ b.rq
+                                d = lop3<0xF6>(d, A.r[q], B[b].r[q]);
+                            // equal = ~(differ | (a.rl ^ b.rl)), last plane
+                            const uint32_t e = lop3<0x09>(d, A.r[NP - 2], B[b].r[NP - 2]);
+                            hit[a][b] += __popc(e);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&pempty[stage]);
+                if (++stage == ID2_PSTAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+
+            // ------------------------------ epilogue --------------------------
+            // both-gap counts: TMEM lane = I row, column = J row.  Warp w may read
+            // lanes 32*(w%4)..+31; warps w and w+4 split the 64 columns.
+            const int buf = (int)(k & 1);
+            mbar_wait(&accfull[buf], (uint32_t)((k >> 1) & 1));
+            tc_fence_after();
+            uint32_t both[32];
+            tmem_ld32(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) +
+                          (uint32_t)(buf * RB + 32 * (warp >> 2)),
+                      both);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&accempty[buf]);
+
+            math_bar_sync();  // the previous tile's readers are done with s_xch
+            {
+                uint32_t *dstrow = s_xch + (32 * (warp & 3) + lane) * ID2_XS + 32 * (warp >> 2);
+#pragma unroll
+                for (int q = 0; q < 32; q += 4)
+                    *reinterpret_cast<uint4 *>(dstrow + q) =
+                        make_uint4(both[q], both[q + 1], both[q + 2], both[q + 3]);
+            }
+            math_bar_sync();
+
+#pragma unroll
+            for (int a = 0; a < 8; a++) {
+                const int il = 64 * half + rowA0 + 4 * a;  // row inside the super-block
+                const int i = BI * IB + il;
+                if (i >= p.nk) continue;
+                // offset of pair (i, i+1): i*n - i*(i+1)/2 - i - 1 + (i+1)
+                const unsigned long long row_base =
+                    (unsigned long long)i * n - ((unsigned long long)i * (i + 1)) / 2 - i - 1;
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int jl = rowB0 + 8 * b;
+                    const int j = bj * RB + jl;
+                    if (j >= p.nk || j <= i) continue;
+                    const unsigned long long pos = row_base + j;
+                    const int h = (int)hit[a][b];
+                    const int d = p.total_bits - (int)s_xch[il * ID2_XS + jl];
+                    const float v = d == 0 ? 0.0f : __fdiv_rn((float)h, (float)d);
+                    p.out[pos - p.out_base] = v;
+                    if (p.hit_out) p.hit_out[pos] = h;
+                    if (p.dst_out) p.dst_out[pos] = d;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"((uint32_t)ID2_TMEM_COLS)
+                     : "memory");
+    }
+}
+
+cudaError_t launch_identity2(int np, const Identity2Params &p, int num_sms, cudaStream_t stream)
+{
+    const long long ntiles = p.tile_end - p.tile_begin;
+    if (ntiles <= 0) return cudaSuccess;
+#define TCU_ID2_CASE(N)                                                                           \
+    case N: {                                                                                     \
+        const size_t smem = id2_smem_bytes(N);                                                    \
+        cudaError_t e = cudaFuncSetAttribute(k_identity2<N>,                                      \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                             (int)smem);                                          \
+        if (e != cudaSuccess) return e;                                                           \
+        int per_sm = 0;                                                                           \
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_identity2<N>, ID2_THREADS,   \
+                                                          smem);                                  \
+        if (e != cudaSuccess) return e;                                                           \
+        per_sm = std::max(1, std::min(per_sm, 2));                                                \
+        const int grid = (int)std::min<long long>(ntiles, (long long)num_sms * per_sm);           \
+        k_identity2<N><<<grid, ID2_THREADS, smem, stream>>>(p);                                   \
+        break;                                                                                    \
+    }
+    switch (np) {
+        TCU_ID2_CASE(3)
+        TCU_ID2_CASE(4)
+        TCU_ID2_CASE(5)
+        TCU_ID2_CASE(6)
+        TCU_ID2_CASE(7)
+    default: return cudaErrorInvalidValue;
+    }
+#undef TCU_ID2_CASE
+    return cudaGetLastError();
+}
+
+}  // namespace tcu

@@ -138,4 +138,116 @@ cudaError_t launch_pack_planes(const uint8_t *raw, size_t pitch, int ncol, const
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// v2 operand (layout: tcu_internal.cuh).  One CTA per (chunk, block): 64 rows x
+// 128 columns.  A warp takes one (row, 32-column word) at a time: each lane maps
+// one byte through the code LUT, the plane words are formed with warp ballots,
+// and the same lane writes its gap flag as one byte of the UMMA operand.
+// ---------------------------------------------------------------------------
+template <int NP>
+__global__ void __launch_bounds__(256) k_pack_planes2(const uint8_t *__restrict__ raw, size_t pitch,
+                                                      int ncol, const int *__restrict__ kept_rows,
+                                                      int nk, const uint8_t *__restrict__ col_drop,
+                                                      const uint8_t *__restrict__ lut256,
+                                                      int nb2, int nchunks,
+                                                      uint32_t *__restrict__ planes,
+                                                      uint8_t *__restrict__ gbytes)
+{
+    constexpr int RP = rest_words(NP);
+    constexpr int TW = tile2_words(NP);
+    constexpr uint32_t GAP_BITS = (1u << NP) - 2u;  // p0 = 0, rest = 1..1
+
+    __shared__ __align__(16) uint32_t tile[TW];
+    __shared__ __align__(16) uint8_t gsm[G_STAGES_PER_CHUNK * G_BLOCK_BYTES];
+    __shared__ uint8_t lut[256];
+
+    const int chunk = blockIdx.x;
+    const int block = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    lut[threadIdx.x] = lut256[threadIdx.x];
+    if (RP > NP - 1) {  // padding words of the rest group must be defined
+        for (int i = threadIdx.x; i < TW; i += 256) tile[i] = 0;
+    }
+    __syncthreads();
+
+    uint32_t *p0b = tile;
+    uint32_t *rest = tile + p0_words();
+    uint32_t *p0a = rest + KC2 * RB * RP;
+
+    for (int r = warp; r < RB; r += 8) {
+        const int ki = block * RB + r;
+        const bool row_ok = ki < nk;
+        const uint8_t *src = row_ok ? raw + (size_t)kept_rows[ki] * pitch : nullptr;
+#pragma unroll
+        for (int kw = 0; kw < KC2; kw++) {
+            const int col = (chunk * KC2 + kw) * 32 + lane;
+            uint32_t code = GAP_BITS;
+            uint32_t gap = 1;
+            if (row_ok && col < ncol && !col_drop[col]) {
+                const uint8_t c = lut[src[col]];
+                if (c != CODE_GAP) {
+                    code = c;
+                    gap = 0;
+                }
+            }
+            const uint32_t g = __ballot_sync(0xffffffffu, gap);
+            uint32_t mine = 0;
+#pragma unroll
+            for (int p = 0; p < NP; p++) {
+                const uint32_t w = __ballot_sync(0xffffffffu, (code >> p) & 1u);
+                if (lane == p) mine = w;
+            }
+            const int cell = kw * RB + r;
+            if (lane == 0) {
+                p0b[cell] = mine;
+                p0a[cell] = mine | g;
+            } else if (lane < NP) {
+                rest[cell * RP + lane - 1] = mine;
+            }
+            // gap byte: stage (kw / 2), column within the stage (kw % 2) * 32 + lane
+            const int c64 = (kw & 1) * 32 + lane;
+            gsm[(kw >> 1) * G_BLOCK_BYTES + (r >> 3) * 512 + (c64 >> 4) * 128 + (r & 7) * 16 +
+                (c64 & 15)] = (uint8_t)gap;
+        }
+    }
+    __syncthreads();
+
+    uint4 *dst = reinterpret_cast<uint4 *>(planes + ((size_t)block * nchunks + chunk) * TW);
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(tile);
+    for (int i = threadIdx.x; i < TW / 4; i += 256) dst[i] = s4[i];
+    const uint4 *g4 = reinterpret_cast<const uint4 *>(gsm);
+#pragma unroll
+    for (int s = 0; s < G_STAGES_PER_CHUNK; s++) {
+        uint4 *gd = reinterpret_cast<uint4 *>(
+            gbytes + ((size_t)(chunk * G_STAGES_PER_CHUNK + s) * nb2 + block) * G_BLOCK_BYTES);
+        for (int i = threadIdx.x; i < G_BLOCK_BYTES / 16; i += 256)
+            gd[i] = g4[s * (G_BLOCK_BYTES / 16) + i];
+    }
+}
+
+cudaError_t launch_pack_planes2(const uint8_t *raw, size_t pitch, int ncol, const int *kept_rows,
+                                int nk, const uint8_t *col_drop, const uint8_t *lut256, int np,
+                                int nb2, int nchunks, uint32_t *planes, uint8_t *gbytes,
+                                cudaStream_t stream)
+{
+    if (nb2 == 0 || nchunks == 0) return cudaSuccess;
+    dim3 grid(nchunks, nb2);
+#define TCU_PACK2_CASE(N)                                                                        \
+    case N:                                                                                      \
+        k_pack_planes2<N><<<grid, 256, 0, stream>>>(raw, pitch, ncol, kept_rows, nk, col_drop,   \
+                                                    lut256, nb2, nchunks, planes, gbytes);       \
+        break;
+    switch (np) {
+        TCU_PACK2_CASE(3)
+        TCU_PACK2_CASE(4)
+        TCU_PACK2_CASE(5)
+        TCU_PACK2_CASE(6)
+        TCU_PACK2_CASE(7)
+    default: return cudaErrorInvalidValue;
+    }
+#undef TCU_PACK2_CASE
+    return cudaGetLastError();
+}
+
 }  // namespace tcu

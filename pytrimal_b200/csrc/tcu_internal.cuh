@@ -62,6 +62,69 @@ struct IdentityParams {
     int total_bits;          // nchunks * KC * 32
 };
 
+// ---------------------------------------------------------------------------
+// Layout of the v2 identity operand (identity2.cu: hits on the integer pipes,
+// both-gap counts on the tensor cores)
+//
+// Rows are grouped in blocks of RB = 64; a tile of the pair matrix is one I
+// super-block (two consecutive blocks, 128 rows: the MMA's M) against one J
+// block (64 rows: N).  Columns are grouped in chunks of KC2 = 4 words (128
+// columns).
+//
+// planes   [block][chunk]{ p0B[kw][row] | rest[kw][row][RP] | p0A[kw][row] }
+//          NP code bit-planes per (row, 32-column word); plane 0 is stored
+//          twice: p0A = p0 | gap for rows used on the I side, p0B = p0 for the
+//          J side.  The gap class carries the code 2^NP-2 (p0 = 0, rest = 1..1)
+//          so  (a.p0A ^ b.p0B) | (a.r ^ b.r)...  is 1 wherever either side is a
+//          gap: gap|gap differ in plane 0, gap|residue in the rest planes.
+//          The I side copies {rest, p0A} (one contiguous run), the J side
+//          {p0B, rest}: NP+... words per row reach shared memory, no gap plane.
+// gbytes   [kstage][block]{ [rowgroup 8][kchunk 4][row 8][16 bytes] }
+//          the gap indicator as one u8 per column, 64 columns per k-stage, in
+//          the tcgen05 K-major no-swizzle canonical layout (8x16-byte core
+//          matrices; leading-dimension byte offset 128 between the 16-column
+//          kchunks, stride byte offset 512 between 8-row groups), so that
+//          both(i,j) = sum_k g_i(k) g_j(k) is a kind::i8 UMMA straight from a
+//          1-D bulk copy.  Two consecutive blocks are contiguous (the A operand
+//          of a super-block is one 8 KB copy).
+// Padding rows/columns and masked columns are gaps in every row, so
+//          dst = total_bits - both.
+// ---------------------------------------------------------------------------
+constexpr int IB = 2 * RB;        // rows per I super-block
+constexpr int KC2 = 4;            // 32-column words per plane chunk (128 columns)
+constexpr int GS_COLS = 64;       // columns per gbytes k-stage
+constexpr int G_BLOCK_BYTES = RB * GS_COLS;
+constexpr int G_STAGES_PER_CHUNK = KC2 * 32 / GS_COLS;
+
+__host__ __device__ constexpr int rest_words(int np) { return np - 1 <= 2 ? 2 : (np - 1 <= 4 ? 4 : 8); }
+__host__ __device__ constexpr int p0_words() { return KC2 * RB; }
+__host__ __device__ constexpr int tile2_words(int np) { return KC2 * RB * (2 + rest_words(np)); }
+__host__ __device__ constexpr int tile2_bytes(int np) { return tile2_words(np) * 4; }
+__host__ __device__ constexpr int role_words(int np) { return KC2 * RB * (1 + rest_words(np)); }
+__host__ __device__ constexpr int role_bytes(int np) { return role_words(np) * 4; }
+
+struct Identity2Params {
+    const uint32_t *planes;  // v2 plane tiles
+    const uint8_t *gbytes;   // gap indicator bytes, UMMA canonical layout
+    float *out;              // identities, element 0 = packed offset out_base
+    int *hit_out;            // optional, absolute packed offsets
+    int *dst_out;            // optional
+    unsigned long long out_base;
+    long long tile_begin;    // linear tile range [begin, end), see tiles_before2()
+    long long tile_end;
+    int nb;                  // 64-row blocks holding kept rows
+    int nb2;                 // blocks allocated (even)
+    int nchunks;             // 128-column chunks
+    int nk;                  // kept rows
+    int total_bits;          // nchunks * 128
+};
+
+// tiles in super-block rows < sb: each super-block BI pairs with J blocks 2*BI .. nb-1
+__host__ __device__ inline long long tiles_before2(long long sb, long long nb)
+{
+    return sb * nb - sb * (sb - 1);
+}
+
 // launchers (each enqueues on `stream` and returns the launch status)
 cudaError_t launch_byte_presence(const uint8_t *raw, int nseq, int ncol, size_t pitch,
                                  unsigned int *present256, cudaStream_t stream);
@@ -69,6 +132,11 @@ cudaError_t launch_pack_planes(const uint8_t *raw, size_t pitch, int ncol, const
                                int nk, const uint8_t *col_drop, const uint8_t *lut256, int np,
                                int nb, int nchunks, uint32_t *planes, cudaStream_t stream);
 cudaError_t launch_identity(int np, const IdentityParams &p, int num_sms, cudaStream_t stream);
+cudaError_t launch_pack_planes2(const uint8_t *raw, size_t pitch, int ncol, const int *kept_rows,
+                                int nk, const uint8_t *col_drop, const uint8_t *lut256, int np,
+                                int nb2, int nchunks, uint32_t *planes, uint8_t *gbytes,
+                                cudaStream_t stream);
+cudaError_t launch_identity2(int np, const Identity2Params &p, int num_sms, cudaStream_t stream);
 cudaError_t launch_identity_bytes(const uint8_t *raw, size_t pitch, int ncol, const int *kept_rows,
                                   int nk, const uint8_t *col_drop, uint8_t indet, float *out,
                                   int *hit_out, int *dst_out, cudaStream_t stream);

@@ -220,15 +220,16 @@ def test_identity_row_band_matches_full(gpu, port):
     import ctypes as C
     import torch
     from pytrimal_b200.synthetic import synthetic_msa
-    m = synthetic_msa(300, 700, 5)
+    m = synthetic_msa(600, 700, 5)
     oi = port.identity(m, X)
     lib = gpu.load()
+    R = lib.tcu_identity_band_rows()
     with gpu.DeviceAlignment(m) as d:
         nk = d.identity_prepare(X)
         nb = lib.tcu_identity_row_blocks(nk)
         out = torch.full((nk * (nk - 1) // 2,), -1.0, dtype=torch.float32, device="cuda:0")
         for b0, b1 in [(0, 2), (2, 3), (3, nb)]:
-            off = lib.tcu_identity_row_offset(nk, 64 * b0)
+            off = lib.tcu_identity_row_offset(nk, R * b0)
             d.identity_device(b0, b1, out.data_ptr() + 4 * off)
         d.sync()
         got = out.cpu().numpy()

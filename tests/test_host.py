@@ -48,6 +48,8 @@ def test_row_offset_and_blocks_match_python(lib):
     from pytrimal_b200 import sharding
     for n in [0, 1, 2, 63, 64, 65, 1000, 50000, 100000]:
         assert lib.tcu_identity_row_blocks(n) == sharding.row_blocks(n)
+        for b in [0, 1, 2, sharding.row_blocks(n) // 2, sharding.row_blocks(n), sharding.row_blocks(n) + 3]:
+            assert lib.tcu_identity_tiles_before(n, b) == sharding.tiles_before(b, n), (n, b)
         for i in [0, 1, 63, 64, n // 2, n - 2, n - 1, n, n + 5]:
             assert lib.tcu_identity_row_offset(n, i) == sharding.row_offset(n, i), (n, i)
     n = 1000
@@ -56,19 +58,22 @@ def test_row_offset_and_blocks_match_python(lib):
         assert sharding.row_offset(n, i) == pos
         pos += n - 1 - i
     assert sharding.row_offset(n, n - 1) == n * (n - 1) // 2
+    assert lib.tcu_identity_band_rows() == sharding.ROW_BLOCK
 
 
 def test_band_partition_balanced_and_covering():
     from pytrimal_b200.sharding import band_partition, band_slice, row_blocks, tiles_before
     for n in [100, 4097, 50000, 100000]:
         nb = row_blocks(n)
+        nj = (n + 63) // 64
         for world in [1, 2, 3, 4, 8]:
-            b = band_partition(nb, world)
+            b = band_partition(n, world)
             assert b[0] == 0 and b[-1] == nb and all(x <= y for x, y in zip(b, b[1:]))
-            counts = [tiles_before(b[g + 1], nb) - tiles_before(b[g], nb) for g in range(world)]
-            assert sum(counts) == nb * (nb + 1) // 2
+            counts = [tiles_before(b[g + 1], n) - tiles_before(b[g], n) for g in range(world)]
+            # block B meets the 64-row column blocks 2B .. nj-1
+            assert sum(counts) == sum(nj - 2 * B for B in range(nb))
             if nb >= 16 * world:
-                assert max(counts) <= 1.05 * sum(counts) / world + nb
+                assert max(counts) <= 1.05 * sum(counts) / world + nj
             total = 0
             for g in range(world):
                 off, cnt = band_slice(n, b, g)

@@ -31,7 +31,7 @@ def _worker(rank, world, port, n, L, tmpdir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     m = random_msa(np.random.default_rng(3), n, L)
     full = oracle.Port().identity(m, ord("X"))
-    bounds = band_partition(row_blocks(n), world)
+    bounds = band_partition(n, world)
     off, cnt = band_slice(n, bounds, rank)
     mine = torch.from_numpy(full[off:off + cnt].copy())
     sizes = [band_slice(n, bounds, g)[1] for g in range(world)]
@@ -50,7 +50,7 @@ def _worker(rank, world, port, n, L, tmpdir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n", [130, 257])
+@pytest.mark.parametrize("n", [130, 257, 700])
 def test_two_rank_bands_rebuild_full_array(tmp_path, n):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), n, 90, str(tmp_path)), nprocs=world, join=True)
