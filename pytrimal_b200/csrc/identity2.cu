@@ -415,11 +415,11 @@ cudaError_t launch_identity2(int np, const Identity2Params &p, int num_sms, cuda
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                              (int)smem);                                          \
         if (e != cudaSuccess) return e;                                                           \
-        int per_sm = 0;                                                                           \
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_identity2<N>, ID2_THREADS,   \
-                                                          smem);                                  \
+        e = cudaFuncSetAttribute(k_identity2<N>, cudaFuncAttributePreferredSharedMemoryCarveout,  \
+                                 cudaSharedmemCarveoutMaxShared);                                 \
         if (e != cudaSuccess) return e;                                                           \
-        per_sm = std::max(1, std::min(per_sm, 2));                                                \
+        /* 228 KB per SM, 1 KB reserved per CTA: two CTAs when both fit */                        \
+        const int per_sm = 2 * (smem + 1024) <= 228 * 1024 ? 2 : 1;                               \
         const int grid = (int)std::min<long long>(ntiles, (long long)num_sms * per_sm);           \
         k_identity2<N><<<grid, ID2_THREADS, smem, stream>>>(p);                                   \
         break;                                                                                    \
