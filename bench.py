@@ -317,10 +317,11 @@ def main():
             "roofline": {
                 "bound": "tensor", "achieved": achieved_tops, "peak": peak_tops, "unit": "TFLOP/s",
                 "frac": achieved_tops / peak_tops, "traffic": None,
-                "kernel": "tcu::k_identity<5>", "kernel_ms": kernel_ms_max, "pack_ms": pack_ms,
+                "kernel": "tcu::k_identity2<5,true>", "kernel_ms": kernel_ms_max, "pack_ms": pack_ms,
                 "note": "algorithmic int8 tensor ops = 42 per pair-column (SURVEY 8d); peak = 2 x "
-                        "bf16 dense, " + peaks["source"] + "; the kernel itself runs on the "
-                        "LOP3/POPC integer pipes (bit-plane formulation)",
+                        "bf16 dense, " + peaks["source"] + "; the kernel counts hits on "
+                        "the LOP3/POPC integer pipes (bit-plane formulation, 5 LOP3 per 32 "
+                        "pair-columns) and the both-gap counts with tcgen05 kind::i8 UMMAs",
             },
         }
         if world == 1 and not args.no_cpu_baseline:

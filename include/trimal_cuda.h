@@ -76,6 +76,12 @@ int tcu_msa_create_strided(const uint8_t *data, int nseq, int ncol, size_t strid
 
 void tcu_msa_destroy(tcu_msa *msa);
 
+/*
+ * The library keeps the largest freed identity buffer per device and its pinned
+ * staging buffers for reuse by later handles; this returns them to the driver.
+ */
+void tcu_release_cached_memory(void);
+
 int tcu_msa_nseq(const tcu_msa *msa);
 int tcu_msa_ncol(const tcu_msa *msa);
 

@@ -62,6 +62,7 @@ PROTOTYPES = {
     "tcu_msa_create_strided": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int,
                                          C.POINTER(_h)]),
     "tcu_msa_destroy": (None, [_h]),
+    "tcu_release_cached_memory": (None, []),
     "tcu_msa_nseq": (C.c_int, [_h]),
     "tcu_msa_ncol": (C.c_int, [_h]),
     "tcu_gaps": (C.c_int, [_h, _i32p, _i32p, _i32p, _i32p]),

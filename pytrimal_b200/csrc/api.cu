@@ -115,6 +115,74 @@ void stage_release(void *p)
 }  // namespace
 
 // ---------------------------------------------------------------------------
+// device buffer cache: the packed identity array is the one multi-GB allocation
+// (5 GB at 50 000 rows); cudaMalloc / cudaFree of it cost ~10 ms per call, so the
+// largest freed one is kept per device for the next handle
+// (tcu_release_cached_memory() returns it to the driver).
+// ---------------------------------------------------------------------------
+namespace {
+struct DevSlot {
+    void *ptr = nullptr;
+    size_t cap = 0;
+};
+std::mutex g_dev_cache_mutex;
+DevSlot g_dev_cache[64];
+
+void *dev_cache_take(int device, size_t need, size_t *cap)
+{
+    std::lock_guard<std::mutex> lk(g_dev_cache_mutex);
+    DevSlot &s = g_dev_cache[device & 63];
+    if (s.ptr && s.cap >= need && s.cap <= 2 * need + (64u << 20)) {
+        void *p = s.ptr;
+        *cap = s.cap;
+        s = DevSlot{};
+        return p;
+    }
+    return nullptr;
+}
+void dev_cache_give(int device, void *ptr, size_t cap)
+{
+    if (!ptr) return;
+    void *drop = ptr;
+    {
+        std::lock_guard<std::mutex> lk(g_dev_cache_mutex);
+        DevSlot &s = g_dev_cache[device & 63];
+        if (cap >= (16u << 20) && cap > s.cap) {
+            drop = s.ptr;
+            s.ptr = ptr;
+            s.cap = cap;
+        }
+    }
+    if (drop) cudaFree(drop);
+}
+}  // namespace
+
+extern "C" void tcu_release_cached_memory(void)
+{
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (int d = 0; d < 64; d++) {
+        void *p = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(g_dev_cache_mutex);
+            p = g_dev_cache[d].ptr;
+            g_dev_cache[d] = DevSlot{};
+        }
+        if (p) {
+            cudaSetDevice(d);
+            cudaFree(p);
+        }
+    }
+    cudaSetDevice(cur);
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mutex);
+        for (void *p : g_pool) cudaFreeHost(p);
+        g_pool.clear();
+    }
+    cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // handle
 // ---------------------------------------------------------------------------
 struct tcu_msa {
@@ -133,7 +201,6 @@ struct tcu_msa {
     bool prepared = false;
     int np = 0, nk = 0, nb = 0, nchunks = 0;
     int nsb = 0, nb2 = 0;     // v2: 128-row super-blocks, allocated 64-row blocks (even)
-    bool use_v1 = false;      // TCU_IDENTITY_IMPL=v1: the integer-pipe-only kernel (A/B timing)
     uint32_t *d_planes = nullptr;
     size_t planes_cap = 0;
     uint8_t *d_gbytes = nullptr;
@@ -152,7 +219,10 @@ struct tcu_msa {
     void *d_scratch = nullptr;
     size_t scratch_cap = 0;
 
+    cudaStream_t copy_stream = nullptr;       // D2H of finished sub-bands, overlapping the kernel
+    std::vector<cudaEvent_t> band_done;       // one per sub-band (no timing)
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t cev[2] = {nullptr, nullptr};  // first / last D2H on copy_stream
     tcu_timings timings{};
     bool pending_device_timing = false;  // ev[2]..ev[3] bracket an async tcu_identity_device
 };
@@ -167,6 +237,21 @@ static int ensure(void **p, size_t *cap, size_t need)
     CK(cudaMalloc(p, need));
     *cap = need;
     return TCU_OK;
+}
+
+static int ensure_ident(tcu_msa *m, size_t need)
+{
+    if (m->ident_cap >= need && m->d_ident) return TCU_OK;
+    dev_cache_give(m->device, m->d_ident, m->ident_cap);
+    m->d_ident = nullptr;
+    m->ident_cap = 0;
+    size_t cap = 0;
+    if (void *p = dev_cache_take(m->device, need, &cap)) {
+        m->d_ident = (float *)p;
+        m->ident_cap = cap;
+        return TCU_OK;
+    }
+    return ensure((void **)&m->d_ident, &m->ident_cap, need);
 }
 
 static float ev_ms(cudaEvent_t a, cudaEvent_t b)
@@ -203,7 +288,9 @@ static int msa_alloc(int nseq, int ncol, int device, tcu_msa **out)
     m->pitch = ((size_t)ncol + 127) / 128 * 128;
     if (m->pitch == 0) m->pitch = 128;
     cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventCreate(&m->ev[i]);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreate(&m->cev[i]);
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_raw, std::max<size_t>(1, (size_t)nseq) * m->pitch);
     if (e != cudaSuccess) {
         tcu_msa_destroy(m);
@@ -305,17 +392,23 @@ extern "C" void tcu_msa_destroy(tcu_msa *m)
     if (!m) return;
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
+    if (m->copy_stream) cudaStreamSynchronize(m->copy_stream);
     cudaFree(m->d_raw);
     cudaFree(m->d_planes);
     cudaFree(m->d_gbytes);
     cudaFree(m->d_kept_rows);
     cudaFree(m->d_col_drop);
     cudaFree(m->d_lut);
-    cudaFree(m->d_ident);
+    dev_cache_give(m->device, m->d_ident, m->ident_cap);
     cudaFree(m->d_scratch);
     for (auto &e : m->ev)
         if (e) cudaEventDestroy(e);
+    for (auto &e : m->cev)
+        if (e) cudaEventDestroy(e);
+    for (auto &e : m->band_done)
+        if (e) cudaEventDestroy(e);
     if (m->stream) cudaStreamDestroy(m->stream);
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     cudaGetLastError();
     delete m;
 }
@@ -419,8 +512,6 @@ extern "C" size_t tcu_identity_row_offset(int kept_rows, int i)
     return r * n - r * (r + 1) / 2;
 }
 
-static long long tiles_before(int b, int nb) { return (long long)b * nb - (long long)b * (b - 1) / 2; }
-
 extern "C" int tcu_identity_prepare(tcu_msa *m, const int *save_seq, const int *save_res,
                                     uint8_t indet, int *kept_rows_out)
 {
@@ -471,11 +562,7 @@ extern "C" int tcu_identity_prepare(tcu_msa *m, const int *save_seq, const int *
     m->nb = (m->nk + RB - 1) / RB;
     m->nsb = (m->nk + IB - 1) / IB;
     m->nb2 = 2 * m->nsb;
-    {
-        const char *impl = getenv("TCU_IDENTITY_IMPL");
-        m->use_v1 = impl && strcmp(impl, "v1") == 0;
-    }
-    m->nchunks = m->use_v1 ? (L + KC * 32 - 1) / (KC * 32) : (L + KC2 * 32 - 1) / (KC2 * 32);
+    m->nchunks = (L + KC2 * 32 - 1) / (KC2 * 32);
     m->prepared_indet = indet;
 
     if (!m->d_lut) CK(cudaMalloc((void **)&m->d_lut, 256));
@@ -488,23 +575,14 @@ extern "C" int tcu_identity_prepare(tcu_msa *m, const int *save_seq, const int *
     if (L) CK(cudaMemcpyAsync(m->d_col_drop, drop.data(), L, cudaMemcpyHostToDevice, m->stream));
     CK(cudaStreamSynchronize(m->stream));  // the host vectors go out of scope
 
-    int rc;
-    if (m->use_v1) {
-        rc = ensure((void **)&m->d_planes, &m->planes_cap, (size_t)m->nb * m->nchunks * tile_bytes(np));
-        if (rc != TCU_OK) return rc;
-        CK(cudaEventRecord(m->ev[1], m->stream));
-        CK(launch_pack_planes(m->d_raw, m->pitch, L, m->d_kept_rows, m->nk, m->d_col_drop, m->d_lut,
-                              np, m->nb, m->nchunks, m->d_planes, m->stream));
-    } else {
-        rc = ensure((void **)&m->d_planes, &m->planes_cap, (size_t)m->nb2 * m->nchunks * tile2_bytes(np));
-        if (rc != TCU_OK) return rc;
-        rc = ensure((void **)&m->d_gbytes, &m->gbytes_cap,
-                    (size_t)m->nb2 * m->nchunks * G_STAGES_PER_CHUNK * G_BLOCK_BYTES);
-        if (rc != TCU_OK) return rc;
-        CK(cudaEventRecord(m->ev[1], m->stream));
-        CK(launch_pack_planes2(m->d_raw, m->pitch, L, m->d_kept_rows, m->nk, m->d_col_drop, m->d_lut,
-                               np, m->nb2, m->nchunks, m->d_planes, m->d_gbytes, m->stream));
-    }
+    int rc = ensure((void **)&m->d_planes, &m->planes_cap, (size_t)m->nb2 * m->nchunks * tile2_bytes(np));
+    if (rc != TCU_OK) return rc;
+    rc = ensure((void **)&m->d_gbytes, &m->gbytes_cap,
+                (size_t)m->nb2 * m->nchunks * G_STAGES_PER_CHUNK * G_BLOCK_BYTES);
+    if (rc != TCU_OK) return rc;
+    CK(cudaEventRecord(m->ev[1], m->stream));
+    CK(launch_pack_planes(m->d_raw, m->pitch, L, m->d_kept_rows, m->nk, m->d_col_drop, m->d_lut, np,
+                          m->nb2, m->nchunks, m->d_planes, m->d_gbytes, m->stream));
     CK(cudaEventRecord(m->ev[2], m->stream));
     if (m->nb && m->nchunks) m->timings.kernel_launches++;
     m->prepared = true;
@@ -517,40 +595,75 @@ static int identity_launch(tcu_msa *m, int sb_begin, int sb_end, float *d_out, i
                            int *d_dst)
 {
     if (m->nchunks == 0 || sb_end <= sb_begin) return TCU_OK;
-    if (m->use_v1) {
-        IdentityParams p{};
-        p.planes = m->d_planes;
-        p.out = d_out;
-        p.hit_out = d_hit;
-        p.dst_out = d_dst;
-        p.nb = m->nb;
-        p.nchunks = m->nchunks;
-        p.nk = m->nk;
-        p.total_bits = m->nchunks * KC * 32;
-        p.tile_begin = tiles_before(std::min(2 * sb_begin, m->nb), m->nb);
-        p.tile_end = tiles_before(std::min(2 * sb_end, m->nb), m->nb);
-        p.out_base = tcu_identity_row_offset(m->nk, sb_begin * IB);
-        if (p.tile_end <= p.tile_begin) return TCU_OK;
-        CK(launch_identity(m->np, p, m->num_sms, m->stream));
-    } else {
-        Identity2Params p{};
-        p.planes = m->d_planes;
-        p.gbytes = m->d_gbytes;
-        p.out = d_out;
-        p.hit_out = d_hit;
-        p.dst_out = d_dst;
-        p.nb = m->nb;
-        p.nb2 = m->nb2;
-        p.nchunks = m->nchunks;
-        p.nk = m->nk;
-        p.total_bits = m->nchunks * KC2 * 32;
-        p.tile_begin = tiles_before2(sb_begin, m->nb);
-        p.tile_end = tiles_before2(sb_end, m->nb);
-        p.out_base = tcu_identity_row_offset(m->nk, sb_begin * IB);
-        if (p.tile_end <= p.tile_begin) return TCU_OK;
-        CK(launch_identity2(m->np, p, m->num_sms, m->stream));
-    }
+    Identity2Params p{};
+    p.planes = m->d_planes;
+    p.gbytes = m->d_gbytes;
+    p.out = d_out;
+    p.hit_out = d_hit;
+    p.dst_out = d_dst;
+    p.nb = m->nb;
+    p.nb2 = m->nb2;
+    p.nchunks = m->nchunks;
+    p.nk = m->nk;
+    p.total_bits = m->nchunks * KC2 * 32;
+    p.tile_begin = tiles_before2(sb_begin, m->nb);
+    p.tile_end = tiles_before2(sb_end, m->nb);
+    p.out_base = tcu_identity_row_offset(m->nk, sb_begin * IB);
+    if (p.tile_end <= p.tile_begin) return TCU_OK;
+    CK(launch_identity2(m->np, p, m->num_sms, m->stream));
     m->timings.kernel_launches++;
+    return TCU_OK;
+}
+
+// Identity of super-blocks [sb_begin, sb_end) into d_out (element 0 = packed offset of
+// row sb_begin * IB) and, when `host` is given, on into host memory: the range is cut
+// into sub-bands of equal work; the kernel of sub-band s+1 runs while sub-band s
+// crosses PCIe on the copy stream.  ev[3] marks the end of the last kernel; cev[0..1]
+// bracket the copies.  Returns with both streams idle when `host` is given.
+static int identity_pipeline(tcu_msa *m, int sb_begin, int sb_end, float *d_out, float *host,
+                             int *d_hit, int *d_dst)
+{
+    constexpr int MAX_SUB = 16;
+    const long long t0 = tiles_before2(sb_begin, m->nb), t1 = tiles_before2(sb_end, m->nb);
+    // sub-bands only pay off when each still fills the GPU for several waves
+    int nsub = host ? (int)std::min<long long>(MAX_SUB, (t1 - t0) / (8LL * 2 * m->num_sms)) : 1;
+    nsub = std::max(1, std::min(nsub, sb_end - sb_begin));
+    while ((int)m->band_done.size() < nsub) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        m->band_done.push_back(e);
+    }
+    const size_t base = tcu_identity_row_offset(m->nk, sb_begin * IB);
+    int b0 = sb_begin;
+    for (int s = 0; s < nsub; s++) {
+        int b1 = sb_end;
+        if (s + 1 < nsub) {
+            const long long target = t0 + (t1 - t0) * (s + 1) / nsub;
+            b1 = b0;
+            while (b1 < sb_end && tiles_before2(b1, m->nb) < target) b1++;
+        }
+        const size_t lo = tcu_identity_row_offset(m->nk, b0 * IB);
+        const size_t hi = tcu_identity_row_offset(m->nk, std::min(b1 * IB, m->nk));
+        if (b1 > b0) {
+            int rc = identity_launch(m, b0, b1, d_out + (lo - base), d_hit, d_dst);
+            if (rc != TCU_OK) return rc;
+        }
+        if (s + 1 == nsub) CK(cudaEventRecord(m->ev[3], m->stream));
+        if (host && hi > lo) {
+            CK(cudaEventRecord(m->band_done[s], m->stream));
+            CK(cudaStreamWaitEvent(m->copy_stream, m->band_done[s], 0));
+            if (s == 0) CK(cudaEventRecord(m->cev[0], m->copy_stream));
+            CK(cudaMemcpyAsync(host + (lo - base), d_out + (lo - base), (hi - lo) * sizeof(float),
+                               cudaMemcpyDeviceToHost, m->copy_stream));
+        }
+        b0 = b1;
+    }
+    if (host) {
+        CK(cudaEventRecord(m->cev[1], m->copy_stream));
+        CK(cudaStreamSynchronize(m->copy_stream));
+        CK(cudaStreamSynchronize(m->stream));
+        m->timings.d2h_ms = ev_ms(m->cev[0], m->cev[1]);
+    }
     return TCU_OK;
 }
 
@@ -592,19 +705,13 @@ extern "C" int tcu_identity_band(tcu_msa *m, const int *save_seq, const int *sav
         CK(cudaStreamSynchronize(m->stream));
         return TCU_OK;
     }
-    rc = ensure((void **)&m->d_ident, &m->ident_cap, count * sizeof(float));
+    rc = ensure_ident(m, count * sizeof(float));
     if (rc != TCU_OK) return rc;
-    rc = identity_launch(m, block_begin, block_end, m->d_ident, nullptr, nullptr);
+    rc = identity_pipeline(m, block_begin, block_end, m->d_ident, identities, nullptr, nullptr);
     if (rc != TCU_OK) return rc;
-    CK(cudaEventRecord(m->ev[3], m->stream));
-    rc = download(m, identities, m->d_ident, count * sizeof(float));
-    if (rc != TCU_OK) return rc;
-    CK(cudaEventRecord(m->ev[4], m->stream));
-    CK(cudaStreamSynchronize(m->stream));
     m->timings.h2d_ms = ev_ms(m->ev[0], m->ev[1]);
     m->timings.pack_ms = ev_ms(m->ev[1], m->ev[2]);
-    m->timings.kernel_ms = ev_ms(m->ev[2], m->ev[3]);
-    m->timings.d2h_ms = ev_ms(m->ev[3], m->ev[4]);
+    m->timings.kernel_ms = ev_ms(m->ev[2], m->ev[3]);  // overlaps the copies
     return TCU_OK;
 }
 
@@ -624,7 +731,7 @@ static int identity_host(tcu_msa *m, const int *save_seq, const int *save_res, u
         CK(cudaStreamSynchronize(m->stream));
         return TCU_OK;
     }
-    rc = ensure((void **)&m->d_ident, &m->ident_cap, npairs * sizeof(float));
+    rc = ensure_ident(m, npairs * sizeof(float));
     if (rc != TCU_OK) return rc;
     int *d_hit = nullptr, *d_dst = nullptr;
     if (hit_out || dst_out) {
@@ -638,12 +745,13 @@ static int identity_host(tcu_msa *m, const int *save_seq, const int *save_res, u
         CK(launch_identity_bytes(m->d_raw, m->pitch, m->ncol, m->d_kept_rows, m->nk, m->d_col_drop,
                                  indet, m->d_ident, d_hit, d_dst, m->stream));
         m->timings.kernel_launches++;
+        CK(cudaEventRecord(m->ev[3], m->stream));
+        if (identities) rc = download(m, identities, m->d_ident, npairs * sizeof(float));
     } else {
-        rc = identity_launch(m, 0, m->nsb, m->d_ident, d_hit, d_dst);
-        if (rc != TCU_OK) return rc;
+        rc = identity_pipeline(m, 0, m->nsb, m->d_ident, identities, d_hit, d_dst);
     }
-    CK(cudaEventRecord(m->ev[3], m->stream));
-    if (identities) rc = download(m, identities, m->d_ident, npairs * sizeof(float));
+    if (rc != TCU_OK) return rc;
+    const float pipelined_d2h_ms = m->timings.d2h_ms;
     if (rc == TCU_OK && hit_out) rc = download(m, hit_out, d_hit, npairs * sizeof(int));
     if (rc == TCU_OK && dst_out) rc = download(m, dst_out, d_dst, npairs * sizeof(int));
     if (rc != TCU_OK) return rc;
@@ -652,10 +760,10 @@ static int identity_host(tcu_msa *m, const int *save_seq, const int *save_res, u
     m->timings.h2d_ms = ev_ms(m->ev[0], m->ev[1]);
     m->timings.pack_ms = ev_ms(m->ev[1], m->ev[2]);
     m->timings.kernel_ms = ev_ms(m->ev[2], m->ev[3]);
-    m->timings.d2h_ms = ev_ms(m->ev[3], m->ev[4]);
+    m->timings.d2h_ms = pipelined_d2h_ms + ev_ms(m->ev[3], m->ev[4]);
     m->ident_full = (m->nk == m->nseq);
     if (!keep_on_device) {
-        cudaFree(m->d_ident);
+        dev_cache_give(m->device, m->d_ident, m->ident_cap);
         m->d_ident = nullptr;
         m->ident_cap = 0;
         m->ident_full = false;
@@ -737,7 +845,7 @@ extern "C" int tcu_similarity(tcu_msa *m, uint8_t indet, const float *dist, int 
     if (L == 0) return TCU_OK;
 
     if (identities) {
-        int rc = ensure((void **)&m->d_ident, &m->ident_cap, std::max<size_t>(npairs, 1) * sizeof(float));
+        int rc = ensure_ident(m, std::max<size_t>(npairs, 1) * sizeof(float));
         if (rc != TCU_OK) return rc;
         CK(cudaMemcpyAsync(m->d_ident, identities, npairs * sizeof(float), cudaMemcpyHostToDevice,
                            m->stream));

@@ -24,8 +24,10 @@
 //
 // One CTA (two per SM) walks 128 x 64 tiles of the pair matrix:
 //   warps 0-7  math: 32 x 32 pairs per warp, 8 x 4 per thread, plane chunks of
-//              128 columns from a 3-stage ring; epilogue: TMEM -> registers ->
-//              shared-memory transpose -> divide -> store
+//              128 columns from a 3-stage ring; the popcount of a pair trails its
+//              LOP3 chain by one row-group and the add by another (the in-order warp
+//              never waits on the XU pipe); epilogue: TMEM -> registers ->
+//              warp-private shared-memory transpose -> divide -> store
 //   warp 8     producer: 1-D bulk async copies (TMA unit) of plane chunks and of
 //              the 64-column gap-byte stages, mbarrier complete_tx
 //   warp 9     MMA issuer: one thread, two UMMAs per gap-byte stage, tcgen05.commit
@@ -38,12 +40,12 @@ namespace tcu {
 
 constexpr int ID2_MATH_WARPS = 8;
 constexpr int ID2_MATH_THREADS = ID2_MATH_WARPS * 32;
-constexpr int ID2_THREADS = ID2_MATH_THREADS + 64;
+constexpr int ID2_THREADS = ID2_MATH_THREADS + 64;  // + producer warp + MMA warp
 constexpr int ID2_PSTAGES = 3;                               // plane-chunk ring
 constexpr int ID2_GSTAGES = 2;                               // gap-byte ring
 constexpr int ID2_GSTAGE_BYTES = (IB + RB) * GS_COLS;         // 12288
-constexpr int ID2_XS = 68;                                   // exchange row stride (words)
-constexpr int ID2_XCH_BYTES = IB * ID2_XS * 4;
+constexpr int ID2_XS = 36;                                   // exchange row stride (words)
+constexpr int ID2_XCH_BYTES = ID2_MATH_WARPS * 32 * ID2_XS * 4;  // one 32 x 32 patch per warp
 constexpr int ID2_TMEM_COLS = 2 * RB;                         // two int32 accumulators of N = 64
 constexpr int ID2_NBARS = 2 * ID2_PSTAGES + 2 * ID2_GSTAGES + 4;
 
@@ -106,11 +108,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ void math_bar_sync()
-{
-    asm volatile("bar.sync 1, %0;" ::"n"(ID2_MATH_THREADS) : "memory");
-}
-
 // linear tile index -> (I super-block, J block): super-block BI owns the tiles
 // (BI, 2*BI .. nb-1), tiles_before2(BI, nb) of them precede it
 __device__ __forceinline__ void tile_to_blocks2(long long t, int nb, int &BI, int &bj)
@@ -125,17 +122,22 @@ __device__ __forceinline__ void tile_to_blocks2(long long t, int nb, int &BI, in
     bj = 2 * b + (int)(t - tiles_before2(b, nb));
 }
 
+
+// One row's plane words for one 32-column word: p0 (the role's copy of plane 0)
+// and the NP-1 "rest" planes.
 template <int NP>
-struct Rest {
+struct Row {
+    uint32_t p0;
     uint32_t r[NP - 1];
 };
 
 template <int NP>
-__device__ __forceinline__ void load_rest(const uint32_t *rest, int cell, Rest<NP> &o)
+__device__ __forceinline__ void load_row(const uint32_t *p0, const uint32_t *rest, int cell, Row<NP> &o)
 {
     constexpr int R = NP - 1;
     constexpr int RP = rest_words(NP);
     const uint32_t *q = rest + cell * RP;
+    o.p0 = p0[cell];
     if constexpr (RP == 2) {
         const uint2 v = *reinterpret_cast<const uint2 *>(q);
         o.r[0] = v.x;
@@ -154,7 +156,41 @@ __device__ __forceinline__ void load_rest(const uint32_t *rest, int cell, Rest<N
     }
 }
 
+// ---- order-pinned forms (asm volatile keeps the relative order through NVVM; ptxas
+// still schedules, but starts from this order) ----
+__device__ __forceinline__ uint32_t v_xor(uint32_t a, uint32_t b)
+{
+    uint32_t d;
+    asm volatile("xor.b32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+template <int LUT>
+__device__ __forceinline__ uint32_t v_lop3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm volatile("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return d;
+}
+__device__ __forceinline__ uint32_t v_popc(uint32_t a)
+{
+    uint32_t d;
+    asm volatile("popc.b32 %0, %1;" : "=r"(d) : "r"(a));
+    return d;
+}
+// equal columns of one pair in one 32-column word: NP LOP3
 template <int NP>
+__device__ __forceinline__ uint32_t v_equal_bits(const Row<NP> &a, const Row<NP> &b)
+{
+    uint32_t d = v_xor(a.p0, b.p0);
+#pragma unroll
+    for (int q = 0; q < NP - 2; q++) d = v_lop3<0xF6>(d, a.r[q], b.r[q]);
+    return v_lop3<0x09>(d, a.r[NP - 2], b.r[NP - 2]);
+}
+
+// PACKED: two 16-bit hit counters per register (J rows b and b+2 of a thread share one;
+// the upper one is fed by an IMAD with 65536 on the otherwise idle FMA pipe), valid
+// while a count cannot reach 65536, i.e. total_bits < 65536.  Frees 16 registers.
+template <int NP, bool PACKED>
 __global__ void __launch_bounds__(ID2_THREADS, NP <= 5 ? 2 : 1) k_identity2(const Identity2Params p)
 {
     constexpr int RP = rest_words(NP);
@@ -221,7 +257,7 @@ __global__ void __launch_bounds__(ID2_THREADS, NP <= 5 ? 2 : 1) k_identity2(cons
                     for (int h = 0; h < G_STAGES_PER_CHUNK; h++) {
                         const int s = c * G_STAGES_PER_CHUNK + h;
                         const uint8_t *gsrc = p.gbytes + (size_t)s * p.nb2 * G_BLOCK_BYTES;
-                        mbar_wait(&gempty[gs], gph ^ 1u);
+                        mbar_wait_parked(&gempty[gs], gph ^ 1u);
                         mbar_arrive_expect_tx(&gfull[gs], ID2_GSTAGE_BYTES);
                         uint8_t *gd = s_g + gs * ID2_GSTAGE_BYTES;
                         bulk_copy_g2s(gd, gsrc + (size_t)(2 * BI) * G_BLOCK_BYTES, 2 * G_BLOCK_BYTES,
@@ -233,7 +269,7 @@ __global__ void __launch_bounds__(ID2_THREADS, NP <= 5 ? 2 : 1) k_identity2(cons
                             gph ^= 1u;
                         }
                     }
-                    mbar_wait(&pempty[ps], pph ^ 1u);
+                    mbar_wait_parked(&pempty[ps], pph ^ 1u);
                     mbar_arrive_expect_tx(&pfull[ps], 3u * ROLE_B);
                     uint8_t *pd = s_planes + ps * PST_B;
                     bulk_copy_g2s(pd, srcA0 + (size_t)c * TILE_B, ROLE_B, &pfull[ps]);
@@ -256,11 +292,11 @@ __global__ void __launch_bounds__(ID2_THREADS, NP <= 5 ? 2 : 1) k_identity2(cons
             for (long long t = p.tile_begin + blockIdx.x; t < p.tile_end; t += gridDim.x, k++) {
                 const int buf = (int)(k & 1);
                 const uint32_t use_parity = (uint32_t)((k >> 1) & 1);
-                mbar_wait(&accempty[buf], use_parity ^ 1u);
+                mbar_wait_parked(&accempty[buf], use_parity ^ 1u);
                 tc_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)(buf * RB);
                 for (int s = 0; s < ngs; s++) {
-                    mbar_wait(&gfull[gs], gph);
+                    mbar_wait_parked(&gfull[gs], gph);
                     tc_fence_after();
                     const uint32_t a = smem_u32(s_g + gs * ID2_GSTAGE_BYTES);
                     const uint32_t b = a + 2 * G_BLOCK_BYTES;
@@ -281,7 +317,9 @@ __global__ void __launch_bounds__(ID2_THREADS, NP <= 5 ? 2 : 1) k_identity2(cons
         __syncwarp();
     } else {
         // ------------------------------ math warps ----------------------------
-        const int wi = warp >> 1, wj = warp & 1;  // 4 (I) x 2 (J) warps of 32 x 32 pairs
+        // 4 (I) x 2 (J) warps of 32 x 32 pairs; wi = warp % 4 is also the TMEM lane
+        // quadrant this warp may read, so its both-gap counts are exactly its own patch
+        const int wi = warp & 3, wj = warp >> 2;
         const int li = lane & 3, lj = lane >> 2;
         const int half = wi >> 1;                     // which block of the super-block
         const int rowA0 = 32 * (wi & 1) + li;         // + 4*a, row inside that block
@@ -295,46 +333,45 @@ __global__ void __launch_bounds__(ID2_THREADS, NP <= 5 ? 2 : 1) k_identity2(cons
             int BI, bj;
             tile_to_blocks2(t, p.nb, BI, bj);
 
-            uint32_t hit[8][4];
+            constexpr int HB = PACKED ? 2 : 4;
+            uint32_t hit[8][HB];
 #pragma unroll
             for (int a = 0; a < 8; a++)
 #pragma unroll
-                for (int b = 0; b < 4; b++) hit[a][b] = 0;
+                for (int b = 0; b < HB; b++) hit[a][b] = 0;
+            auto add_hit = [&](int a, int b, uint32_t x) {
+                if (!PACKED) hit[a][b] += x;
+                else if (b < 2) hit[a][b] += x;
+                else hit[a][b - 2] = x * 65536u + hit[a][b - 2];
+            };
 
+            uint32_t ep[4] = {0, 0, 0, 0}, pc[4] = {0, 0, 0, 0};
+            // per word: hold the four J rows, stream the eight I rows (double-buffered);
+            // the popcount of a pair trails its LOP3 chain by one row-group and the add
+            // by another one, so neither the XU latency nor its queue stalls the in-order
+            // warp (ep / pc are the two pipeline registers per J row).
             for (int c = 0; c < p.nchunks; c++) {
                 mbar_wait(&pfull[stage], phase);
-                const uint32_t *sA = reinterpret_cast<const uint32_t *>(s_planes + stage * PST_B) +
-                                     half * ROLE_W;           // {rest, p0A}
-                const uint32_t *sB = reinterpret_cast<const uint32_t *>(s_planes + stage * PST_B) +
-                                     2 * ROLE_W;              // {p0B, rest}
-                const uint32_t *a_rest = sA, *a_p0 = sA + KC2 * RB * RP;
-                const uint32_t *b_p0 = sB, *b_rest = sB + p0_words();
+                const uint32_t *base = reinterpret_cast<const uint32_t *>(s_planes + stage * PST_B);
+                const uint32_t *a_rest = base + half * ROLE_W, *a_p0 = a_rest + KC2 * RB * RP;
+                const uint32_t *b_p0 = base + 2 * ROLE_W, *b_rest = b_p0 + p0_words();
 #pragma unroll 1
                 for (int kw = 0; kw < KC2; kw++) {
-                    Rest<NP> B[4];
-                    uint32_t B0[4];
+                    Row<NP> B[4], A, An;
 #pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        const int cell = kw * RB + rowB0 + 8 * b;
-                        load_rest<NP>(b_rest, cell, B[b]);
-                        B0[b] = b_p0[cell];
-                    }
+                    for (int b = 0; b < 4; b++) load_row<NP>(b_p0, b_rest, kw * RB + rowB0 + 8 * b, B[b]);
+                    load_row<NP>(a_p0, a_rest, kw * RB + rowA0, A);
 #pragma unroll
                     for (int a = 0; a < 8; a++) {
-                        const int cell = kw * RB + rowA0 + 4 * a;
-                        Rest<NP> A;
-                        load_rest<NP>(a_rest, cell, A);
-                        const uint32_t A0 = a_p0[cell];
+                        if (a < 7) load_row<NP>(a_p0, a_rest, kw * RB + rowA0 + 4 * (a + 1), An);
 #pragma unroll
                         for (int b = 0; b < 4; b++) {
-                            uint32_t d = A0 ^ B0[b];
-#pragma unroll
-                            for (int q = 0; q < NP - 2; q++)  // differ |= a.rq ^ b.rq
-                                d = lop3<0xF6>(d, A.r[q], B[b].r[q]);
-                            // equal = ~(differ | (a.rl ^ b.rl)), last plane
-                            const uint32_t e = lop3<0x09>(d, A.r[NP - 2], B[b].r[NP - 2]);
-                            hit[a][b] += __popc(e);
+                            const uint32_t e = v_equal_bits<NP>(A, B[b]);
+                            add_hit((a + 6) & 7, b, pc[b]);
+                            pc[b] = v_popc(ep[b]);
+                            ep[b] = e;
                         }
+                        A = An;
                     }
                 }
                 __syncwarp();
@@ -344,30 +381,39 @@ __global__ void __launch_bounds__(ID2_THREADS, NP <= 5 ? 2 : 1) k_identity2(cons
                     phase ^= 1u;
                 }
             }
+#pragma unroll
+            for (int b = 0; b < 4; b++) {  // drain the popcount pipeline
+                add_hit(6, b, pc[b]);
+                add_hit(7, b, __popc(ep[b]));
+            }
 
             // ------------------------------ epilogue --------------------------
-            // both-gap counts: TMEM lane = I row, column = J row.  Warp w may read
-            // lanes 32*(w%4)..+31; warps w and w+4 split the 64 columns.
+            // both-gap counts: TMEM lane = I row, column = J row; the warp's patch is
+            // lanes 32*wi..+31, columns 32*wj..+31 of the tile's accumulator.  Lane r
+            // receives row r; a warp-private shared-memory patch turns that into the
+            // (li, lj) ownership of the hit counters -- no CTA-wide barrier.
             const int buf = (int)(k & 1);
             mbar_wait(&accfull[buf], (uint32_t)((k >> 1) & 1));
             tc_fence_after();
             uint32_t both[32];
-            tmem_ld32(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) +
-                          (uint32_t)(buf * RB + 32 * (warp >> 2)),
-                      both);
+            tmem_ld32(tmem_base + ((uint32_t)(32 * wi) << 16) + (uint32_t)(buf * RB + 32 * wj), both);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&accempty[buf]);
+            // not needed for correctness (patches are warp-private): re-aligns the eight
+            // warps once per tile so that all of them consume the same ring stage and
+            // the other stages stay prefetched
+            asm volatile("bar.sync 1, %0;" ::"n"(ID2_MATH_THREADS) : "memory");
 
-            math_bar_sync();  // the previous tile's readers are done with s_xch
+            uint32_t *patch = s_xch + warp * (32 * ID2_XS);
             {
-                uint32_t *dstrow = s_xch + (32 * (warp & 3) + lane) * ID2_XS + 32 * (warp >> 2);
+                uint32_t *dstrow = patch + lane * ID2_XS;
 #pragma unroll
                 for (int q = 0; q < 32; q += 4)
                     *reinterpret_cast<uint4 *>(dstrow + q) =
                         make_uint4(both[q], both[q + 1], both[q + 2], both[q + 3]);
             }
-            math_bar_sync();
+            __syncwarp();
 
 #pragma unroll
             for (int a = 0; a < 8; a++) {
@@ -383,14 +429,16 @@ __global__ void __launch_bounds__(ID2_THREADS, NP <= 5 ? 2 : 1) k_identity2(cons
                     const int j = bj * RB + jl;
                     if (j >= p.nk || j <= i) continue;
                     const unsigned long long pos = row_base + j;
-                    const int h = (int)hit[a][b];
-                    const int d = p.total_bits - (int)s_xch[il * ID2_XS + jl];
+                    const int h = !PACKED ? (int)hit[a][b]
+                                          : (b < 2 ? (int)(hit[a][b] & 0xFFFFu) : (int)(hit[a][b - 2] >> 16));
+                    const int d = p.total_bits - (int)patch[(li + 4 * a) * ID2_XS + lj + 8 * b];
                     const float v = d == 0 ? 0.0f : __fdiv_rn((float)h, (float)d);
                     p.out[pos - p.out_base] = v;
                     if (p.hit_out) p.hit_out[pos] = h;
                     if (p.dst_out) p.dst_out[pos] = d;
                 }
             }
+            __syncwarp();  // the patch is rewritten by the next tile
         }
     }
 
@@ -408,22 +456,26 @@ cudaError_t launch_identity2(int np, const Identity2Params &p, int num_sms, cuda
 {
     const long long ntiles = p.tile_end - p.tile_begin;
     if (ntiles <= 0) return cudaSuccess;
-#define TCU_ID2_CASE(N)                                                                           \
-    case N: {                                                                                     \
+#define TCU_ID2_CASE_P(N, P)                                                                      \
+    {                                                                                             \
         const size_t smem = id2_smem_bytes(N);                                                    \
-        cudaError_t e = cudaFuncSetAttribute(k_identity2<N>,                                      \
+        cudaError_t e = cudaFuncSetAttribute(k_identity2<N, P>,                                   \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                              (int)smem);                                          \
         if (e != cudaSuccess) return e;                                                           \
-        e = cudaFuncSetAttribute(k_identity2<N>, cudaFuncAttributePreferredSharedMemoryCarveout,  \
+        e = cudaFuncSetAttribute(k_identity2<N, P>,                                               \
+                                 cudaFuncAttributePreferredSharedMemoryCarveout,                  \
                                  cudaSharedmemCarveoutMaxShared);                                 \
         if (e != cudaSuccess) return e;                                                           \
         /* 228 KB per SM, 1 KB reserved per CTA: two CTAs when both fit */                        \
         const int per_sm = 2 * (smem + 1024) <= 228 * 1024 ? 2 : 1;                               \
         const int grid = (int)std::min<long long>(ntiles, (long long)num_sms * per_sm);           \
-        k_identity2<N><<<grid, ID2_THREADS, smem, stream>>>(p);                                   \
-        break;                                                                                    \
+        k_identity2<N, P><<<grid, ID2_THREADS, smem, stream>>>(p);                                \
     }
+#define TCU_ID2_CASE(N)                                                                           \
+    case N:                                                                                       \
+        if (p.total_bits < 65536) TCU_ID2_CASE_P(N, true) else TCU_ID2_CASE_P(N, false)           \
+        break;
     switch (np) {
         TCU_ID2_CASE(3)
         TCU_ID2_CASE(4)
@@ -433,6 +485,7 @@ cudaError_t launch_identity2(int np, const Identity2Params &p, int num_sms, cuda
     default: return cudaErrorInvalidValue;
     }
 #undef TCU_ID2_CASE
+#undef TCU_ID2_CASE_P
     return cudaGetLastError();
 }
 

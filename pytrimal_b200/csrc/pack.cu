@@ -48,104 +48,13 @@ cudaError_t launch_byte_presence(const uint8_t *raw, int nseq, int ncol, size_t 
 }
 
 // ---------------------------------------------------------------------------
-// One CTA per (chunk, row-block) tile.  A warp takes one (row, 32-column word)
-// at a time: each lane maps one byte through the code LUT and the W plane
-// words are formed with warp ballots, so the 32 bytes are read coalesced and
-// no thread ever shifts bits one by one.
-// ---------------------------------------------------------------------------
-template <int NP>
-__global__ void __launch_bounds__(256) k_pack_planes(const uint8_t *__restrict__ raw, size_t pitch,
-                                                     int ncol, const int *__restrict__ kept_rows,
-                                                     int nk, const uint8_t *__restrict__ col_drop,
-                                                     const uint8_t *__restrict__ lut256,
-                                                     int nchunks, uint32_t *__restrict__ planes)
-{
-    constexpr int W = NP + 1;
-    constexpr int G1 = group1_words(NP);
-    constexpr int WS = words_stored(NP);
-    constexpr int TW = tile_words(NP);
-    constexpr uint32_t GAP_BITS = (1u << NP) - 2u;  // p0 = 0, p1.. = 1
-
-    __shared__ __align__(16) uint32_t tile[TW];
-    __shared__ uint8_t lut[256];
-
-    const int chunk = blockIdx.x;
-    const int block = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    lut[threadIdx.x] = lut256[threadIdx.x];
-    if (G1 + 4 > W) {  // the padding word of group 1 must be defined
-        for (int i = threadIdx.x; i < TW; i += 256) tile[i] = 0;
-    }
-    __syncthreads();
-
-    for (int r = warp; r < RB; r += 8) {
-        const int ki = block * RB + r;
-        const bool row_ok = ki < nk;
-        const uint8_t *src = row_ok ? raw + (size_t)kept_rows[ki] * pitch : nullptr;
-#pragma unroll 2
-        for (int kw = 0; kw < KC; kw++) {
-            const int col = (chunk * KC + kw) * 32 + lane;
-            uint32_t code = GAP_BITS;
-            uint32_t gap = 1;
-            if (row_ok && col < ncol && !col_drop[col]) {
-                const uint8_t c = lut[src[col]];
-                if (c != CODE_GAP) {
-                    code = c;
-                    gap = 0;
-                }
-            }
-            uint32_t mine = __ballot_sync(0xffffffffu, gap);
-#pragma unroll
-            for (int p = 0; p < NP; p++) {
-                const uint32_t w = __ballot_sync(0xffffffffu, (code >> p) & 1u);
-                if (lane == p + 1) mine = w;
-            }
-            if (lane < W) {
-                const int base = kw * RB * WS;
-                const int off = lane < 4 ? base + r * 4 + lane : base + RB * 4 + r * G1 + (lane - 4);
-                tile[off] = mine;
-            }
-        }
-    }
-    __syncthreads();
-
-    uint4 *dst = reinterpret_cast<uint4 *>(planes + ((size_t)block * nchunks + chunk) * TW);
-    const uint4 *s4 = reinterpret_cast<const uint4 *>(tile);
-    for (int i = threadIdx.x; i < TW / 4; i += 256) dst[i] = s4[i];
-}
-
-cudaError_t launch_pack_planes(const uint8_t *raw, size_t pitch, int ncol, const int *kept_rows,
-                               int nk, const uint8_t *col_drop, const uint8_t *lut256, int np,
-                               int nb, int nchunks, uint32_t *planes, cudaStream_t stream)
-{
-    if (nb == 0 || nchunks == 0) return cudaSuccess;
-    dim3 grid(nchunks, nb);
-#define TCU_PACK_CASE(N)                                                                         \
-    case N:                                                                                      \
-        k_pack_planes<N><<<grid, 256, 0, stream>>>(raw, pitch, ncol, kept_rows, nk, col_drop,    \
-                                                   lut256, nchunks, planes);                     \
-        break;
-    switch (np) {
-        TCU_PACK_CASE(3)
-        TCU_PACK_CASE(4)
-        TCU_PACK_CASE(5)
-        TCU_PACK_CASE(6)
-        TCU_PACK_CASE(7)
-    default: return cudaErrorInvalidValue;
-    }
-#undef TCU_PACK_CASE
-    return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------
-// v2 operand (layout: tcu_internal.cuh).  One CTA per (chunk, block): 64 rows x
+// The identity operand (layout: tcu_internal.cuh).  One CTA per (chunk, block): 64 rows x
 // 128 columns.  A warp takes one (row, 32-column word) at a time: each lane maps
 // one byte through the code LUT, the plane words are formed with warp ballots,
 // and the same lane writes its gap flag as one byte of the UMMA operand.
 // ---------------------------------------------------------------------------
 template <int NP>
-__global__ void __launch_bounds__(256) k_pack_planes2(const uint8_t *__restrict__ raw, size_t pitch,
+__global__ void __launch_bounds__(256) k_pack_planes(const uint8_t *__restrict__ raw, size_t pitch,
                                                       int ncol, const int *__restrict__ kept_rows,
                                                       int nk, const uint8_t *__restrict__ col_drop,
                                                       const uint8_t *__restrict__ lut256,
@@ -226,27 +135,27 @@ __global__ void __launch_bounds__(256) k_pack_planes2(const uint8_t *__restrict_
     }
 }
 
-cudaError_t launch_pack_planes2(const uint8_t *raw, size_t pitch, int ncol, const int *kept_rows,
+cudaError_t launch_pack_planes(const uint8_t *raw, size_t pitch, int ncol, const int *kept_rows,
                                 int nk, const uint8_t *col_drop, const uint8_t *lut256, int np,
                                 int nb2, int nchunks, uint32_t *planes, uint8_t *gbytes,
                                 cudaStream_t stream)
 {
     if (nb2 == 0 || nchunks == 0) return cudaSuccess;
     dim3 grid(nchunks, nb2);
-#define TCU_PACK2_CASE(N)                                                                        \
+#define TCU_PACK_CASE(N)                                                                        \
     case N:                                                                                      \
-        k_pack_planes2<N><<<grid, 256, 0, stream>>>(raw, pitch, ncol, kept_rows, nk, col_drop,   \
+        k_pack_planes<N><<<grid, 256, 0, stream>>>(raw, pitch, ncol, kept_rows, nk, col_drop,   \
                                                     lut256, nb2, nchunks, planes, gbytes);       \
         break;
     switch (np) {
-        TCU_PACK2_CASE(3)
-        TCU_PACK2_CASE(4)
-        TCU_PACK2_CASE(5)
-        TCU_PACK2_CASE(6)
-        TCU_PACK2_CASE(7)
+        TCU_PACK_CASE(3)
+        TCU_PACK_CASE(4)
+        TCU_PACK_CASE(5)
+        TCU_PACK_CASE(6)
+        TCU_PACK_CASE(7)
     default: return cudaErrorInvalidValue;
     }
-#undef TCU_PACK2_CASE
+#undef TCU_PACK_CASE
     return cudaGetLastError();
 }
 

@@ -9,34 +9,7 @@
 
 namespace tcu {
 
-// ---------------------------------------------------------------------------
-// Packed layout of the identity operand ("bit-planes")
-//
-// The kept rows are renumbered 0..nk-1 and grouped into row-blocks of RB rows;
-// the columns are grouped into words of 32 and the words into chunks of KC.
-// One (row-block, chunk) TILE is stored contiguously so that a single 1-D
-// bulk async copy (cp.async.bulk, TMA unit) brings it into shared memory:
-//
-//     tile[kw][group][row][word]      kw < KC, row < RB
-//
-// For every (row, 32-column word) there are W = NP+1 words: word 0 is the
-// identity-gap mask g ('-' or indet, masked-out and padding columns, padding
-// rows); words 1..NP are the bits of a dense residue code (bit p of the code
-// of column c sits at bit c%32 of word 1+p).  Gap-class positions carry the
-// code 2^NP-2, residues use codes < 2^NP-2, so in the kernel
-//     differ = (a.p0 ^ (b.p0 | b.g)) | (a.p1 ^ b.p1) | ...
-// is 1 wherever either side is a gap or the bytes differ -- hits need no
-// separate gap test.  Words are split into group 0 (g,p0,p1,p2: one 16-byte
-// shared load) and group 1 (the rest, padded to 1, 2 or 4 words).
-// Tiles are ordered block-major: tile(b, c) at ((b * nchunks) + c) * TILE_BYTES.
-// ---------------------------------------------------------------------------
-constexpr int RB = 64;  // rows per row-block
-constexpr int KC = 8;   // 32-column words per chunk (256 columns)
-
-__host__ __device__ constexpr int group1_words(int np) { return np + 1 - 4 == 3 ? 4 : np + 1 - 4; }
-__host__ __device__ constexpr int words_stored(int np) { return 4 + group1_words(np); }
-__host__ __device__ constexpr int tile_words(int np) { return KC * RB * words_stored(np); }
-__host__ __device__ constexpr int tile_bytes(int np) { return tile_words(np) * 4; }
+constexpr int RB = 64;  // rows per row-block (J side of a tile, MMA N)
 
 constexpr int MIN_PLANES = 3;
 constexpr int MAX_PLANES = 7;
@@ -48,22 +21,9 @@ constexpr uint8_t SIM_INCORRECT = 0xFE;
 constexpr uint8_t SIM_UNDEFINED = 0xFD;
 constexpr int SIM_MAX_POS = 28;
 
-struct IdentityParams {
-    const uint32_t *planes;  // packed tiles
-    float *out;              // identities, element 0 = packed offset out_base
-    int *hit_out;            // optional, absolute packed offsets
-    int *dst_out;            // optional
-    unsigned long long out_base;
-    long long tile_begin;    // linear upper-triangular tile range [begin, end)
-    long long tile_end;
-    int nb;                  // number of row-blocks
-    int nchunks;             // chunks per row-block
-    int nk;                  // kept rows
-    int total_bits;          // nchunks * KC * 32
-};
 
 // ---------------------------------------------------------------------------
-// Layout of the v2 identity operand (identity2.cu: hits on the integer pipes,
+// Layout of the identity operand (identity2.cu: hits on the integer pipes,
 // both-gap counts on the tensor cores)
 //
 // Rows are grouped in blocks of RB = 64; a tile of the pair matrix is one I
@@ -130,12 +90,8 @@ cudaError_t launch_byte_presence(const uint8_t *raw, int nseq, int ncol, size_t 
                                  unsigned int *present256, cudaStream_t stream);
 cudaError_t launch_pack_planes(const uint8_t *raw, size_t pitch, int ncol, const int *kept_rows,
                                int nk, const uint8_t *col_drop, const uint8_t *lut256, int np,
-                               int nb, int nchunks, uint32_t *planes, cudaStream_t stream);
-cudaError_t launch_identity(int np, const IdentityParams &p, int num_sms, cudaStream_t stream);
-cudaError_t launch_pack_planes2(const uint8_t *raw, size_t pitch, int ncol, const int *kept_rows,
-                                int nk, const uint8_t *col_drop, const uint8_t *lut256, int np,
-                                int nb2, int nchunks, uint32_t *planes, uint8_t *gbytes,
-                                cudaStream_t stream);
+                               int nb2, int nchunks, uint32_t *planes, uint8_t *gbytes,
+                               cudaStream_t stream);
 cudaError_t launch_identity2(int np, const Identity2Params &p, int num_sms, cudaStream_t stream);
 cudaError_t launch_identity_bytes(const uint8_t *raw, size_t pitch, int ncol, const int *kept_rows,
                                   int nk, const uint8_t *col_drop, uint8_t indet, float *out,
@@ -193,6 +149,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "TCU_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
+        : "memory");
+}
+// Same wait with a suspend-time hint: the waiting thread is parked by the hardware
+// until the phase completes (or the hint, in ns, expires) instead of re-polling.
+// For the single-thread producer / MMA-issuer warps, whose polling would otherwise
+// take issue slots from the math warps of the same SM sub-partition.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "TCU_WAITP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+        "@P1 bra TCU_DONEP;\n"
+        "bra TCU_WAITP;\n"
+        "TCU_DONEP:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(0x989680u)
         : "memory");
 }
 __device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes,

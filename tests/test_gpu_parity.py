@@ -110,6 +110,46 @@ def test_identity_small_alphabets(gpu, port, alphabet, indet):
     assert (hit == oh).all() and (dst == od).all() and (bits(ident) == bits(oi)).all()
 
 
+@pytest.mark.parametrize("n,L", [(40, 65536), (130, 66000)])
+def test_identity_very_long_rows_unpacked_counters(gpu, port, n, L):
+    """>= 65536 columns: the kernel variant with 32-bit hit counters (the packed
+    16-bit pairs could overflow); also many k-stages of the both-gap UMMA."""
+    rng = np.random.default_rng(L + n)
+    m = random_msa(rng, n, L, gap=0.3)
+    m[: n // 2, : L // 2] = m[0, : L // 2]      # long identical stretches: hits > 32767
+    with gpu.DeviceAlignment(m) as d:
+        ident, hit, dst = d.identity(X, counts=True)
+    oi, oh, od = port.identity(m, X, counts=True)
+    assert hit.max() > 32767
+    assert (hit == oh).all() and (dst == od).all() and (bits(ident) == bits(oi)).all()
+
+
+@pytest.mark.parametrize("n,L", [(127, 129), (128, 128), (129, 127), (191, 64), (193, 65),
+                                 (600, 130), (1100, 70)])
+def test_identity_tile_edges(gpu, port, n, L):
+    """Row counts around the 128-row super-block / 64-row block edges and several
+    tiles per CTA (both TMEM accumulator buffers, ring wrap-around)."""
+    rng = np.random.default_rng(n * 31 + L)
+    m = random_msa(rng, n, L, gap=0.4)
+    with gpu.DeviceAlignment(m) as d:
+        ident, hit, dst = d.identity(X, counts=True)
+    oi, oh, od = port.identity(m, X, counts=True)
+    assert (hit == oh).all() and (dst == od).all() and (bits(ident) == bits(oi)).all()
+
+
+@pytest.mark.parametrize("nsym", [8, 14, 15, 30, 31, 62, 63, 100])
+def test_identity_plane_counts(gpu, port, nsym):
+    """Alphabets that need 4, 5, 6 and 7 code planes (2^NP - 2 residue codes)."""
+    rng = np.random.default_rng(nsym)
+    pool = bytes(b for b in range(33, 127) if b not in (ord("-"), X))[:nsym] if nsym <= 92 else \
+        bytes(b for b in range(33, 256) if b not in (ord("-"), X))[:nsym]
+    m = random_msa(rng, 140, 300, alphabet=pool)
+    with gpu.DeviceAlignment(m) as d:
+        ident, hit, dst = d.identity(X, counts=True)
+    oi, oh, od = port.identity(m, X, counts=True)
+    assert (hit == oh).all() and (dst == od).all() and (bits(ident) == bits(oi)).all()
+
+
 def test_identity_all_gap_pairs(gpu, port):
     """dst == 0 -> identity 0 (template.h:427-428)."""
     m = np.full((5, 70), ord("-"), np.uint8)

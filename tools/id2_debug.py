@@ -10,7 +10,7 @@ from pytrimal_b200.synthetic import synthetic_msa
 port = oracle.Port()
 X = ord("X")
 bad = 0
-for (n, L, seed) in [(6, 46, 1), (130, 90, 2), (300, 700, 3), (700, 1000, 4), (1500, 300, 5)]:
+for (n, L, seed) in [(6, 46, 1), (130, 90, 2), (300, 700, 3), (700, 1000, 4), (1500, 300, 5), (150, 66000, 6)]:
     m = synthetic_msa(n, L, seed)
     oi, oh, od = port.identity(m, X, counts=True)
     with pb.DeviceAlignment(m) as d:
