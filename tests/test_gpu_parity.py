@@ -116,7 +116,8 @@ def test_identity_very_long_rows_unpacked_counters(gpu, port, n, L):
     16-bit pairs could overflow); also many k-stages of the both-gap UMMA."""
     rng = np.random.default_rng(L + n)
     m = random_msa(rng, n, L, gap=0.3)
-    m[: n // 2, : L // 2] = m[0, : L // 2]      # long identical stretches: hits > 32767
+    # long identical gap-free stretches: hit counts beyond 16 bits' half range
+    m[: n // 2, : L // 2 + 100] = random_msa(rng, 1, L // 2 + 100, gap=0.0, indet=0.0)[0]
     with gpu.DeviceAlignment(m) as d:
         ident, hit, dst = d.identity(X, counts=True)
     oi, oh, od = port.identity(m, X, counts=True)
