@@ -869,10 +869,15 @@ extern "C" int tcu_similarity(tcu_msa *m, uint8_t indet, const float *dist, int 
     if (gaps)
         for (int k = 0; k < L; k++) skip[k] = (float)gaps[k] >= gap_threshold;
 
-    const size_t codes_bytes = (size_t)n * m->pitch;
+    const int npad = (n + 31) / 32 * 32;
+    const int ngroups = (int)(m->pitch >> 5);
+    const size_t codes_bytes = (size_t)ngroups * npad * 32;
     const size_t vec_bytes = ((size_t)L * sizeof(float) + 255) / 256 * 256;
     const size_t dist_bytes = 4096;
-    const size_t need = codes_bytes + 2 * vec_bytes + dist_bytes + m->pitch + 256 + 64;
+    const size_t skip_bytes = ((size_t)ngroups * (npad >> 5) * sizeof(uint32_t) + 255) / 256 * 256;
+    const size_t nb_bytes = ((size_t)ngroups * sizeof(unsigned long long) + 255) / 256 * 256;
+    const size_t need = codes_bytes + 2 * vec_bytes + dist_bytes + m->pitch + 256 + 64 + skip_bytes +
+                        nb_bytes;
     int rc = ensure(&m->d_scratch, &m->scratch_cap, need);
     if (rc != TCU_OK) return rc;
     uint8_t *base = (uint8_t *)m->d_scratch;
@@ -882,7 +887,9 @@ extern "C" int tcu_similarity(tcu_msa *m, uint8_t indet, const float *dist, int 
     uint8_t *d_skip = base + 2 * vec_bytes + dist_bytes;
     uint8_t *d_lut = d_skip + m->pitch;
     unsigned long long *d_err = (unsigned long long *)(d_lut + 256);
-    uint8_t *d_codes = (uint8_t *)(d_err + 8);
+    uint32_t *d_rowskip = (uint32_t *)(d_err + 8);
+    unsigned long long *d_nbatches = (unsigned long long *)((uint8_t *)d_rowskip + skip_bytes);
+    uint8_t *d_codes = (uint8_t *)d_nbatches + nb_bytes;
 
     const unsigned long long no_err = ~0ull;
     unsigned long long first_err = no_err;
@@ -894,13 +901,14 @@ extern "C" int tcu_similarity(tcu_msa *m, uint8_t indet, const float *dist, int 
     CK(cudaMemcpyAsync(d_lut, lut, 256, cudaMemcpyHostToDevice, m->stream));
     CK(cudaMemcpyAsync(d_err, &no_err, sizeof no_err, cudaMemcpyHostToDevice, m->stream));
     CK(cudaEventRecord(m->ev[1], m->stream));
-    CK(launch_sim_codes(m->d_raw, n, L, m->pitch, d_lut, d_skip, d_codes, d_err, m->stream));
+    CK(launch_sim_codes(m->d_raw, n, L, m->pitch, npad, d_lut, d_skip, d_codes, d_err, m->stream));
+    CK(launch_sim_rows(d_codes, n, npad, ngroups, d_rowskip, d_nbatches, m->stream));
     CK(cudaEventRecord(m->ev[2], m->stream));
     CK(cudaMemcpyAsync(&first_err, d_err, sizeof first_err, cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
     t.h2d_ms = ev_ms(m->ev[0], m->ev[1]);
     t.pack_ms = ev_ms(m->ev[1], m->ev[2]);
-    t.kernel_launches = n > 0 ? 1 : 0;
+    t.kernel_launches = n > 0 ? 2 : 0;
     if (first_err != no_err) {
         const int byte = (int)(first_err & 0xFF);
         const unsigned long long cell = first_err >> 8;
@@ -915,8 +923,8 @@ extern "C" int tcu_similarity(tcu_msa *m, uint8_t indet, const float *dist, int 
     }
 
     CK(cudaEventRecord(m->ev[2], m->stream));
-    CK(launch_similarity(d_codes, n, L, m->pitch, m->d_ident, d_dist, npos, d_skip, d_num, d_den,
-                         m->num_sms, m->stream));
+    CK(launch_similarity(d_codes, n, npad, L, m->d_ident, d_dist, npos, d_skip, d_rowskip,
+                         d_nbatches, 0, (L + 31) / 32, d_num, d_den, m->num_sms, m->stream));
     CK(cudaEventRecord(m->ev[3], m->stream));
     CK(cudaMemcpyAsync(num, d_num, (size_t)L * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
     CK(cudaMemcpyAsync(den, d_den, (size_t)L * sizeof(float), cudaMemcpyDeviceToHost, m->stream));

@@ -103,13 +103,16 @@ cudaError_t launch_spurious_rows(const uint8_t *raw, int nseq, int ncol, size_t 
                                  uint8_t indet, const int *cnt_gap, const int *cnt_indet,
                                  uint32_t ovrlap, uint8_t *col_flags, float *out,
                                  cudaStream_t stream);
-cudaError_t launch_sim_codes(const uint8_t *raw, int nseq, int ncol, size_t pitch,
-                             const uint8_t *lut256, const uint8_t *col_skip, uint8_t *codes,
+cudaError_t launch_sim_codes(const uint8_t *raw, int nseq, int ncol, size_t pitch, int npad,
+                             const uint8_t *lut256, const uint8_t *col_skip, uint8_t *codesT,
                              unsigned long long *first_error, cudaStream_t stream);
-cudaError_t launch_similarity(const uint8_t *codes, int nseq, int ncol, size_t pitch,
+cudaError_t launch_sim_rows(const uint8_t *codesT, int nseq, int npad, int ngroups,
+                            uint32_t *skipbits, unsigned long long *nbatches, cudaStream_t stream);
+cudaError_t launch_similarity(const uint8_t *codesT, int nseq, int npad, int ncol,
                               const float *identities, const float *dist, int npos,
-                              const uint8_t *col_skip, float *num, float *den, int num_sms,
-                              cudaStream_t stream);
+                              const uint8_t *col_skip, const uint32_t *skipbits,
+                              const unsigned long long *nbatches, int group_begin, int group_end,
+                              float *num, float *den, int num_sms, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------
 // PTX helpers: mbarrier + 1-D bulk async copy (TMA unit, SASS: UBLKCP)
@@ -150,6 +153,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
+}
+// One non-blocking probe (about 90 cycles until the result is usable): issue it early,
+// test the result later, fall back to mbar_wait when it is 0.
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok;
 }
 // Same wait with a suspend-time hint: the waiting thread is parked by the hardware
 // until the phase completes (or the hint, in ns, expires) instead of re-polling.
