@@ -49,7 +49,8 @@ typedef enum tcu_status {
     TCU_ERR_INVALID = -4,          /* bad argument                                     */
     TCU_ERR_INCORRECT_SYMBOL = -5, /* similarity: byte outside 'A'..'Z' (template.h:135-138) */
     TCU_ERR_UNDEFINED_SYMBOL = -6, /* similarity: letter without matrix row (:140-144)  */
-    TCU_ERR_STATE = -7             /* call order (e.g. similarity before identity)     */
+    TCU_ERR_STATE = -7,            /* call order (e.g. similarity before identity)     */
+    TCU_ERR_NCCL = -8              /* NCCL missing or a collective failed (*_all calls) */
 } tcu_status;
 
 typedef struct tcu_msa tcu_msa; /* opaque: one alignment resident on one GPU */
@@ -193,9 +194,54 @@ typedef struct tcu_timings {
     float kernel_ms;     /* the statistic's main kernel(s)                 */
     float d2h_ms;        /* device -> host copies                          */
     int kernel_launches; /* number of kernels launched by the call         */
+    float comm_ms;       /* NCCL collectives of the *_all calls            */
 } tcu_timings;
 
 int tcu_msa_timings(const tcu_msa *msa, tcu_timings *out);
+
+/* ---- several GPUs, one process per GPU --------------------------
+ * The reference has no multi-device path; this is the partition north_star
+ * asks for.  Every rank uploads the same alignment to its own GPU
+ * (tcu_msa_create), joins a communicator, and calls the same *_all function with
+ * the same arguments; each computes its share and the shares are exchanged with
+ * NCCL over NVLink, so every rank returns the complete result, bit-identical to
+ * the single-GPU call.  NCCL is looked up at run time (libnccl.so.2); without it
+ * these calls fail with TCU_ERR_NCCL and nothing else is affected.
+ *
+ *   identity   : row bands of the pair matrix with equal tile counts
+ *                (tcu_shard_blocks), all-gather of the bands -> full matrix on
+ *                every GPU (kept on the device for tcu_similarity_all)
+ *   similarity : 32-column groups (tcu_shard_range), all-gather of num / den
+ *   gaps       : row ranges, all-reduce (integer sum) of the column counts
+ *   spurious   : row ranges; all-reduce of the column composition counts, then
+ *                all-gather of the per-row ratios
+ */
+typedef struct tcu_comm tcu_comm;
+#define TCU_COMM_ID_BYTES 128
+
+/* Rank 0 creates the 128-byte rendezvous id (ncclGetUniqueId); the caller hands it to the
+ * other ranks by any means it has (torch.distributed, MPI, a file). */
+int tcu_comm_id(void *id);
+int tcu_comm_create(const void *id, int rank, int world, int device, tcu_comm **out);
+void tcu_comm_destroy(tcu_comm *comm);
+int tcu_comm_rank(const tcu_comm *comm);
+int tcu_comm_world(const tcu_comm *comm);
+
+/* Host-only partition helpers (no device needed). */
+int tcu_shard_range(int total, int granule, int rank, int world, int *begin, int *end);
+int tcu_shard_blocks(int kept_rows, int rank, int world, int *block_begin, int *block_end);
+
+/* identities (optional): kept_pairs floats on the host, the complete packed array. */
+int tcu_identity_all(tcu_msa *msa, tcu_comm *comm, const int *save_seq, const int *save_res,
+                     uint8_t indet, float *identities);
+/* Needs a preceding tcu_identity_all without masks (the device-resident matrix). */
+int tcu_similarity_all(tcu_msa *msa, tcu_comm *comm, uint8_t indet, const float *dist, int npos,
+                       const int *vhash, const int *gaps, float gap_threshold, float *num,
+                       float *den, float *mdk, int *err_col, int *err_row, int *err_byte);
+int tcu_gaps_all(tcu_msa *msa, tcu_comm *comm, const int *save_seq, int *gaps_in_column,
+                 int *num_cols_with_gaps, int *max_gaps);
+int tcu_spurious_all(tcu_msa *msa, tcu_comm *comm, uint8_t indet, uint32_t ovrlap,
+                     float *spurious);
 
 /* ---- test-only -------------------------------------------------------------
  * Same contract as tcu_identity (without keep_on_device), computed by a slow

@@ -20,6 +20,7 @@ TCU_ERR_INVALID = -4
 TCU_ERR_INCORRECT_SYMBOL = -5
 TCU_ERR_UNDEFINED_SYMBOL = -6
 TCU_ERR_STATE = -7
+TCU_ERR_NCCL = -8
 
 
 class TrimalCudaError(RuntimeError):
@@ -45,7 +46,7 @@ class SymbolError(ValueError):
 
 class Timings(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("pack_ms", C.c_float), ("kernel_ms", C.c_float),
-                ("d2h_ms", C.c_float), ("kernel_launches", C.c_int)]
+                ("d2h_ms", C.c_float), ("kernel_launches", C.c_int), ("comm_ms", C.c_float)]
 
 
 _u8p = C.POINTER(C.c_uint8)
@@ -81,6 +82,18 @@ PROTOTYPES = {
     "tcu_msa_stream": (C.c_void_p, [_h]),
     "tcu_msa_device": (C.c_int, [_h]),
     "tcu_msa_timings": (C.c_int, [_h, C.POINTER(Timings)]),
+    "tcu_comm_id": (C.c_int, [C.c_void_p]),
+    "tcu_comm_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(_h)]),
+    "tcu_comm_destroy": (None, [_h]),
+    "tcu_comm_rank": (C.c_int, [_h]),
+    "tcu_comm_world": (C.c_int, [_h]),
+    "tcu_shard_range": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _i32p]),
+    "tcu_shard_blocks": (C.c_int, [C.c_int, C.c_int, C.c_int, _i32p, _i32p]),
+    "tcu_identity_all": (C.c_int, [_h, _h, _i32p, _i32p, C.c_uint8, _f32p]),
+    "tcu_similarity_all": (C.c_int, [_h, _h, C.c_uint8, _f32p, C.c_int, _i32p, _i32p, C.c_float,
+                                     _f32p, _f32p, _f32p, _i32p, _i32p, _i32p]),
+    "tcu_gaps_all": (C.c_int, [_h, _h, _i32p, _i32p, _i32p, _i32p]),
+    "tcu_spurious_all": (C.c_int, [_h, _h, C.c_uint8, C.c_uint32, _f32p]),
     "tcu_debug_identity_bytes": (C.c_int, [_h, _i32p, _i32p, C.c_uint8, _f32p, _i32p, _i32p]),
 }
 

@@ -9,14 +9,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libtrimal_cuda.so")
 SOURCES = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cu")))
-HEADERS = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cuh"))) + [
+HEADERS = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cuh")) +
+                 glob.glob(os.path.join(HERE, "csrc", "*.h"))) + [
     os.path.join(ROOT, "include", "trimal_cuda.h")
 ]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-shared", "-ldl",
 ]
 
 

@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 
+#include "nccl_dyn.h"
 #include "tcu_internal.cuh"
 
 using namespace tcu;
@@ -264,6 +265,153 @@ static float ev_ms(cudaEvent_t a, cudaEvent_t b)
     return ms;
 }
 
+// ---------------------------------------------------------------------------
+// several GPUs, one process per GPU: a communicator is an NCCL communicator
+// bound to this rank's device.  Used by the *_all entry points only.
+// ---------------------------------------------------------------------------
+struct tcu_comm {
+    NcclComm comm = nullptr;
+    int rank = 0, world = 1, device = 0;
+};
+
+static int nccl_fail(int r, const char *what)
+{
+    const NcclApi &api = nccl_api();
+    return fail(TCU_ERR_NCCL, "%s: %s", what,
+                api.ok && api.GetErrorString ? api.GetErrorString(r) : api.why);
+}
+
+#define NK(call)                                                \
+    do {                                                        \
+        int r__ = (call);                                       \
+        if (r__ != NCCL_SUCCESS) return nccl_fail(r__, #call);  \
+    } while (0)
+
+static int comm_check(const tcu_msa *m, const tcu_comm *c)
+{
+    if (c && c->device != m->device)
+        return fail(TCU_ERR_INVALID, "communicator is bound to device %d, the alignment to %d",
+                    c->device, m->device);
+    return TCU_OK;
+}
+
+// Share of rank `rank` when `total` units are cut into `world` contiguous ranges whose
+// boundaries are multiples of `granule`: [begin, end), empty for surplus ranks.
+extern "C" int tcu_shard_range(int total, int granule, int rank, int world, int *begin, int *end)
+{
+    if (total < 0 || granule < 1 || world < 1 || rank < 0 || rank >= world || !begin || !end)
+        return fail(TCU_ERR_INVALID, "bad shard arguments");
+    const long long units = ((long long)total + granule - 1) / granule;
+    const long long lo = units * rank / world, hi = units * (rank + 1) / world;
+    *begin = (int)std::min<long long>(lo * granule, total);
+    *end = (int)std::min<long long>(hi * granule, total);
+    return TCU_OK;
+}
+
+// Row-blocks [begin, end) of the pair matrix for rank `rank`: contiguous bands holding
+// (nearly) the same number of 128x64 tiles, i.e. the same work.
+extern "C" int tcu_shard_blocks(int kept_rows, int rank, int world, int *block_begin,
+                                int *block_end)
+{
+    if (kept_rows < 0 || world < 1 || rank < 0 || rank >= world || !block_begin || !block_end)
+        return fail(TCU_ERR_INVALID, "bad shard arguments");
+    const int nb = (kept_rows + RB - 1) / RB, nsb = (kept_rows + IB - 1) / IB;
+    const long long total = tiles_before2(nsb, nb);
+    auto bound = [&](int g) {
+        if (g <= 0) return 0;
+        if (g >= world) return nsb;
+        // first block whose preceding work reaches g/world of the total
+        int lo = 0, hi = nsb;
+        while (lo < hi) {
+            const int mid = (lo + hi) / 2;
+            if (tiles_before2(mid, nb) * world < total * g) lo = mid + 1;
+            else hi = mid;
+        }
+        return lo;
+    };
+    *block_begin = bound(rank);
+    *block_end = bound(rank + 1);
+    return TCU_OK;
+}
+
+extern "C" int tcu_comm_id(void *id)
+{
+    if (!id) return fail(TCU_ERR_INVALID, "id is NULL");
+    const NcclApi &api = nccl_api();
+    if (!api.ok) return fail(TCU_ERR_NCCL, "NCCL unavailable: %s", api.why);
+    NcclUniqueId u;
+    NK(api.GetUniqueId(&u));
+    memcpy(id, &u, sizeof u);
+    return TCU_OK;
+}
+
+extern "C" int tcu_comm_create(const void *id, int rank, int world, int device, tcu_comm **out)
+{
+    if (!id || !out || world < 1 || rank < 0 || rank >= world)
+        return fail(TCU_ERR_INVALID, "bad communicator arguments");
+    *out = nullptr;
+    const NcclApi &api = nccl_api();
+    if (!api.ok) return fail(TCU_ERR_NCCL, "NCCL unavailable: %s", api.why);
+    if (!device_usable(device, nullptr))
+        return fail(TCU_ERR_NO_DEVICE, "device %d is not an sm_100 GPU", device);
+    CK(cudaSetDevice(device));
+    tcu_comm *c = new (std::nothrow) tcu_comm();
+    if (!c) return fail(TCU_ERR_OOM, "host allocation failed");
+    c->rank = rank;
+    c->world = world;
+    c->device = device;
+    NcclUniqueId u;
+    memcpy(&u, id, sizeof u);
+    int r = api.CommInitRank(&c->comm, world, u, rank);
+    if (r != NCCL_SUCCESS) {
+        delete c;
+        return nccl_fail(r, "ncclCommInitRank");
+    }
+    *out = c;
+    return TCU_OK;
+}
+
+extern "C" void tcu_comm_destroy(tcu_comm *c)
+{
+    if (!c) return;
+    if (c->comm) {
+        cudaSetDevice(c->device);
+        nccl_api().CommDestroy(c->comm);
+    }
+    delete c;
+}
+
+extern "C" int tcu_comm_rank(const tcu_comm *c) { return c ? c->rank : -1; }
+extern "C" int tcu_comm_world(const tcu_comm *c) { return c ? c->world : 0; }
+
+// In-place all-gather of unequal contiguous byte ranges of `buf` (rank r owns
+// [off[r], off[r]+cnt[r])): one broadcast per owner, fused into a single NCCL group so
+// that they progress concurrently over NVLink.
+static int comm_allgatherv(tcu_comm *c, void *buf, const size_t *off, const size_t *cnt,
+                           cudaStream_t stream)
+{
+    const NcclApi &api = nccl_api();
+    NK(api.GroupStart());
+    for (int r = 0; r < c->world; r++) {
+        if (cnt[r] == 0) continue;
+        uint8_t *p = (uint8_t *)buf + off[r];
+        int rc = api.Broadcast(p, p, cnt[r], NCCL_UINT8, r, c->comm, stream);
+        if (rc != NCCL_SUCCESS) {
+            api.GroupEnd();
+            return nccl_fail(rc, "ncclBroadcast");
+        }
+    }
+    NK(api.GroupEnd());
+    return TCU_OK;
+}
+
+static int comm_allreduce_i32(tcu_comm *c, int *buf, size_t count, cudaStream_t stream)
+{
+    const NcclApi &api = nccl_api();
+    NK(api.AllReduce(buf, buf, count, NCCL_INT32, NCCL_SUM, c->comm, stream));
+    return TCU_OK;
+}
+
 static int msa_alloc(int nseq, int ncol, int device, tcu_msa **out)
 {
     if (!out) return fail(TCU_ERR_INVALID, "out is NULL");
@@ -449,11 +597,13 @@ static int download(tcu_msa *m, void *dst, const void *d_src, size_t bytes)
 // ---------------------------------------------------------------------------
 // K3 gaps
 // ---------------------------------------------------------------------------
-extern "C" int tcu_gaps(tcu_msa *m, const int *save_seq, int *gaps_in_column,
-                        int *num_cols_with_gaps, int *max_gaps)
+static int gaps_impl(tcu_msa *m, tcu_comm *comm, const int *save_seq, int *gaps_in_column,
+                     int *num_cols_with_gaps, int *max_gaps)
 {
     if (!m || !gaps_in_column) return fail(TCU_ERR_INVALID, "NULL argument");
     CK(cudaSetDevice(m->device));
+    int rc0 = comm_check(m, comm);
+    if (rc0 != TCU_OK) return rc0;
     m->timings = tcu_timings{};
     const int n = m->nseq, L = m->ncol;
     if (L == 0) return TCU_OK;
@@ -472,23 +622,47 @@ extern "C" int tcu_gaps(tcu_msa *m, const int *save_seq, int *gaps_in_column,
     }
     CK(cudaMemsetAsync(d_cnt, 0, (size_t)L * sizeof(int), m->stream));
     CK(cudaEventRecord(m->ev[1], m->stream));
-    CK(launch_column_counts(m->d_raw, n, L, m->pitch, d_drop, '-', '-', d_cnt, nullptr,
-                            m->num_sms, m->stream));
+    // several ranks: each counts its share of the rows, the integer partial counts are
+    // summed across GPUs (exact in any order)
+    int r0 = 0, r1 = n;
+    if (comm) tcu_shard_range(n, 1, comm->rank, comm->world, &r0, &r1);
+    CK(launch_column_counts(m->d_raw + (size_t)r0 * m->pitch, r1 - r0, L, m->pitch,
+                            d_drop ? d_drop + r0 : nullptr, '-', '-', d_cnt, nullptr, m->num_sms,
+                            m->stream));
     CK(cudaEventRecord(m->ev[2], m->stream));
+    if (comm) {
+        rc = comm_allreduce_i32(comm, d_cnt, (size_t)L, m->stream);
+        if (rc != TCU_OK) return rc;
+    }
+    CK(cudaEventRecord(m->ev[5], m->stream));
     CK(cudaMemcpyAsync(gaps_in_column, d_cnt, (size_t)L * sizeof(int), cudaMemcpyDeviceToHost,
                        m->stream));
     CK(cudaEventRecord(m->ev[3], m->stream));
     CK(cudaStreamSynchronize(m->stream));
     m->timings.h2d_ms = ev_ms(m->ev[0], m->ev[1]);
     m->timings.kernel_ms = ev_ms(m->ev[1], m->ev[2]);
-    m->timings.d2h_ms = ev_ms(m->ev[2], m->ev[3]);
-    m->timings.kernel_launches = n > 0 ? 1 : 0;
+    m->timings.comm_ms = ev_ms(m->ev[2], m->ev[5]);
+    m->timings.d2h_ms = ev_ms(m->ev[5], m->ev[3]);
+    m->timings.kernel_launches = r1 > r0 ? 1 : 0;
     // histogram and maximum (template.h:496-501)
     for (int k = 0; k < L; k++) {
         if (num_cols_with_gaps) num_cols_with_gaps[gaps_in_column[k]]++;
         if (max_gaps && gaps_in_column[k] > *max_gaps) *max_gaps = gaps_in_column[k];
     }
     return TCU_OK;
+}
+
+extern "C" int tcu_gaps(tcu_msa *m, const int *save_seq, int *gaps_in_column,
+                        int *num_cols_with_gaps, int *max_gaps)
+{
+    return gaps_impl(m, nullptr, save_seq, gaps_in_column, num_cols_with_gaps, max_gaps);
+}
+
+extern "C" int tcu_gaps_all(tcu_msa *m, tcu_comm *comm, const int *save_seq, int *gaps_in_column,
+                            int *num_cols_with_gaps, int *max_gaps)
+{
+    if (!comm) return fail(TCU_ERR_INVALID, "comm is NULL");
+    return gaps_impl(m, comm, save_seq, gaps_in_column, num_cols_with_gaps, max_gaps);
 }
 
 // ---------------------------------------------------------------------------
@@ -778,6 +952,60 @@ extern "C" int tcu_identity(tcu_msa *m, const int *save_seq, const int *save_res
                          keep_on_device, false);
 }
 
+// Every rank computes the band of the pair matrix tcu_shard_blocks() assigns it,
+// straight into its place in a full-size device array; the bands are then exchanged so
+// that each GPU holds the whole matrix (what tcu_similarity_all needs).
+extern "C" int tcu_identity_all(tcu_msa *m, tcu_comm *comm, const int *save_seq,
+                                const int *save_res, uint8_t indet, float *identities)
+{
+    if (!m || !comm) return fail(TCU_ERR_INVALID, "NULL argument");
+    int rc = comm_check(m, comm);
+    if (rc != TCU_OK) return rc;
+    m->timings = tcu_timings{};
+    m->ident_full = false;
+    rc = tcu_identity_prepare(m, save_seq, save_res, indet, nullptr);
+    if (rc != TCU_OK) return rc;
+    const size_t npairs = (size_t)m->nk * (size_t)std::max(m->nk - 1, 0) / 2;
+    if (npairs == 0) {
+        CK(cudaStreamSynchronize(m->stream));
+        return TCU_OK;
+    }
+    rc = ensure_ident(m, npairs * sizeof(float));
+    if (rc != TCU_OK) return rc;
+    std::vector<size_t> off(comm->world), cnt(comm->world);
+    int my_b0 = 0, my_b1 = 0;
+    for (int r = 0; r < comm->world; r++) {
+        int b0, b1;
+        tcu_shard_blocks(m->nk, r, comm->world, &b0, &b1);
+        const size_t lo = tcu_identity_row_offset(m->nk, b0 * IB);
+        const size_t hi = tcu_identity_row_offset(m->nk, std::min(b1 * IB, m->nk));
+        off[r] = lo * sizeof(float);
+        cnt[r] = (hi - lo) * sizeof(float);
+        if (r == comm->rank) {
+            my_b0 = b0;
+            my_b1 = b1;
+        }
+    }
+    rc = identity_launch(m, my_b0, my_b1, m->d_ident + off[comm->rank] / sizeof(float), nullptr,
+                         nullptr);
+    if (rc != TCU_OK) return rc;
+    CK(cudaEventRecord(m->ev[3], m->stream));
+    rc = comm_allgatherv(comm, m->d_ident, off.data(), cnt.data(), m->stream);
+    if (rc != TCU_OK) return rc;
+    CK(cudaEventRecord(m->ev[4], m->stream));
+    if (identities) rc = download(m, identities, m->d_ident, npairs * sizeof(float));
+    if (rc != TCU_OK) return rc;
+    CK(cudaEventRecord(m->ev[5], m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    m->timings.h2d_ms = ev_ms(m->ev[0], m->ev[1]);
+    m->timings.pack_ms = ev_ms(m->ev[1], m->ev[2]);
+    m->timings.kernel_ms = ev_ms(m->ev[2], m->ev[3]);
+    m->timings.comm_ms = ev_ms(m->ev[3], m->ev[4]);
+    m->timings.d2h_ms = ev_ms(m->ev[4], m->ev[5]);
+    m->ident_full = (m->nk == m->nseq);
+    return TCU_OK;
+}
+
 // test-only: same contract as tcu_identity, computed by the byte-wise kernel
 extern "C" int tcu_debug_identity_bytes(tcu_msa *m, const int *save_seq, const int *save_res,
                                         uint8_t indet, float *identities, int *hit_out,
@@ -789,10 +1017,13 @@ extern "C" int tcu_debug_identity_bytes(tcu_msa *m, const int *save_seq, const i
 // ---------------------------------------------------------------------------
 // K2 spurious
 // ---------------------------------------------------------------------------
-extern "C" int tcu_spurious(tcu_msa *m, uint8_t indet, uint32_t ovrlap, float *spurious)
+static int spurious_impl(tcu_msa *m, tcu_comm *comm, uint8_t indet, uint32_t ovrlap,
+                         float *spurious)
 {
     if (!m || !spurious) return fail(TCU_ERR_INVALID, "NULL argument");
     CK(cudaSetDevice(m->device));
+    int rc0 = comm_check(m, comm);
+    if (rc0 != TCU_OK) return rc0;
     m->timings = tcu_timings{};
     const int n = m->nseq, L = m->ncol;
     if (n == 0) return TCU_OK;
@@ -812,33 +1043,71 @@ extern "C" int tcu_spurious(tcu_msa *m, uint8_t indet, uint32_t ovrlap, float *s
     CK(cudaMemsetAsync(d_cg, 0, 2 * cnt_bytes, m->stream));
     CK(cudaMemsetAsync(d_flags, 0, m->pitch, m->stream));
     CK(cudaEventRecord(m->ev[1], m->stream));
-    CK(launch_column_counts(m->d_raw, n, L, m->pitch, nullptr, '-', indet, d_cg, d_cx, m->num_sms,
-                            m->stream));
-    CK(launch_spurious_rows(m->d_raw, n, L, m->pitch, indet, d_cg, d_cx, ovrlap, d_flags, d_out,
-                            m->stream));
+    // several ranks: partial column counts over this rank's rows, summed across GPUs
+    // (d_cg and d_cx are adjacent: one all-reduce), then this rank's rows of the
+    // vector, all-gathered
+    int r0 = 0, r1 = n;
+    if (comm) tcu_shard_range(n, 1, comm->rank, comm->world, &r0, &r1);
+    CK(launch_column_counts(m->d_raw + (size_t)r0 * m->pitch, r1 - r0, L, m->pitch, nullptr, '-',
+                            indet, d_cg, d_cx, m->num_sms, m->stream));
+    CK(cudaEventRecord(m->ev[4], m->stream));
+    if (comm) {
+        rc = comm_allreduce_i32(comm, d_cg, 2 * cnt_bytes / sizeof(int), m->stream);
+        if (rc != TCU_OK) return rc;
+    }
+    CK(cudaEventRecord(m->ev[5], m->stream));
+    CK(launch_spurious_rows(m->d_raw, n, r0, r1, L, m->pitch, indet, d_cg, d_cx, ovrlap, d_flags,
+                            d_out, m->stream));
     CK(cudaEventRecord(m->ev[2], m->stream));
+    if (comm) {
+        std::vector<size_t> off(comm->world), cnt(comm->world);
+        for (int r = 0; r < comm->world; r++) {
+            int a, b;
+            tcu_shard_range(n, 1, r, comm->world, &a, &b);
+            off[r] = (size_t)a * sizeof(float);
+            cnt[r] = (size_t)(b - a) * sizeof(float);
+        }
+        rc = comm_allgatherv(comm, d_out, off.data(), cnt.data(), m->stream);
+        if (rc != TCU_OK) return rc;
+    }
+    CK(cudaEventRecord(m->ev[0], m->stream));
     CK(cudaMemcpyAsync(spurious, d_out, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost,
                        m->stream));
     CK(cudaEventRecord(m->ev[3], m->stream));
     CK(cudaStreamSynchronize(m->stream));
-    m->timings.kernel_ms = ev_ms(m->ev[1], m->ev[2]);
-    m->timings.d2h_ms = ev_ms(m->ev[2], m->ev[3]);
+    m->timings.kernel_ms = ev_ms(m->ev[1], m->ev[4]) + ev_ms(m->ev[5], m->ev[2]);
+    m->timings.comm_ms = ev_ms(m->ev[4], m->ev[5]) + ev_ms(m->ev[2], m->ev[0]);
+    m->timings.d2h_ms = ev_ms(m->ev[0], m->ev[3]);
     m->timings.kernel_launches = 3;
     return TCU_OK;
+}
+
+extern "C" int tcu_spurious(tcu_msa *m, uint8_t indet, uint32_t ovrlap, float *spurious)
+{
+    return spurious_impl(m, nullptr, indet, ovrlap, spurious);
+}
+
+extern "C" int tcu_spurious_all(tcu_msa *m, tcu_comm *comm, uint8_t indet, uint32_t ovrlap,
+                                float *spurious)
+{
+    if (!comm) return fail(TCU_ERR_INVALID, "comm is NULL");
+    return spurious_impl(m, comm, indet, ovrlap, spurious);
 }
 
 // ---------------------------------------------------------------------------
 // K4 similarity
 // ---------------------------------------------------------------------------
-extern "C" int tcu_similarity(tcu_msa *m, uint8_t indet, const float *dist, int npos,
-                              const int *vhash, const int *gaps, float gap_threshold,
-                              const float *identities, float *num, float *den, float *mdk,
-                              int *err_col, int *err_row, int *err_byte)
+static int similarity_impl(tcu_msa *m, tcu_comm *comm, uint8_t indet, const float *dist, int npos,
+                           const int *vhash, const int *gaps, float gap_threshold,
+                           const float *identities, float *num, float *den, float *mdk,
+                           int *err_col, int *err_row, int *err_byte)
 {
     if (!m || !dist || !vhash || !num || !den) return fail(TCU_ERR_INVALID, "NULL argument");
     if (npos < 1 || npos > SIM_MAX_POS)
         return fail(TCU_ERR_INVALID, "similarity matrix order %d outside [1,%d]", npos, SIM_MAX_POS);
     CK(cudaSetDevice(m->device));
+    int rc0 = comm_check(m, comm);
+    if (rc0 != TCU_OK) return rc0;
     const int n = m->nseq, L = m->ncol;
     const size_t npairs = (size_t)n * (size_t)std::max(n - 1, 0) / 2;
     tcu_timings t{};
@@ -922,17 +1191,39 @@ extern "C" int tcu_similarity(tcu_msa *m, uint8_t indet, const float *dist, int 
                     "symbol '%c' at column %d, row %d cannot be scored", byte, col, row);
     }
 
+    // several ranks: columns are independent given the identities, so each rank runs the
+    // chains of its share of the 32-column groups and the two vectors are all-gathered
+    // (d_num and d_den sit vec_bytes apart: two ranges per rank)
+    const int col_groups = (L + 31) / 32;
+    int g0 = 0, g1 = col_groups;
+    if (comm) tcu_shard_range(col_groups, 1, comm->rank, comm->world, &g0, &g1);
     CK(cudaEventRecord(m->ev[2], m->stream));
     CK(launch_similarity(d_codes, n, npad, L, m->d_ident, d_dist, npos, d_skip, d_rowskip,
-                         d_nbatches, 0, (L + 31) / 32, d_num, d_den, m->num_sms, m->stream));
+                         d_nbatches, g0, g1, d_num, d_den, m->num_sms, m->stream));
     CK(cudaEventRecord(m->ev[3], m->stream));
+    if (comm) {
+        for (int v = 0; v < 2; v++) {
+            std::vector<size_t> off(comm->world), cnt(comm->world);
+            for (int r = 0; r < comm->world; r++) {
+                int a, b;
+                tcu_shard_range(col_groups, 1, r, comm->world, &a, &b);
+                off[r] = (size_t)a * 32 * sizeof(float);
+                cnt[r] = (size_t)(std::min(b * 32, L) - std::min(a * 32, L)) * sizeof(float);
+            }
+            rc = comm_allgatherv(comm, v ? (void *)d_den : (void *)d_num, off.data(), cnt.data(),
+                                 m->stream);
+            if (rc != TCU_OK) return rc;
+        }
+    }
+    CK(cudaEventRecord(m->ev[5], m->stream));
     CK(cudaMemcpyAsync(num, d_num, (size_t)L * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
     CK(cudaMemcpyAsync(den, d_den, (size_t)L * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
     CK(cudaEventRecord(m->ev[4], m->stream));
     CK(cudaStreamSynchronize(m->stream));
     t.kernel_ms = ev_ms(m->ev[2], m->ev[3]);
-    t.d2h_ms = ev_ms(m->ev[3], m->ev[4]);
-    t.kernel_launches += n > 0 ? 1 : 0;
+    t.comm_ms = ev_ms(m->ev[3], m->ev[5]);
+    t.d2h_ms = ev_ms(m->ev[5], m->ev[4]);
+    t.kernel_launches += (n > 0 && g1 > g0) ? 1 : 0;
     m->timings = t;
 
     if (mdk) {
@@ -946,4 +1237,23 @@ extern "C" int tcu_similarity(tcu_msa *m, uint8_t indet, const float *dist, int 
         }
     }
     return TCU_OK;
+}
+
+extern "C" int tcu_similarity(tcu_msa *m, uint8_t indet, const float *dist, int npos,
+                              const int *vhash, const int *gaps, float gap_threshold,
+                              const float *identities, float *num, float *den, float *mdk,
+                              int *err_col, int *err_row, int *err_byte)
+{
+    return similarity_impl(m, nullptr, indet, dist, npos, vhash, gaps, gap_threshold, identities,
+                           num, den, mdk, err_col, err_row, err_byte);
+}
+
+extern "C" int tcu_similarity_all(tcu_msa *m, tcu_comm *comm, uint8_t indet, const float *dist,
+                                  int npos, const int *vhash, const int *gaps, float gap_threshold,
+                                  float *num, float *den, float *mdk, int *err_col, int *err_row,
+                                  int *err_byte)
+{
+    if (!comm) return fail(TCU_ERR_INVALID, "comm is NULL");
+    return similarity_impl(m, comm, indet, dist, npos, vhash, gaps, gap_threshold, nullptr, num,
+                           den, mdk, err_col, err_row, err_byte);
 }

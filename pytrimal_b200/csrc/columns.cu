@@ -130,15 +130,16 @@ __global__ void __launch_bounds__(256) k_spurious_flags(int nseq, int ncol,
     col_flags[k] = f;
 }
 
-// one warp per row
-__global__ void __launch_bounds__(256) k_spurious_rows(const uint8_t *__restrict__ raw, int nseq,
-                                                       int ncol, size_t pitch, uint8_t indet,
+// one warp per row of [row_begin, row_end)
+__global__ void __launch_bounds__(256) k_spurious_rows(const uint8_t *__restrict__ raw,
+                                                       int row_begin, int row_end, int ncol,
+                                                       size_t pitch, uint8_t indet,
                                                        const uint8_t *__restrict__ col_flags,
                                                        float *__restrict__ out)
 {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int warp = row_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
-    if (warp >= nseq) return;
+    if (warp >= row_end) return;
     const uint8_t *row = raw + (size_t)warp * pitch;
     uint32_t good = 0;
     // 4 columns per lane per step: 128 contiguous bytes per warp
@@ -160,20 +161,21 @@ __global__ void __launch_bounds__(256) k_spurious_rows(const uint8_t *__restrict
     if (lane == 0) out[warp] = __fdiv_rn((float)good, (float)ncol);
 }
 
-// col_flags: scratch of at least roundup(ncol, 4) bytes.
-cudaError_t launch_spurious_rows(const uint8_t *raw, int nseq, int ncol, size_t pitch,
-                                 uint8_t indet, const int *cnt_gap, const int *cnt_indet,
-                                 uint32_t ovrlap, uint8_t *col_flags, float *out,
-                                 cudaStream_t stream)
+// col_flags: scratch of at least roundup(ncol, 4) bytes.  The column counts cover all
+// nseq rows; out[row_begin .. row_end) is written (a rank's share of the rows).
+cudaError_t launch_spurious_rows(const uint8_t *raw, int nseq, int row_begin, int row_end,
+                                 int ncol, size_t pitch, uint8_t indet, const int *cnt_gap,
+                                 const int *cnt_indet, uint32_t ovrlap, uint8_t *col_flags,
+                                 float *out, cudaStream_t stream)
 {
     if (nseq == 0 || ncol == 0) return cudaSuccess;
     k_spurious_flags<<<(ncol + 255) / 256, 256, 0, stream>>>(nseq, ncol, cnt_gap, cnt_indet,
                                                              ovrlap, col_flags);
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    const long long threads = (long long)nseq * 32;
-    k_spurious_rows<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(raw, nseq, ncol, pitch,
-                                                                           indet, col_flags, out);
+    if (e != cudaSuccess || row_end <= row_begin) return e;
+    const long long threads = (long long)(row_end - row_begin) * 32;
+    k_spurious_rows<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
+        raw, row_begin, row_end, ncol, pitch, indet, col_flags, out);
     return cudaGetLastError();
 }
 

@@ -99,10 +99,10 @@ cudaError_t launch_identity_bytes(const uint8_t *raw, size_t pitch, int ncol, co
 cudaError_t launch_column_counts(const uint8_t *raw, int nseq, int ncol, size_t pitch,
                                  const uint8_t *row_drop, uint8_t sym_a, uint8_t sym_b,
                                  int *count_a, int *count_b, int num_sms, cudaStream_t stream);
-cudaError_t launch_spurious_rows(const uint8_t *raw, int nseq, int ncol, size_t pitch,
-                                 uint8_t indet, const int *cnt_gap, const int *cnt_indet,
-                                 uint32_t ovrlap, uint8_t *col_flags, float *out,
-                                 cudaStream_t stream);
+cudaError_t launch_spurious_rows(const uint8_t *raw, int nseq, int row_begin, int row_end,
+                                 int ncol, size_t pitch, uint8_t indet, const int *cnt_gap,
+                                 const int *cnt_indet, uint32_t ovrlap, uint8_t *col_flags,
+                                 float *out, cudaStream_t stream);
 cudaError_t launch_sim_codes(const uint8_t *raw, int nseq, int ncol, size_t pitch, int npad,
                              const uint8_t *lut256, const uint8_t *col_skip, uint8_t *codesT,
                              unsigned long long *first_error, cudaStream_t stream);

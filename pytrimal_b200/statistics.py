@@ -36,8 +36,78 @@ def _mask(m, n):
     return m
 
 
+class Communicator:
+    """NCCL communicator of the ``*_all`` calls (wraps ``tcu_comm``), one process per GPU.
+
+    The 128-byte rendezvous id is made by rank 0 and handed to the other ranks
+    by ``exchange(bytes_or_None) -> bytes``; :meth:`from_torch` uses an initialised
+    ``torch.distributed`` process group (any backend) for that and nothing else."""
+
+    ID_BYTES = 128
+
+    def __init__(self, rank, world, device, exchange):
+        self.lib = _lib.load()
+        ident = None
+        if rank == 0:
+            buf = C.create_string_buffer(self.ID_BYTES)
+            _lib.check(self.lib.tcu_comm_id(buf))
+            ident = buf.raw
+        ident = exchange(ident)
+        if not isinstance(ident, (bytes, bytearray)) or len(ident) != self.ID_BYTES:
+            raise ValueError("exchange() must return the 128-byte id of rank 0")
+        self._h = C.c_void_p()
+        _lib.check(self.lib.tcu_comm_create(C.c_char_p(bytes(ident)), rank, world, device,
+                                            C.byref(self._h)))
+        self.rank, self.world, self.device = rank, world, device
+
+    @classmethod
+    def from_torch(cls, device):
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+
+        def exchange(ident):
+            box = [ident]
+            dist.broadcast_object_list(box, src=0, device=torch.device("cpu")
+                                       if dist.get_backend() == "gloo" else None)
+            return box[0]
+
+        return cls(rank, world, device, exchange)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.tcu_comm_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def shard_range(total, granule, rank, world):
+    """``tcu_shard_range``: rank's contiguous share [begin, end) of ``total`` units."""
+    a, b = C.c_int(0), C.c_int(0)
+    _lib.check(_lib.load().tcu_shard_range(total, granule, rank, world, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def shard_blocks(kept_rows, rank, world):
+    """``tcu_shard_blocks``: rank's band [begin, end) of 128-row blocks of the pair matrix."""
+    a, b = C.c_int(0), C.c_int(0)
+    _lib.check(_lib.load().tcu_shard_blocks(kept_rows, rank, world, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
 class DeviceAlignment:
-    """One alignment uploaded to one GPU (wraps a ``tcu_msa`` handle)."""
+    """One alignment uploaded to one GPU (wraps a ``tcu_msa`` handle).
+
+    Every statistic takes ``comm=``: with a :class:`Communicator` the ``tcu_*_all``
+    entry point is used (each rank computes its share, NCCL exchanges the shares,
+    every rank returns the complete result)."""
 
     def __init__(self, alignment, device=0):
         if not isinstance(alignment, Alignment):
@@ -70,29 +140,41 @@ class DeviceAlignment:
         t = _lib.Timings()
         _lib.check(self.lib.tcu_msa_timings(self._h, C.byref(t)))
         return {"h2d_ms": t.h2d_ms, "pack_ms": t.pack_ms, "kernel_ms": t.kernel_ms,
-                "d2h_ms": t.d2h_ms, "kernel_launches": t.kernel_launches}
+                "d2h_ms": t.d2h_ms, "kernel_launches": t.kernel_launches, "comm_ms": t.comm_ms}
 
     # -- K3 -------------------------------------------------------------------
-    def gaps(self, save_seq=None):
+    def gaps(self, save_seq=None, comm=None):
         """(gapsInColumn, numColumnsWithGaps, maxGaps) -- template.h:444-502."""
         ss = _mask(save_seq, self.nseq)
         g = np.zeros(self.ncol, np.int32)
         hist = np.zeros(self.nseq + 1, np.int32)
         mx = C.c_int(0)
-        _lib.check(self.lib.tcu_gaps(self._h, _p(ss, _i32p), _p(g, _i32p), _p(hist, _i32p),
-                                     C.byref(mx)))
+        if comm is None:
+            rc = self.lib.tcu_gaps(self._h, _p(ss, _i32p), _p(g, _i32p), _p(hist, _i32p),
+                                   C.byref(mx))
+        else:
+            rc = self.lib.tcu_gaps_all(self._h, comm._h, _p(ss, _i32p), _p(g, _i32p),
+                                       _p(hist, _i32p), C.byref(mx))
+        _lib.check(rc)
         return g, hist, mx.value
 
     # -- K1 -------------------------------------------------------------------
     def identity(self, indet=None, save_seq=None, save_res=None, counts=False,
-                 keep_on_device=False, out=None, _debug_bytes=False):
-        """Packed identity array over kept pairs -- template.h:320-442."""
+                 keep_on_device=False, out=None, _debug_bytes=False, comm=None):
+        """Packed identity array over kept pairs -- template.h:320-442.  With ``comm``
+        the matrix always stays on every rank's device as well."""
         indet = self.alignment.indet if indet is None else indet
         ss, sr = _mask(save_seq, self.nseq), _mask(save_res, self.ncol)
         nk = self.nseq if ss is None else int((ss != -1).sum())
         npairs = nk * (nk - 1) // 2
         ident = np.empty(npairs, np.float32) if out is None else out
         assert ident.dtype == np.float32 and ident.size >= npairs and ident.flags.c_contiguous
+        if comm is not None:
+            if counts or _debug_bytes:
+                raise ValueError("counts are a single-GPU debugging output")
+            _lib.check(self.lib.tcu_identity_all(self._h, comm._h, _p(ss, _i32p), _p(sr, _i32p),
+                                                 indet, _p(ident, _f32p)))
+            return ident[:npairs]
         hit = np.zeros(npairs, np.int32) if counts else None
         dst = np.zeros(npairs, np.int32) if counts else None
         if _debug_bytes:
@@ -108,7 +190,7 @@ class DeviceAlignment:
 
     # -- K4 -------------------------------------------------------------------
     def similarity(self, matrix: SimilarityMatrix, gaps=None, number_of_residues=None,
-                   identities=None, indet=None):
+                   identities=None, indet=None, comm=None):
         """(mdk, num, den) -- template.h:69-204.  ``gaps=None`` is cutByGap=False.
         Needs the device identities of a previous ``identity(keep_on_device=True)``
         unless ``identities`` is given."""
@@ -121,21 +203,36 @@ class DeviceAlignment:
         ids = None if identities is None else np.ascontiguousarray(identities, np.float32)
         num, den, mdk = (np.zeros(self.ncol, np.float32) for _ in range(3))
         ec, er, eb = C.c_int(-1), C.c_int(-1), C.c_int(0)
-        rc = self.lib.tcu_similarity(self._h, indet, _p(dist, _f32p), dist.shape[0],
-                                     _p(vhash, _i32p), _p(g, _i32p), C.c_float(thr),
-                                     _p(ids, _f32p), _p(num, _f32p), _p(den, _f32p),
-                                     _p(mdk, _f32p), C.byref(ec), C.byref(er), C.byref(eb))
+        if comm is not None:
+            if ids is not None:
+                raise ValueError("similarity(comm=...) uses the matrix identity(comm=...) left "
+                                 "on the device")
+            rc = self.lib.tcu_similarity_all(self._h, comm._h, indet, _p(dist, _f32p),
+                                             dist.shape[0], _p(vhash, _i32p), _p(g, _i32p),
+                                             C.c_float(thr), _p(num, _f32p), _p(den, _f32p),
+                                             _p(mdk, _f32p), C.byref(ec), C.byref(er),
+                                             C.byref(eb))
+        else:
+            rc = self.lib.tcu_similarity(self._h, indet, _p(dist, _f32p), dist.shape[0],
+                                         _p(vhash, _i32p), _p(g, _i32p), C.c_float(thr),
+                                         _p(ids, _f32p), _p(num, _f32p), _p(den, _f32p),
+                                         _p(mdk, _f32p), C.byref(ec), C.byref(er), C.byref(eb))
         _lib.check(rc, (ec.value, er.value, eb.value))
         return mdk, num, den
 
     # -- K2 -------------------------------------------------------------------
-    def spurious(self, overlap, indet=None):
+    def spurious(self, overlap, indet=None, comm=None):
         """spuriousVector -- template.h:206-318."""
         indet = self.alignment.indet if indet is None else indet
         # template.h:217-218: fp32 product, then ceil
         ovrlap = int(math.ceil(float(np.float32(overlap) * np.float32(self.nseq - 1))))
         out = np.zeros(self.nseq, np.float32)
-        _lib.check(self.lib.tcu_spurious(self._h, indet, max(ovrlap, 0), _p(out, _f32p)))
+        if comm is None:
+            rc = self.lib.tcu_spurious(self._h, indet, max(ovrlap, 0), _p(out, _f32p))
+        else:
+            rc = self.lib.tcu_spurious_all(self._h, comm._h, indet, max(ovrlap, 0),
+                                           _p(out, _f32p))
+        _lib.check(rc)
         return out
 
     # -- device-resident identity (benchmarks / multi-GPU) ---------------------

@@ -153,3 +153,36 @@ def test_synthetic_generator_is_deterministic():
     b = synthetic_msa(300, 200, 7)
     assert (a == b).all() and a.shape == (300, 200)
     assert 0.1 < (a == ord("-")).mean() < 0.5
+
+
+def test_shard_helpers_cover_and_balance(lib):
+    """tcu_shard_range / tcu_shard_blocks (the partition the *_all calls use): contiguous,
+    covering, and equal to the Python partition bench.py uses."""
+    import pytrimal_b200 as pb
+    from pytrimal_b200 import sharding
+    for total, gran in [(0, 1), (5, 1), (157, 1), (100000, 1), (1000, 32)]:
+        for world in (1, 2, 3, 8):
+            cuts = [pb.shard_range(total, gran, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == total
+            for a, b in zip(cuts, cuts[1:]):
+                assert a[1] == b[0]
+            sizes = [b - a for a, b in cuts]
+            assert max(sizes) - min(sizes) <= gran
+    for n in (1, 100, 130, 257, 700, 12345, 50000):
+        for world in (1, 2, 3, 8):
+            bounds = sharding.band_partition(n, world)
+            cuts = [pb.shard_blocks(n, r, world) for r in range(world)]
+            assert [c[0] for c in cuts] + [cuts[-1][1]] == bounds
+    with pytest.raises(ValueError):
+        pb.shard_range(10, 1, 3, 2)
+
+
+def test_comm_calls_fail_loudly_without_device(lib):
+    """No GPU here: creating a communicator must fail (NCCL or device), never pretend."""
+    import ctypes as C
+    import pytrimal_b200 as pb
+    if pb.device_count() > 0:
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    rc = lib.tcu_comm_create(C.create_string_buffer(128), 0, 1, 0, C.byref(h))
+    assert rc < 0 and not h.value
