@@ -199,6 +199,72 @@ typedef struct tcu_timings {
 
 int tcu_msa_timings(const tcu_msa *msa, tcu_timings *out);
 
+/* ---- consumers of the device-resident identity matrix ----
+ * The three host walks over Identity::identities in vendor/trimal/source/Cleaner.cpp
+ * -- selectMethod (:46-99), getCutPointClusters (:1026-1156) and
+ * calculateRepresentativeSeq (:1398-1466) -- done where the matrix already is, so
+ * that its 4*P bytes never cross PCIe.  All need a preceding
+ * tcu_identity(..., keep_on_device=1) with every row kept (the reference's own
+ * index arithmetic in these walks assumes that too); otherwise TCU_ERR_STATE.  */
+
+/* 1 when such a matrix is resident on the handle's device. */
+int tcu_identity_resident(const tcu_msa *msa);
+
+/* Copy the resident matrix (nseq*(nseq-1)/2 floats, reference's packed order) to the host. */
+int tcu_identity_download(tcu_msa *msa, float *identities);
+
+/*
+ * Per-row statistics of the matrix read as symmetric, in the reference's fp32
+ * order (j ascending): upper_only = 0 -> over all j != i (selectMethod's mx / avg,
+ * Cleaner.cpp:68-80); upper_only = 1 -> over j > i (getCutPointClusters' max / min /
+ * avg, :1054-1063).  Neutral start values as the reference: max 0, min 1, sum 0.
+ * Each output is nseq floats; any may be NULL.
+ */
+int tcu_identity_row_stats(tcu_msa *msa, int upper_only, float *row_max, float *row_min,
+                           float *row_sum);
+
+/*
+ * Greedy clustering shared by calculateRepresentativeSeq (Cleaner.cpp:1427-1447) and
+ * the search loop of getCutPointClusters (:1100-1118): walking order[0..count) (row
+ * indices, distinct), a sequence becomes the representative of a new cluster iff no
+ * earlier representative has identity > threshold with it.  clusters (optional,
+ * count ints) receives the representatives in creation order, *n_clusters their
+ * number.
+ */
+int tcu_identity_clusters(tcu_msa *msa, const int *order, int count, float threshold,
+                          int *clusters, int *n_clusters);
+
+/* ---- alignment-wide scans of the host layer ------------ */
+
+/*
+ * Number of occurrences of every byte value over all rows and columns (256 counts).
+ * It is all that utils::checkAlignmentType (source/utils.cpp:476-545; reached through
+ * Alignment::getAlignmentType on every trim()) needs from its O(nseq*ncol) scan with
+ * seven std::string::find calls per byte: each of its counters is a sum of bins.
+ */
+int tcu_byte_histogram(tcu_msa *msa, unsigned long long *hist256);
+
+/* Alignment::getSequenceLength (source/Alignment/Alignment.cpp:296-298) of every row:
+ * ncol minus the number of '-' bytes.  lengths: nseq ints. */
+int tcu_sequence_lengths(tcu_msa *msa, int *lengths);
+
+/*
+ * Host only (no device needed).  The order in which both clustering walks visit the
+ * sequences: (length, index) records sorted with the reference's own non-stable
+ * quicksort (utils.cpp:246-273) and walked from the end (Cleaner.cpp:1413-1426 /
+ * 1078-1089); order[0] is the first representative.  lengths, order: nseq ints.
+ */
+int tcu_cluster_order(const int *lengths, int nseq, int *order);
+
+/*
+ * Cleaner::calculateRepresentativeSeq (Cleaner.cpp:1398-1466) in one call for an
+ * alignment with every row kept: identity matrix over the kept columns (save_res;
+ * left resident on the device), sequence lengths, visiting order, greedy clustering
+ * at `threshold` (maximumIdent).  clusters: up to nseq ints (may be NULL).
+ */
+int tcu_representatives(tcu_msa *msa, const int *save_res, uint8_t indet, float threshold,
+                        int *clusters, int *n_clusters);
+
 /* ---- several GPUs, one process per GPU --------------------------
  * The reference has no multi-device path; this is the partition north_star
  * asks for.  Every rank uploads the same alignment to its own GPU

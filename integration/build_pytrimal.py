@@ -93,6 +93,11 @@ def prepare_sources():
     unified_patch(os.path.join(TRIMAL, "source/Statistics/Manager.cpp"),
                   os.path.join(HERE, "patches", "Manager.cpp.patch"),
                   os.path.join(PATCHED, "source/Statistics/Manager.cpp"), PATCHED)
+    unified_patch(os.path.join(TRIMAL, "source/Alignment/Alignment.cpp"),
+                  os.path.join(HERE, "patches", "Alignment.cpp.patch"),
+                  os.path.join(PATCHED, "source/Alignment/Alignment.cpp"), PATCHED)
+    # Cleaner.cpp: our patch goes on top of pytrimal's own (applied above)
+    run(["patch", "-s", "-p1", "-d", PATCHED, "-i", os.path.join(HERE, "patches", "Cleaner.cpp.patch")])
     os.makedirs(os.path.join(PATCHED, "include/Platform/CUDA"), exist_ok=True)
     shutil.copyfile(os.path.join(ROOT, "pytrimal_b200/csrc/shim/CUDA.h"),
                     os.path.join(PATCHED, "include/Platform/CUDA/CUDA.h"))
@@ -149,7 +154,8 @@ def compile_all():
         return obj
 
     objs = []
-    patched_src = {"source/Cleaner.cpp", "source/reportsystem.cpp", "source/Statistics/Manager.cpp"}
+    patched_src = {"source/Cleaner.cpp", "source/reportsystem.cpp", "source/Statistics/Manager.cpp",
+                   "source/Alignment/Alignment.cpp"}
     core = ["source/Cleaner.cpp", "source/Alignment/Alignment.cpp", "source/Alignment/sequencesMatrix.cpp",
             "source/Statistics/similarityMatrix.cpp", "source/Statistics/Mold.cpp",
             "source/Statistics/Gaps.cpp", "source/Statistics/Manager.cpp",

@@ -112,6 +112,18 @@ class Port:
         L.orc_similarity_finish.restype = None
         L.orc_similarity_window.argtypes = [_f32p, C.c_int, C.c_int, _f32p]
         L.orc_similarity_window.restype = C.c_int
+        L.orc_sequence_lengths.argtypes = [_u8p, C.c_int, C.c_int, C.c_size_t, _i32p]
+        L.orc_sequence_lengths.restype = None
+        L.orc_cluster_order.argtypes = [_i32p, C.c_int, _i32p]
+        L.orc_cluster_order.restype = C.c_int
+        L.orc_greedy_clusters.argtypes = [_f32p, C.c_int, _i32p, C.c_int, C.c_float, _i32p]
+        L.orc_greedy_clusters.restype = C.c_int
+        L.orc_identity_row_stats.argtypes = [_f32p, C.c_int, C.c_int, _f32p, _f32p, _f32p]
+        L.orc_identity_row_stats.restype = None
+        L.orc_select_method.argtypes = [_f32p, C.c_int, _f32p, _f32p]
+        L.orc_select_method.restype = C.c_int
+        L.orc_cutpoint_clusters.argtypes = [_f32p, C.c_int, _i32p, C.c_int, _i32p]
+        L.orc_cutpoint_clusters.restype = C.c_float
 
     # -- gaps ---------------------------------------------------------------
     def gaps(self, msa, save_seq=None):
@@ -155,6 +167,53 @@ class Port:
                                       _ptr(hit, _i32p), _ptr(dst, _i32p))
         assert wrote == npairs
         return (ident, hit, dst) if counts else ident
+
+    # -- consumers of the identity matrix (Cleaner.cpp walks) ------------------
+    def sequence_lengths(self, msa):
+        msa = _msa(msa)
+        n, L = msa.shape
+        out = np.zeros(n, np.int32)
+        self.lib.orc_sequence_lengths(_ptr(msa, _u8p), n, L, msa.strides[0] if n else L,
+                                      _ptr(out, _i32p))
+        return out
+
+    def cluster_order(self, lengths):
+        lengths = np.ascontiguousarray(lengths, np.int32)
+        out = np.zeros(len(lengths), np.int32)
+        if self.lib.orc_cluster_order(_ptr(lengths, _i32p), len(lengths), _ptr(out, _i32p)):
+            raise MemoryError
+        return out
+
+    def greedy_clusters(self, identities, nseq, order, threshold):
+        identities = np.ascontiguousarray(identities, np.float32)
+        order = np.ascontiguousarray(order, np.int32)
+        out = np.zeros(max(len(order), 1), np.int32)
+        k = self.lib.orc_greedy_clusters(_ptr(identities, _f32p), nseq, _ptr(order, _i32p),
+                                         len(order), C.c_float(threshold), _ptr(out, _i32p))
+        return out[:k].copy()
+
+    def identity_row_stats(self, identities, nseq, upper_only):
+        identities = np.ascontiguousarray(identities, np.float32)
+        mx, mn, sm = (np.zeros(nseq, np.float32) for _ in range(3))
+        self.lib.orc_identity_row_stats(_ptr(identities, _f32p), nseq, int(upper_only),
+                                        _ptr(mx, _f32p), _ptr(mn, _f32p), _ptr(sm, _f32p))
+        return mx, mn, sm
+
+    def select_method(self, identities, nseq):
+        """(1 = gappyout | 2 = strict, avgSeq, maxSeq)"""
+        identities = np.ascontiguousarray(identities, np.float32)
+        a, m = C.c_float(0), C.c_float(0)
+        r = self.lib.orc_select_method(_ptr(identities, _f32p), nseq, C.byref(a), C.byref(m))
+        return r, np.float32(a.value), np.float32(m.value)
+
+    def cutpoint_clusters(self, identities, nseq, order, cluster_number):
+        """(threshold, number of clusterings run)"""
+        identities = np.ascontiguousarray(identities, np.float32)
+        order = np.ascontiguousarray(order, np.int32)
+        it = C.c_int(0)
+        t = self.lib.orc_cutpoint_clusters(_ptr(identities, _f32p), nseq, _ptr(order, _i32p),
+                                           int(cluster_number), C.byref(it))
+        return np.float32(t), it.value
 
     # -- spurious -----------------------------------------------------------
     def spurious_pairwise(self, msa, indet, overlap, hits=False):
@@ -253,6 +312,12 @@ class Ref:
             L.ref_spurious.argtypes = [C.c_void_p, C.c_float, _f32p]
             L.ref_trim.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.POINTER(C.c_double), _i32p,
                                    _i32p]
+            L.ref_representatives.argtypes = [C.c_void_p, C.c_float, _i32p]
+            L.ref_cutpoint.argtypes = [C.c_void_p, C.c_int]
+            L.ref_cutpoint.restype = C.c_float
+            L.ref_select_method.argtypes = [C.c_void_p]
+            L.ref_identity_on_host.argtypes = [C.c_void_p]
+            L.ref_detect_type.argtypes = [C.c_void_p]
             cls._lib = L
         return cls._lib
 
@@ -329,6 +394,27 @@ class Ref:
         if self.lib().ref_spurious(self.h, C.c_float(overlap), _ptr(out, _f32p)):
             raise RuntimeError("reference spurious vector failed")
         return out
+
+    def representatives(self, max_identity):
+        """Cleaner::calculateRepresentativeSeq: representatives in creation order."""
+        out = np.zeros(max(self.n, 1), np.int32)
+        k = self.lib().ref_representatives(self.h, C.c_float(max_identity), _ptr(out, _i32p))
+        if k < 0:
+            raise RuntimeError("reference clustering failed")
+        return out[:k].copy()
+
+    def cutpoint(self, clusters):
+        return np.float32(self.lib().ref_cutpoint(self.h, int(clusters)))
+
+    def select_method(self):
+        return self.lib().ref_select_method(self.h)
+
+    def detect_type(self):
+        """Alignment::getAlignmentType from scratch with the current platform."""
+        return self.lib().ref_detect_type(self.h)
+
+    def identity_on_host(self):
+        return bool(self.lib().ref_identity_on_host(self.h))
 
     def trim(self, method, params=(), platform=None):
         """Returns (keep_seq, keep_res) int32 arrays (-1 = removed)."""

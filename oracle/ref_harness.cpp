@@ -122,6 +122,16 @@ void ref_alignment_free(void *hv)
 
 int ref_alignment_type(void *hv) { return ((RefAlignment *)hv)->ali->getAlignmentType(); }
 
+/* Forget the cached type and detect it again (Alignment::getAlignmentType ->
+ * utils::checkAlignmentType, utils.cpp:476-545) with the platform set by
+ * ref_set_platform: the CUDA platform answers from a device byte histogram. */
+int ref_detect_type(void *hv)
+{
+    Alignment *a = ((RefAlignment *)hv)->ali;
+    a->dataType = SequenceTypes::NotDefined;
+    return a->getAlignmentType();
+}
+
 /* 0 = generic, 1 = SSE2, 2 = AVX2, 3 = CUDA (integration build only).
  * Must be called before any statistic. */
 void ref_set_platform(void *hv, int platform)
@@ -226,6 +236,41 @@ int ref_spurious(void *hv, float overlap, float *out)
 {
     Alignment *a = ((RefAlignment *)hv)->ali;
     return a->Statistics->calculateSpuriousVector(overlap, out) ? 0 : -1;
+}
+
+/* The three Cleaner walks over the identity matrix, called on
+ * the harness's own alignment with whatever platform ref_set_platform chose:
+ *   ref_representatives : Cleaner::calculateRepresentativeSeq (Cleaner.cpp:1398-1466);
+ *                         out[0..count) = representatives in creation order
+ *   ref_cutpoint        : Cleaner::getCutPointClusters (Cleaner.cpp:1026-1156)
+ *   ref_select_method   : Cleaner::selectMethod (Cleaner.cpp:46-99); 1 = GAPPYOUT, 2 = STRICT */
+int ref_representatives(void *hv, float max_identity, int *out)
+{
+    Alignment *a = ((RefAlignment *)hv)->ali;
+    int *r = a->Cleaning->calculateRepresentativeSeq(max_identity);
+    if (!r) return -1;
+    const int count = r[0];
+    if (out) memcpy(out, r + 1, sizeof(int) * count);
+    delete[] r;
+    return count;
+}
+
+float ref_cutpoint(void *hv, int clusters)
+{
+    return ((RefAlignment *)hv)->ali->Cleaning->getCutPointClusters(clusters);
+}
+
+int ref_select_method(void *hv)
+{
+    return ((RefAlignment *)hv)->ali->Cleaning->selectMethod() == GAPPYOUT ? 1 : 2;
+}
+
+/* 1 when the identity statistic object holds a host copy of the matrix (the CUDA
+ * platform leaves it on the device until something on the host asks for it). */
+int ref_identity_on_host(void *hv)
+{
+    Alignment *a = ((RefAlignment *)hv)->ali;
+    return a->Statistics->identity && a->Statistics->identity->identities ? 1 : 0;
 }
 
 /*

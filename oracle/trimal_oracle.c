@@ -344,3 +344,196 @@ int orc_similarity_window(const float *mdk, int ncol, int half_window, float *md
     }
     return 0;
 }
+
+/* ========================================================================
+ * Consumers of the identity matrix: the three host walks
+ * of source/Cleaner.cpp over Identity::identities, for the case the
+ * reference's own index arithmetic supports (no masked rows, so
+ * numberOfSequences == originalNumberOfSequences == n).
+ * ====================================================================== */
+
+/* packed position of pair (i<j): Cleaner.cpp:72-75 / 1105-1108 / 1431-1434 */
+static inline size_t orc_pair_pos(size_t n, size_t a, size_t b)
+{
+    size_t mn = a < b ? a : b, mx = a < b ? b : a;
+    size_t sq = (mn + 1) * (mn + 1);
+    return n * mn - ((sq + (mn + 1)) / 2) + mx;
+}
+
+/* Alignment::getSequenceLength (Alignment/Alignment.cpp:296-298): bytes that are
+ * not '-' (only '-'). */
+void orc_sequence_lengths(const uint8_t *msa, int nseq, int ncol, size_t stride, int *lengths)
+{
+    for (int r = 0; r < nseq; r++) {
+        int g = 0;
+        for (int k = 0; k < ncol; k++) g += msa[(size_t)r * stride + k] == '-';
+        lengths[r] = ncol - g;
+    }
+}
+
+/* utils::quicksort(int **vect, int ini, int fin) (utils.cpp:246-273): sorts
+ * (key, index) records by key, pivot = last element held as a float, not
+ * stable.  The permutation it leaves decides the clustering order, so it is
+ * restated step by step.  key/idx are parallel arrays standing for vect[i][0]
+ * and vect[i][1]. */
+static void orc_qs(int *key, int *idx, int ini, int fin)
+{
+    if (ini >= fin || fin < 0) return;
+    float div = (float)key[fin];
+    int i = ini - 1, j = fin, t;
+    for (;;) {
+        while ((float)key[++i] < div)
+            if (i == fin) break;
+        while ((float)key[--j] > div)
+            if (j == 0) break;
+        if (i < j) {
+            t = key[i]; key[i] = key[j]; key[j] = t;
+            t = idx[i]; idx[i] = idx[j]; idx[j] = t;
+        } else
+            break;
+    }
+    t = key[i]; key[i] = key[fin]; key[fin] = t;
+    t = idx[i]; idx[i] = idx[fin]; idx[fin] = t;
+    orc_qs(key, idx, ini, i - 1);
+    orc_qs(key, idx, i + 1, fin);
+}
+
+/* Order in which calculateRepresentativeSeq / getCutPointClusters visit the
+ * sequences: seqs[] = (length, index), quicksort ascending, then walked from
+ * the END (Cleaner.cpp:1413-1426 / 1078-1089).  order[0] is the first cluster
+ * representative. */
+int orc_cluster_order(const int *lengths, int nseq, int *order)
+{
+    int *key = (int *)malloc(sizeof(int) * (nseq ? nseq : 1));
+    int *idx = (int *)malloc(sizeof(int) * (nseq ? nseq : 1));
+    if (!key || !idx) { free(key); free(idx); return ORC_ERR_NOMEM; }
+    for (int i = 0; i < nseq; i++) { key[i] = lengths[i]; idx[i] = i; }
+    orc_qs(key, idx, 0, nseq - 1);
+    for (int i = 0; i < nseq; i++) order[i] = idx[nseq - 1 - i];
+    free(key); free(idx);
+    return ORC_OK;
+}
+
+/* The greedy walk (Cleaner.cpp:1427-1447, and the inner loop :1100-1118 of
+ * getCutPointClusters, which breaks at the first hit instead of looking for
+ * the best one -- same set of representatives): order[k] opens a new cluster
+ * iff no existing representative has identity > thr with it.  Returns the
+ * number of clusters; clusters (optional) lists the representatives in
+ * creation order. */
+int orc_greedy_clusters(const float *identities, int nseq, const int *order, int count, float thr,
+                        int *clusters)
+{
+    int *cl = clusters ? clusters : (int *)malloc(sizeof(int) * (count ? count : 1));
+    int ncl = 0;
+    for (int k = 0; k < count; k++) {
+        int s = order[k], j;
+        for (j = 0; j < ncl; j++)
+            if (identities[orc_pair_pos((size_t)nseq, (size_t)s, (size_t)cl[j])] > thr) break;
+        if (j == ncl) cl[ncl++] = s;
+    }
+    if (!clusters) free(cl);
+    return ncl;
+}
+
+/* Per-row statistics.  upper_only = 0: selectMethod's inner loop
+ * (Cleaner.cpp:68-80), all j != i in ascending j; upper_only = 1:
+ * getCutPointClusters' (:1054-1063), j > i. */
+void orc_identity_row_stats(const float *identities, int nseq, int upper_only, float *row_max,
+                            float *row_min, float *row_sum)
+{
+    for (int i = 0; i < nseq; i++) {
+        float mx = 0, mn = 1, avg = 0;
+        for (int j = upper_only ? i + 1 : 0; j < nseq; j++) {
+            if (j == i) continue;
+            float v = identities[orc_pair_pos((size_t)nseq, (size_t)i, (size_t)j)];
+            mx = mx < v ? v : mx;
+            mn = v < mn ? v : mn;
+            avg += v;
+        }
+        if (row_max) row_max[i] = mx;
+        if (row_min) row_min[i] = mn;
+        if (row_sum) row_sum[i] = avg;
+    }
+}
+
+/* Cleaner::selectMethod (Cleaner.cpp:46-99).  Returns 1 for GAPPYOUT, 2 for
+ * STRICT (defines.h values are not reproduced; the caller only distinguishes
+ * the two); avg_seq / max_seq (optional) receive the two decision values. */
+int orc_select_method(const float *identities, int nseq, float *avg_seq, float *max_seq)
+{
+    float maxSeq = 0, avgSeq = 0;
+    for (int i = 0; i < nseq; i++) {
+        float mx = 0, avg = 0;
+        for (int j = 0; j < nseq; j++) {
+            if (i == j) continue;
+            float v = identities[orc_pair_pos((size_t)nseq, (size_t)i, (size_t)j)];
+            mx = mx < v ? v : mx;
+            avg += v;
+        }
+        avgSeq += avg / (nseq - 1);
+        maxSeq += mx;
+    }
+    avgSeq = avgSeq / nseq;
+    maxSeq = maxSeq / nseq;
+    if (avg_seq) *avg_seq = avgSeq;
+    if (max_seq) *max_seq = maxSeq;
+    if (avgSeq >= 0.55) return 1;
+    else if (avgSeq <= 0.38) return 2;
+    else {
+        if (nseq <= 20) return 1;
+        if ((maxSeq >= 0.5) && (maxSeq <= 0.65)) return 1;
+        return 2;
+    }
+}
+
+/* Cleaner::getCutPointClusters (Cleaner.cpp:1026-1156): the identity threshold
+ * that yields `cluster_number` clusters, found by bisection from the mean
+ * identity.  `order` as orc_cluster_order.  iterations (optional) counts the
+ * clusterings run. */
+float orc_cutpoint_clusters(const float *identities, int nseq, const int *order, int cluster_number,
+                            int *iterations)
+{
+    float max, min, avg, gMax, gMin, startingPoint, prevValue = 0, iter = 0;
+    size_t pos = 0;
+    int runs = 0;
+    if (iterations) *iterations = 0;
+    if (cluster_number == nseq) return 1;
+    else if (cluster_number == 1) return 0;
+    gMax = 0; gMin = 1; startingPoint = 0;
+    for (int i = 0; i < nseq; i++) {
+        int compared = 0;
+        avg = 0; min = 1; max = 0;
+        for (int j = i + 1; j < nseq; j++) {
+            max = max < identities[pos] ? identities[pos] : max;   /* std::max(max, v) */
+            min = identities[pos] < min ? identities[pos] : min;   /* std::min(min, v) */
+            avg += identities[pos];
+            pos++;
+            compared++;
+        }
+        if (compared > 0) {
+            startingPoint += avg / compared;
+            gMax = gMax < max ? max : gMax;
+            gMin = min < gMin ? min : gMin;
+        }
+    }
+    if (pos > 0) startingPoint /= pos;
+    for (;;) {
+        int clusterNum = orc_greedy_clusters(identities, nseq, order, nseq, startingPoint, NULL);
+        runs++;
+        if (clusterNum == cluster_number || iter > 10) break;
+        if (clusterNum > cluster_number) {
+            gMax = startingPoint;
+            startingPoint = (gMax + gMin) / 2;
+        } else {
+            gMin = startingPoint;
+            startingPoint = (gMax + gMin) / 2;
+        }
+        if (prevValue != clusterNum) {
+            iter = 0;
+            prevValue = clusterNum;
+        } else
+            iter++;
+    }
+    if (iterations) *iterations = runs;
+    return startingPoint;
+}

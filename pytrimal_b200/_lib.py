@@ -94,6 +94,14 @@ PROTOTYPES = {
                                      _f32p, _f32p, _f32p, _i32p, _i32p, _i32p]),
     "tcu_gaps_all": (C.c_int, [_h, _h, _i32p, _i32p, _i32p, _i32p]),
     "tcu_spurious_all": (C.c_int, [_h, _h, C.c_uint8, C.c_uint32, _f32p]),
+    "tcu_identity_resident": (C.c_int, [_h]),
+    "tcu_identity_download": (C.c_int, [_h, _f32p]),
+    "tcu_identity_row_stats": (C.c_int, [_h, C.c_int, _f32p, _f32p, _f32p]),
+    "tcu_identity_clusters": (C.c_int, [_h, _i32p, C.c_int, C.c_float, _i32p, _i32p]),
+    "tcu_byte_histogram": (C.c_int, [_h, C.POINTER(C.c_ulonglong)]),
+    "tcu_sequence_lengths": (C.c_int, [_h, _i32p]),
+    "tcu_cluster_order": (C.c_int, [_i32p, C.c_int, _i32p]),
+    "tcu_representatives": (C.c_int, [_h, _i32p, C.c_uint8, C.c_float, _i32p, _i32p]),
     "tcu_debug_identity_bytes": (C.c_int, [_h, _i32p, _i32p, C.c_uint8, _f32p, _i32p, _i32p]),
 }
 

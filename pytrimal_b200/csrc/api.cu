@@ -12,6 +12,8 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "nccl_dyn.h"
@@ -1012,6 +1014,260 @@ extern "C" int tcu_debug_identity_bytes(tcu_msa *m, const int *save_seq, const i
                                         int *dst_out)
 {
     return identity_host(m, save_seq, save_res, indet, identities, hit_out, dst_out, 0, true);
+}
+
+// ---------------------------------------------------------------------------
+// consumers of the device-resident identity matrix (clusters.cu)
+// ---------------------------------------------------------------------------
+extern "C" int tcu_identity_resident(const tcu_msa *m)
+{
+    return m && m->ident_full && (m->d_ident || m->nseq < 2) ? 1 : 0;
+}
+
+static int need_resident(tcu_msa *m)
+{
+    if (!m) return fail(TCU_ERR_INVALID, "msa is NULL");
+    if (!tcu_identity_resident(m))
+        return fail(TCU_ERR_STATE,
+                    "no device-resident identity matrix: call tcu_identity with keep_on_device=1 "
+                    "and all rows kept first");
+    CK(cudaSetDevice(m->device));
+    m->timings = tcu_timings{};
+    return TCU_OK;
+}
+
+extern "C" int tcu_identity_download(tcu_msa *m, float *identities)
+{
+    int rc = need_resident(m);
+    if (rc != TCU_OK) return rc;
+    if (!identities) return fail(TCU_ERR_INVALID, "identities is NULL");
+    const size_t npairs = (size_t)m->nseq * (size_t)std::max(m->nseq - 1, 0) / 2;
+    if (npairs == 0) return TCU_OK;
+    CK(cudaEventRecord(m->ev[0], m->stream));
+    CK(cudaMemcpyAsync(identities, m->d_ident, npairs * sizeof(float), cudaMemcpyDeviceToHost,
+                       m->stream));
+    CK(cudaEventRecord(m->ev[1], m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    m->timings.d2h_ms = ev_ms(m->ev[0], m->ev[1]);
+    return TCU_OK;
+}
+
+extern "C" int tcu_identity_row_stats(tcu_msa *m, int upper_only, float *row_max, float *row_min,
+                                      float *row_sum)
+{
+    int rc = need_resident(m);
+    if (rc != TCU_OK) return rc;
+    const int n = m->nseq;
+    if (n == 0) return TCU_OK;
+    const size_t vec = ((size_t)n * sizeof(float) + 255) / 256 * 256;
+    rc = ensure(&m->d_scratch, &m->scratch_cap, 3 * vec);
+    if (rc != TCU_OK) return rc;
+    float *d_max = (float *)m->d_scratch;
+    float *d_min = (float *)((uint8_t *)m->d_scratch + vec);
+    float *d_sum = (float *)((uint8_t *)m->d_scratch + 2 * vec);
+    CK(cudaEventRecord(m->ev[1], m->stream));
+    // n == 1: no pairs, the kernel only writes the neutral values (0, 1, 0)
+    CK(launch_row_stats(m->d_ident, n, upper_only != 0, d_max, d_min, d_sum, m->stream));
+    CK(cudaEventRecord(m->ev[2], m->stream));
+    if (row_max) CK(cudaMemcpyAsync(row_max, d_max, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
+    if (row_min) CK(cudaMemcpyAsync(row_min, d_min, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
+    if (row_sum) CK(cudaMemcpyAsync(row_sum, d_sum, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaEventRecord(m->ev[3], m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    m->timings.kernel_ms = ev_ms(m->ev[1], m->ev[2]);
+    m->timings.d2h_ms = ev_ms(m->ev[2], m->ev[3]);
+    m->timings.kernel_launches = 1;
+    return TCU_OK;
+}
+
+extern "C" int tcu_identity_clusters(tcu_msa *m, const int *order, int count, float threshold,
+                                     int *clusters, int *n_clusters)
+{
+    int rc = need_resident(m);
+    if (rc != TCU_OK) return rc;
+    if (!n_clusters || (count > 0 && !order)) return fail(TCU_ERR_INVALID, "NULL argument");
+    const int n = m->nseq;
+    if (count < 0 || count > n) return fail(TCU_ERR_INVALID, "count %d outside [0,%d]", count, n);
+    for (int k = 0; k < count; k++)
+        if (order[k] < 0 || order[k] >= n)
+            return fail(TCU_ERR_INVALID, "order[%d] = %d outside [0,%d)", k, order[k], n);
+    *n_clusters = 0;
+    if (count == 0) return TCU_OK;
+    const int W = (n + 31) / 32;
+    auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+    const size_t bits_b = up((size_t)n * W * 4), rep_b = up((size_t)W * 4 + 4);
+    const size_t ord_b = up((size_t)count * 4), alive_b = up((size_t)mis_block());
+    const size_t adj_b = up((size_t)mis_block() * 32 * 4);
+    rc = ensure(&m->d_scratch, &m->scratch_cap, bits_b + rep_b + 2 * ord_b + alive_b + adj_b);
+    if (rc != TCU_OK) return rc;
+    uint8_t *p = (uint8_t *)m->d_scratch;
+    uint32_t *d_bits = (uint32_t *)p;
+    p += bits_b;
+    uint32_t *d_rep = (uint32_t *)p;  // W words, then the cluster counter
+    int *d_count = (int *)(d_rep + W);
+    p += rep_b;
+    int *d_order = (int *)p;
+    p += ord_b;
+    int *d_clusters = (int *)p;
+    p += ord_b;
+    uint8_t *d_alive = p;
+    p += alive_b;
+    uint32_t *d_adj = (uint32_t *)p;
+    CK(cudaEventRecord(m->ev[0], m->stream));
+    CK(cudaMemcpyAsync(d_order, order, (size_t)count * 4, cudaMemcpyHostToDevice, m->stream));
+    CK(cudaMemsetAsync(d_rep, 0, rep_b, m->stream));
+    CK(cudaEventRecord(m->ev[1], m->stream));
+    CK(launch_identity_bits(m->d_ident, n, W, threshold, d_bits, m->stream));
+    CK(cudaEventRecord(m->ev[2], m->stream));
+    CK(launch_greedy_clusters(d_bits, W, d_order, count, d_rep, d_alive, d_adj, d_clusters, d_count,
+                              m->stream));
+    CK(cudaEventRecord(m->ev[3], m->stream));
+    int found = 0;
+    CK(cudaMemcpyAsync(&found, d_count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    if (clusters && found > 0)
+        CK(cudaMemcpyAsync(clusters, d_clusters, (size_t)found * 4, cudaMemcpyDeviceToHost,
+                           m->stream));
+    CK(cudaEventRecord(m->ev[4], m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    *n_clusters = found;
+    m->timings.h2d_ms = ev_ms(m->ev[0], m->ev[1]);
+    m->timings.pack_ms = ev_ms(m->ev[1], m->ev[2]);    // threshold -> bit matrix
+    m->timings.kernel_ms = ev_ms(m->ev[2], m->ev[3]);  // greedy clustering
+    m->timings.d2h_ms = ev_ms(m->ev[3], m->ev[4]);
+    m->timings.kernel_launches = 1 + 2 * ((count + mis_block() - 1) / mis_block());
+    return TCU_OK;
+}
+
+extern "C" int tcu_byte_histogram(tcu_msa *m, unsigned long long *hist256)
+{
+    if (!m || !hist256) return fail(TCU_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(m->device));
+    m->timings = tcu_timings{};
+    memset(hist256, 0, 256 * sizeof(unsigned long long));
+    if (m->nseq == 0 || m->ncol == 0) return TCU_OK;
+    int rc = ensure(&m->d_scratch, &m->scratch_cap, 256 * sizeof(unsigned long long));
+    if (rc != TCU_OK) return rc;
+    unsigned long long *d_hist = (unsigned long long *)m->d_scratch;
+    CK(cudaMemsetAsync(d_hist, 0, 256 * sizeof(unsigned long long), m->stream));
+    CK(cudaEventRecord(m->ev[1], m->stream));
+    CK(launch_byte_histogram(m->d_raw, m->nseq, m->ncol, m->pitch, d_hist, m->num_sms, m->stream));
+    CK(cudaEventRecord(m->ev[2], m->stream));
+    CK(cudaMemcpyAsync(hist256, d_hist, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                       m->stream));
+    CK(cudaEventRecord(m->ev[3], m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    m->timings.kernel_ms = ev_ms(m->ev[1], m->ev[2]);
+    m->timings.d2h_ms = ev_ms(m->ev[2], m->ev[3]);
+    m->timings.kernel_launches = 1;
+    return TCU_OK;
+}
+
+extern "C" int tcu_sequence_lengths(tcu_msa *m, int *lengths)
+{
+    if (!m || !lengths) return fail(TCU_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(m->device));
+    m->timings = tcu_timings{};
+    if (m->nseq == 0) return TCU_OK;
+    int rc = ensure(&m->d_scratch, &m->scratch_cap, (size_t)m->nseq * sizeof(int));
+    if (rc != TCU_OK) return rc;
+    CK(cudaEventRecord(m->ev[1], m->stream));
+    CK(launch_row_lengths(m->d_raw, m->nseq, m->ncol, m->pitch, (int *)m->d_scratch, m->stream));
+    CK(cudaEventRecord(m->ev[2], m->stream));
+    CK(cudaMemcpyAsync(lengths, m->d_scratch, (size_t)m->nseq * sizeof(int), cudaMemcpyDeviceToHost,
+                       m->stream));
+    CK(cudaEventRecord(m->ev[3], m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    m->timings.kernel_ms = ev_ms(m->ev[1], m->ev[2]);
+    m->timings.d2h_ms = ev_ms(m->ev[2], m->ev[3]);
+    m->timings.kernel_launches = 1;
+    return TCU_OK;
+}
+
+// Host only.  The visiting order of the two clustering walks: records (length, index)
+// sorted ascending by the reference's own quicksort -- pivot = last element, compared as a
+// float, Hoare-style scans that stop on equal keys, not stable -- and then walked from the
+// end (Cleaner.cpp:1413-1426, utils.cpp:246-273).  The permutation a non-stable sort leaves
+// among equal lengths decides which sequence represents a cluster, so the partition steps
+// are replayed exactly; recursion is replaced by an explicit stack (sorted inputs make the
+// reference recurse n deep).
+extern "C" int tcu_cluster_order(const int *lengths, int nseq, int *order)
+{
+    if (nseq < 0 || (nseq > 0 && (!lengths || !order))) return fail(TCU_ERR_INVALID, "bad argument");
+    struct Rec {
+        int key, idx;
+    };
+    std::vector<Rec> v((size_t)nseq);
+    for (int i = 0; i < nseq; i++) v[i] = Rec{lengths[i], i};
+    std::vector<std::pair<int, int>> todo;
+    todo.emplace_back(0, nseq - 1);
+    while (!todo.empty()) {
+        const int ini = todo.back().first, fin = todo.back().second;
+        todo.pop_back();
+        if (ini >= fin || fin < 0) continue;
+        const float pivot = (float)v[fin].key;
+        int i = ini - 1, j = fin;
+        for (;;) {
+            while ((float)v[++i].key < pivot)
+                if (i == fin) break;
+            while ((float)v[--j].key > pivot)
+                if (j == 0) break;
+            if (i < j)
+                std::swap(v[i], v[j]);
+            else
+                break;
+        }
+        std::swap(v[i], v[fin]);
+        // the two halves are independent; order of processing does not change the result
+        todo.emplace_back(i + 1, fin);
+        todo.emplace_back(ini, i - 1);
+    }
+    for (int i = 0; i < nseq; i++) order[i] = v[nseq - 1 - i].idx;
+    return TCU_OK;
+}
+
+// Cleaner::calculateRepresentativeSeq in one call: identity matrix (left on the device),
+// sequence lengths, visiting order, greedy clustering.
+extern "C" int tcu_representatives(tcu_msa *m, const int *save_res, uint8_t indet, float threshold,
+                                   int *clusters, int *n_clusters)
+{
+    if (!m || !n_clusters) return fail(TCU_ERR_INVALID, "NULL argument");
+    tcu_timings total{};
+    auto add = [&](const tcu_timings &t) {
+        total.h2d_ms += t.h2d_ms;
+        total.pack_ms += t.pack_ms;
+        total.kernel_ms += t.kernel_ms;
+        total.d2h_ms += t.d2h_ms;
+        total.kernel_launches += t.kernel_launches;
+    };
+    // lengths first (one tiny kernel), so that the host-side sort of the visiting order
+    // runs on another thread while the GPU computes the identity matrix
+    std::vector<int> lengths((size_t)m->nseq), order((size_t)m->nseq);
+    int rc = tcu_sequence_lengths(m, lengths.data());
+    if (rc != TCU_OK) return rc;
+    add(m->timings);
+    int sort_rc = TCU_OK;
+    std::string sort_err;
+    auto sort = [&]() {
+        sort_rc = tcu_cluster_order(lengths.data(), m->nseq, order.data());
+        if (sort_rc != TCU_OK) sort_err = g_last_error;  // thread-local: carry it over
+    };
+    std::thread sorter;
+    try {
+        sorter = std::thread(sort);
+    } catch (...) {  // no thread to be had: sort here, nothing may escape the C ABI
+        sort();
+    }
+    rc = tcu_identity(m, nullptr, save_res, indet, nullptr, nullptr, nullptr, 1);
+    if (sorter.joinable()) sorter.join();
+    if (rc != TCU_OK) return rc;
+    add(m->timings);
+    if (sort_rc != TCU_OK) return fail(sort_rc, "%s", sort_err.c_str());
+    rc = tcu_identity_clusters(m, order.data(), m->nseq, threshold, clusters, n_clusters);
+    if (rc != TCU_OK) return rc;
+    add(m->timings);
+    m->timings = total;
+    return TCU_OK;
 }
 
 // ---------------------------------------------------------------------------

@@ -179,4 +179,38 @@ cudaError_t launch_spurious_rows(const uint8_t *raw, int nseq, int row_begin, in
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// Sequence lengths: Alignment::getSequenceLength (source/Alignment/Alignment.cpp:296-298)
+// for every row = ncol - number of '-' bytes.  One warp per row, 16 bytes per lane per
+// step; the zero padding up to `pitch` never matches '-'.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_row_lengths(const uint8_t *__restrict__ raw, int nseq,
+                                                     int ncol, size_t pitch,
+                                                     int *__restrict__ lengths)
+{
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= nseq) return;
+    const uint4 *p = reinterpret_cast<const uint4 *>(raw + (size_t)row * pitch);
+    const uint32_t dash = 0x2d2d2d2du;
+    int c = 0;
+    for (int k = lane; k < (int)(pitch / 16); k += 32) {
+        const uint4 v = __ldg(p + k);
+        c += __popc(byte_eq_ones(v.x, dash)) + __popc(byte_eq_ones(v.y, dash)) +
+             __popc(byte_eq_ones(v.z, dash)) + __popc(byte_eq_ones(v.w, dash));
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0) lengths[row] = ncol - c;
+}
+
+cudaError_t launch_row_lengths(const uint8_t *raw, int nseq, int ncol, size_t pitch, int *lengths,
+                               cudaStream_t stream)
+{
+    if (nseq == 0) return cudaSuccess;
+    const long long threads = (long long)nseq * 32;
+    k_row_lengths<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(raw, nseq, ncol, pitch,
+                                                                         lengths);
+    return cudaGetLastError();
+}
+
 }  // namespace tcu

@@ -48,6 +48,65 @@ cudaError_t launch_byte_presence(const uint8_t *raw, int nseq, int ncol, size_t 
 }
 
 // ---------------------------------------------------------------------------
+// 256-bin histogram of the bytes in columns [0, ncol) of every row: everything
+// utils::checkAlignmentType (source/utils.cpp:476-545) derives from its scan of the
+// alignment is a sum of these bins.  16 bytes per thread per step; runs of equal bytes
+// inside the 16 (gap stretches) are merged before they reach the warp-private
+// shared-memory bins, which keeps same-address atomics rare.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_byte_histogram(const uint8_t *__restrict__ raw, int nseq,
+                                                        int ncol, size_t pitch,
+                                                        unsigned long long *__restrict__ hist256)
+{
+    __shared__ unsigned int bins[8][256];
+    for (int k = threadIdx.x; k < 8 * 256; k += 256) (&bins[0][0])[k] = 0;
+    __syncthreads();
+    unsigned int *mine = bins[threadIdx.x >> 5];
+
+    const int groups = (ncol + 15) >> 4;
+    const long long total = (long long)nseq * groups;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(idx / groups);
+        const int g = (int)(idx - (long long)r * groups);
+        const uint4 v = *reinterpret_cast<const uint4 *>(raw + (size_t)r * pitch + (size_t)g * 16);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        const int valid = min(16, ncol - g * 16);
+        uint32_t prev = w[0] & 0xFF, run = 0;
+#pragma unroll
+        for (int b = 0; b < 16; b++) {
+            if (b < valid) {
+                const uint32_t c = (w[b >> 2] >> ((b & 3) * 8)) & 0xFF;
+                if (c == prev) {
+                    run++;
+                } else {
+                    atomicAdd(&mine[prev], run);
+                    prev = c;
+                    run = 1;
+                }
+            }
+        }
+        if (run) atomicAdd(&mine[prev], run);
+    }
+    __syncthreads();
+    unsigned long long sum = 0;
+#pragma unroll
+    for (int wq = 0; wq < 8; wq++) sum += bins[wq][threadIdx.x];
+    if (sum) atomicAdd(&hist256[threadIdx.x], sum);
+}
+
+// hist256 must be zeroed by the caller
+cudaError_t launch_byte_histogram(const uint8_t *raw, int nseq, int ncol, size_t pitch,
+                                  unsigned long long *hist256, int num_sms, cudaStream_t stream)
+{
+    if (nseq == 0 || ncol == 0) return cudaSuccess;
+    const long long total = (long long)nseq * ((ncol + 15) >> 4);
+    int blocks = (int)std::min<long long>((total + 255) / 256, (long long)num_sms * 8);
+    k_byte_histogram<<<blocks, 256, 0, stream>>>(raw, nseq, ncol, pitch, hist256);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // The identity operand (layout: tcu_internal.cuh).  One CTA per (chunk, block): 64 rows x
 // 128 columns.  A warp takes one (row, 32-column word) at a time: each lane maps
 // one byte through the code LUT, the plane words are formed with warp ballots,

@@ -2,12 +2,14 @@
 // 126-148 (four thin overrides), with the SIMD template calls replaced by the
 // C ABI of libtrimal_cuda.  Error convention: never throw; report
 // through debug.report(...) and return false / leave zero-filled outputs.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <map>
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "Alignment/Alignment.h"
@@ -17,6 +19,7 @@
 #include "Statistics/similarityMatrix.h"
 #include "defines.h"
 #include "reportsystem.h"
+#include "residueValues.h"
 #include "trimal_cuda.h"
 #include "utils.h"
 
@@ -78,6 +81,78 @@ std::shared_ptr<CUDAContext> CUDAContext::acquire(Alignment *alig)
 }
 
 // ---------------------------------------------------------------------------
+// Alignment type.  The reference classifies every byte with seven string searches
+// (utils.cpp:487-512); all it keeps are six counters, i.e. sums over byte values, so
+// one 256-bin histogram from the device and the same membership tests per byte VALUE
+// give the same counters, the same early NotDefined and the same warnings.
+// ---------------------------------------------------------------------------
+bool cudaAlignmentType(const Alignment *calig, int *type)
+{
+  StartTiming("bool cudaAlignmentType(const Alignment *, int *) ");
+  Alignment *alig = const_cast<Alignment *>(calig);
+  const int n = alig->originalNumberOfSequences, L = alig->originalNumberOfResidues;
+  if (alig->sequences == nullptr || n <= 0 || L <= 0 || alig->numberOfSequences != n) return false;
+  for (int i = 0; i < n; i++)
+    if (alig->sequences[i].size() != (size_t)L) return false;
+  std::shared_ptr<CUDAContext> ctx = CUDAContext::acquire(alig);
+  if (!ctx) return false;
+  unsigned long long hist[256];
+  {
+    std::lock_guard<std::mutex> lk(ctx->mutex);
+    if (tcu_byte_histogram(ctx->handle, hist) != TCU_OK) {
+      report_failure("CUDA platform: byte histogram failed");
+      return false;
+    }
+  }
+  static const std::string dna = "ACGT", rna = "ACGU", gapSymbols = "-?.";  // utils.cpp:477-480
+  size_t rnaCount = 0, dnaCount = 0, degNtCount = 0, aaCount = 0, degAaCount = 0, altAaCount = 0;
+  for (int b = 0; b < 256; b++) {
+    const size_t k = hist[b];
+    if (k == 0) continue;
+    char c = (char)b;
+    if (utils::checkPattern(gapSymbols, c)) continue;
+    c = utils::toUpper(c);
+    const bool isRNA = utils::checkPattern(rna, c), isDNA = utils::checkPattern(dna, c);
+    const bool isDegNN = utils::checkPattern(degenerateNucleotideResidues, c);
+    const bool isAA = utils::checkPattern(aminoAcidResidues, c);
+    const bool isDegAA = utils::checkPattern(ambiguousAA, c);
+    const bool isAltAA = utils::checkPattern(alternativeAminoAcidResidues, c);
+    if (!(isRNA || isDNA || isDegNN || isAA || isDegAA || isAltAA)) {
+      *type = SequenceTypes::NotDefined;  // utils.cpp:501-503: first unknown symbol ends the scan
+      return true;
+    }
+    if (isRNA) rnaCount += k;
+    if (isDNA) dnaCount += k;
+    if (isDegNN && !isDNA && !isRNA) degNtCount += k;
+    if (isAA) aaCount += k;
+    if (isDegAA) degAaCount += k;
+    if (isAltAA) altAaCount += k;
+  }
+  // decision and warnings of utils.cpp:514-545
+  dnaCount += degNtCount;
+  rnaCount += degNtCount;
+  aaCount += degAaCount + altAaCount;
+  if (aaCount > dnaCount && aaCount > rnaCount) {
+    if (altAaCount > 0) debug.report(WarningCode::AlternativeAminoAcids);
+    *type = degAaCount > 0 ? SequenceTypes::AA | SequenceTypes::DEG : SequenceTypes::AA;
+    return true;
+  }
+  const bool asDNA = dnaCount >= aaCount && dnaCount >= rnaCount;
+  const char *self = asDNA ? "DNA" : "RNA", *other = asDNA ? "RNA" : "DNA";
+  if (aaCount == (asDNA ? dnaCount : rnaCount))
+    debug.report(WarningCode::IndeterminateAlignmentType, new std::string[3]{self, "AA", self});
+  if (dnaCount == rnaCount)
+    debug.report(WarningCode::IndeterminateAlignmentType, new std::string[3]{self, other, self});
+  const int base = asDNA ? SequenceTypes::DNA : SequenceTypes::RNA;
+  if (degNtCount > 0) {
+    debug.report(WarningCode::DegenerateNucleotides);
+    *type = base | SequenceTypes::DEG;
+  } else
+    *type = base;
+  return true;
+}
+
+// ---------------------------------------------------------------------------
 void CUDAGaps::CalculateVectors()
 {
   StartTiming("void CUDAGaps::CalculateVectors() ");
@@ -92,9 +167,52 @@ void CUDAGaps::CalculateVectors()
     report_failure("CUDA platform: gap statistic failed");
 }
 
-void CUDAIdentity::calculateSeqIdentity()
+// Set while the caller only needs the matrix on the device (the cuda* walks below and
+// CUDASimilarity): CUDAIdentity::calculateSeqIdentity then skips the host array.
+static thread_local int t_device_only = 0;
+struct DeviceOnlyScope {
+  DeviceOnlyScope() { t_device_only++; }
+  ~DeviceOnlyScope() { t_device_only--; }
+};
+
+static bool all_rows_kept(const Alignment *alig)
 {
-  StartTiming("void CUDAIdentity::calculateSeqIdentity() ");
+  const int n = alig->originalNumberOfSequences;
+  if (alig->numberOfSequences != n) return false;
+  for (int i = 0; i < n; i++)
+    if (alig->saveSequences[i] == -1) return false;
+  return true;
+}
+
+CUDAIdentity::CUDAIdentity(Alignment *parent)
+    : Identity(parent), share(std::make_shared<IdentityShare>())
+{
+}
+
+CUDAIdentity::CUDAIdentity(Alignment *parent, Identity *parentIdentity)
+    : Identity(parent, parentIdentity)
+{
+  if (auto *mold = dynamic_cast<CUDAIdentity *>(parentIdentity)) {
+    share = mold->share;
+    ctx = mold->ctx;
+  } else {
+    share = std::make_shared<IdentityShare>();
+    share->host = identities;
+  }
+}
+
+CUDAIdentity::~CUDAIdentity()
+{
+  // the base destructor frees `identities` of the LAST object of the group
+  // (Identity.cpp:110-118); hand it the array a sibling may have materialized
+  if (identities == nullptr && share) {
+    std::lock_guard<std::mutex> lk(share->mutex);
+    identities = share->host;
+  }
+}
+
+bool CUDAIdentity::allocateHost()
+{
   const int n = alig->originalNumberOfSequences;
   // same allocation as template.h:327-328 (size computed in fp32); owned and
   // delete[]d by the base class (Identity.cpp:110-118)
@@ -102,20 +220,264 @@ void CUDAIdentity::calculateSeqIdentity()
   identities = new (std::nothrow) float[size ? size : 1];
   if (identities == nullptr) {
     report_failure("CUDA platform: identity matrix allocation failed");
-    return;
+    return false;
   }
+  return true;
+}
+
+// the four-override contract: host array filled, device copy kept when it can feed
+// the similarity statistic and the Cleaner walks
+void CUDAIdentity::computeToHost()
+{
+  const int n = alig->originalNumberOfSequences;
+  const size_t size = ((float)n * n + n) / 2;
+  if (!allocateHost()) return;
   if (!ctx) ctx = CUDAContext::acquire(alig);
   int kept = 0;
   for (int i = 0; i < n; i++) kept += alig->saveSequences[i] != -1;
-  // keep the device copy when it can feed the similarity statistic
   const int keep_on_device = kept == n;
   std::unique_lock<std::mutex> lk;
   if (ctx) lk = std::unique_lock<std::mutex>(ctx->mutex);
   if (!ctx || tcu_identity(ctx->handle, alig->saveSequences, alig->saveResidues, indet_of(alig),
                            identities, nullptr, nullptr, keep_on_device) != TCU_OK) {
-    if (ctx) report_failure("CUDA platform: identity statistic failed");
+    if (ctx) {
+      report_failure("CUDA platform: identity statistic failed");
+      ctx->ident_owner = nullptr;
+    }
     memset(identities, 0, sizeof(float) * size);
+  } else {
+    ctx->ident_owner = keep_on_device ? share.get() : nullptr;
   }
+  std::lock_guard<std::mutex> sl(share->mutex);
+  share->host = identities;
+}
+
+void CUDAIdentity::calculateSeqIdentity()
+{
+  StartTiming("void CUDAIdentity::calculateSeqIdentity() ");
+  if (t_device_only > 0 && computeOnDevice()) return;
+  if (identities != nullptr) return;
+  computeToHost();
+}
+
+bool CUDAIdentity::computeOnDevice()
+{
+  if (!all_rows_kept(alig)) return false;
+  if (!ctx) ctx = CUDAContext::acquire(alig);
+  if (!ctx) return false;
+  std::lock_guard<std::mutex> lk(ctx->mutex);
+  if (ctx->ident_owner == share.get() && tcu_identity_resident(ctx->handle)) return true;
+  {
+    // a host copy without a device copy: let the reference code walk the host array
+    std::lock_guard<std::mutex> sl(share->mutex);
+    if (identities != nullptr || share->host != nullptr) return false;
+  }
+  if (tcu_identity(ctx->handle, alig->saveSequences, alig->saveResidues, indet_of(alig), nullptr,
+                   nullptr, nullptr, /*keep_on_device=*/1) != TCU_OK) {
+    report_failure("CUDA platform: identity statistic failed");
+    ctx->ident_owner = nullptr;
+    return false;
+  }
+  ctx->ident_owner = share.get();
+  return true;
+}
+
+void CUDAIdentity::materialize()
+{
+  if (identities != nullptr) return;
+  {
+    std::lock_guard<std::mutex> sl(share->mutex);
+    if (share->host != nullptr) {
+      identities = share->host;
+      return;
+    }
+  }
+  if (ctx) {
+    std::unique_lock<std::mutex> lk(ctx->mutex);
+    if (ctx->ident_owner == share.get() && tcu_identity_resident(ctx->handle)) {
+      if (!allocateHost()) return;
+      if (tcu_identity_download(ctx->handle, identities) == TCU_OK) {
+        std::lock_guard<std::mutex> sl(share->mutex);
+        share->host = identities;
+        return;
+      }
+      report_failure("CUDA platform: identity matrix download failed");
+      delete[] identities;
+      identities = nullptr;
+    }
+  }
+  computeToHost();
+}
+
+void cudaMaterializeIdentity(Identity *identity)
+{
+  if (t_device_only > 0) return;
+  if (auto *ci = dynamic_cast<CUDAIdentity *>(identity)) ci->materialize();
+}
+
+// ---------------------------------------------------------------------------
+// Cleaner's walks over the identity matrix, on the device
+// ---------------------------------------------------------------------------
+namespace {
+
+// the CUDAIdentity of `alig` with its matrix resident on the device, or nullptr
+CUDAIdentity *device_identity(Alignment *alig)
+{
+  if (!all_rows_kept(alig)) return nullptr;
+  {
+    DeviceOnlyScope scope;
+    if (!alig->Statistics->calculateSeqIdentity()) return nullptr;
+  }
+  auto *ci = dynamic_cast<CUDAIdentity *>(alig->Statistics->identity);
+  if (ci == nullptr || !ci->computeOnDevice()) return nullptr;
+  return ci;
+}
+
+// visiting order of the clustering walks (Cleaner.cpp:1413-1426 / 1078-1089)
+bool cluster_order(CUDAContext &ctx, int n, std::vector<int> &order)
+{
+  std::vector<int> lengths((size_t)n);
+  order.resize((size_t)n);
+  std::lock_guard<std::mutex> lk(ctx.mutex);
+  return tcu_sequence_lengths(ctx.handle, lengths.data()) == TCU_OK &&
+         tcu_cluster_order(lengths.data(), n, order.data()) == TCU_OK;
+}
+
+}  // namespace
+
+bool cudaSelectMethod(Alignment *alig, int *method)
+{
+  StartTiming("bool cudaSelectMethod(Alignment *, int *) ");
+  CUDAIdentity *ci = device_identity(alig);
+  if (ci == nullptr) return false;
+  const int n = alig->numberOfSequences;
+  std::vector<float> rowMax((size_t)n), rowSum((size_t)n);
+  {
+    std::lock_guard<std::mutex> lk(ci->ctx->mutex);
+    if (tcu_identity_row_stats(ci->ctx->handle, /*upper_only=*/0, rowMax.data(), nullptr,
+                               rowSum.data()) != TCU_OK) {
+      report_failure("CUDA platform: identity row statistics failed");
+      return false;
+    }
+  }
+  // Cleaner.cpp:80-85: the per-row values enter two running fp32 sums in row order
+  float avgSeq = 0, maxSeq = 0;
+  for (int i = 0; i < n; i++) {
+    avgSeq += rowSum[i] / (n - 1);
+    maxSeq += rowMax[i];
+  }
+  avgSeq = avgSeq / n;
+  maxSeq = maxSeq / n;
+  // decision table of Cleaner.cpp:89-98
+  const bool gappy = avgSeq >= 0.55 ||
+                     (avgSeq > 0.38 && (n <= 20 || (maxSeq >= 0.5 && maxSeq <= 0.65)));
+  *method = gappy ? GAPPYOUT : STRICT;
+  return true;
+}
+
+bool cudaCutPointClusters(Alignment *alig, int clusterNumber, float *cut)
+{
+  StartTiming("bool cudaCutPointClusters(Alignment *, int, float *) ");
+  CUDAIdentity *ci = device_identity(alig);
+  if (ci == nullptr) return false;
+  const int n = alig->numberOfSequences;
+  std::vector<float> rowMax((size_t)n), rowMin((size_t)n), rowSum((size_t)n);
+  {
+    std::lock_guard<std::mutex> lk(ci->ctx->mutex);
+    if (tcu_identity_row_stats(ci->ctx->handle, /*upper_only=*/1, rowMax.data(), rowMin.data(),
+                               rowSum.data()) != TCU_OK) {
+      report_failure("CUDA platform: identity row statistics failed");
+      return false;
+    }
+  }
+  // Cleaner.cpp:1049-1071
+  float gMax = 0, gMin = 1, startingPoint = 0;
+  for (int i = 0; i < n; i++) {
+    const int compared = n - 1 - i;
+    if (compared > 0) {
+      startingPoint += rowSum[i] / compared;
+      gMax = std::max(gMax, rowMax[i]);
+      gMin = std::min(gMin, rowMin[i]);
+    }
+  }
+  const size_t pairs = (size_t)n * (size_t)(n - 1) / 2;
+  if (pairs > 0) startingPoint /= pairs;
+
+  std::vector<int> order;
+  if (!cluster_order(*ci->ctx, n, order)) {
+    report_failure("CUDA platform: clustering order failed");
+    return false;
+  }
+  // the bisection of Cleaner.cpp:1098-1147; each probe is one clustering on the device
+  float prevValue = 0, iter = 0;
+  for (;;) {
+    int clusterNum = 0;
+    {
+      std::lock_guard<std::mutex> lk(ci->ctx->mutex);
+      if (tcu_identity_clusters(ci->ctx->handle, order.data(), n, startingPoint, nullptr,
+                                &clusterNum) != TCU_OK) {
+        report_failure("CUDA platform: clustering failed");
+        return false;
+      }
+    }
+    if (clusterNum == clusterNumber || iter > 10) break;
+    if (clusterNum > clusterNumber) gMax = startingPoint;
+    else gMin = startingPoint;
+    startingPoint = (gMax + gMin) / 2;
+    if (prevValue != clusterNum) {
+      iter = 0;
+      prevValue = clusterNum;
+    } else
+      iter++;
+  }
+  *cut = startingPoint;
+  return true;
+}
+
+int *cudaRepresentativeSeq(Alignment *alig, float maximumIdent)
+{
+  StartTiming("int *cudaRepresentativeSeq(Alignment *, float) ");
+  if (!all_rows_kept(alig)) return nullptr;
+  const int n = alig->originalNumberOfSequences;
+  std::shared_ptr<CUDAContext> ctx = CUDAContext::acquire(alig);
+  if (!ctx) return nullptr;
+  // lengths first (one small kernel); the host-side sort of the visiting order then runs
+  // on another thread while the device computes the identity matrix
+  std::vector<int> lengths((size_t)n), order((size_t)n);
+  {
+    std::lock_guard<std::mutex> lk(ctx->mutex);
+    if (tcu_sequence_lengths(ctx->handle, lengths.data()) != TCU_OK) {
+      report_failure("CUDA platform: sequence lengths failed");
+      return nullptr;
+    }
+  }
+  int sort_rc = TCU_OK;
+  std::thread sorter;
+  try {
+    sorter = std::thread([&]() { sort_rc = tcu_cluster_order(lengths.data(), n, order.data()); });
+  } catch (...) {
+    sort_rc = tcu_cluster_order(lengths.data(), n, order.data());
+  }
+  CUDAIdentity *ci = device_identity(alig);
+  if (sorter.joinable()) sorter.join();
+  if (ci == nullptr || sort_rc != TCU_OK) return nullptr;
+  // Cleaner.cpp:1435-1440: a hit needs identity > maximumIdent AND > max (0 at first)
+  const float threshold = maximumIdent < 0 ? 0 : maximumIdent;
+  std::vector<int> reps((size_t)n);
+  int count = 0;
+  {
+    std::lock_guard<std::mutex> lk(ci->ctx->mutex);
+    if (tcu_identity_clusters(ci->ctx->handle, order.data(), n, threshold, reps.data(), &count) !=
+        TCU_OK) {
+      report_failure("CUDA platform: clustering failed");
+      return nullptr;
+    }
+  }
+  int *repres = new (std::nothrow) int[count + 1];  // freed by the caller (Cleaner.cpp:1201)
+  if (repres == nullptr) return nullptr;
+  repres[0] = count;
+  for (int i = 0; i < count; i++) repres[i + 1] = reps[i];
+  return repres;
 }
 
 bool CUDAOverlap::calculateSpuriousVector(float overlap, float *spuriousVector)
@@ -139,9 +501,12 @@ bool CUDASimilarity::calculateVectors(bool cutByGap)
   StartTiming("bool CUDASimilarity::calculateVectors(bool cutByGap) ");
   if (simMatrix == nullptr) return false;  // template.h:73-74
 
-  // identities first, through the manager so the object is cached (template.h:79)
-  alig->Statistics->calculateSeqIdentity();
-  const float *identities = alig->Statistics->identity->identities;
+  // identities first, through the manager so the object is cached (template.h:79); the
+  // kernel reads them on the device, so no host copy is asked for here
+  {
+    DeviceOnlyScope scope;
+    alig->Statistics->calculateSeqIdentity();
+  }
 
   int *gaps = nullptr;
   if (cutByGap) {  // template.h:87-91
@@ -166,17 +531,24 @@ bool CUDASimilarity::calculateVectors(bool cutByGap)
   int err_col = -1, err_row = -1, err_byte = 0;
   if (!ctx) ctx = CUDAContext::acquire(alig);
   if (!ctx) return false;
-  std::lock_guard<std::mutex> lk(ctx->mutex);
+  std::unique_lock<std::mutex> lk(ctx->mutex);
   // a CUDAIdentity leaves its result on the device; identities computed by any
-  // other platform are uploaded by passing the host pointer
-  const bool on_device = dynamic_cast<CUDAIdentity *>(alig->Statistics->identity) != nullptr;
+  // other platform (or whose device copy was replaced) are uploaded from the host
+  auto *cid = dynamic_cast<CUDAIdentity *>(alig->Statistics->identity);
+  const bool on_device = cid != nullptr && ctx->ident_owner == cid->share.get() &&
+                         tcu_identity_resident(ctx->handle);
+  const float *identities = nullptr;
+  if (!on_device) {
+    lk.unlock();
+    if (cid != nullptr) cid->materialize();
+    identities = alig->Statistics->identity->identities;
+    lk.lock();
+  }
   int rc = tcu_similarity(ctx->handle, indet_of(alig), dist.data(), npos, vhash, gaps,
                           gapThreshold, on_device ? nullptr : identities, num.data(), den.data(),
                           MDK, &err_col, &err_row, &err_byte);
-  if (rc == TCU_ERR_STATE)  // device copy not there (masked rows): fall back to an upload
-    rc = tcu_similarity(ctx->handle, indet_of(alig), dist.data(), npos, vhash, gaps,
-                        gapThreshold, identities, num.data(), den.data(), MDK, &err_col, &err_row,
-                        &err_byte);
+  // an uploaded matrix replaces whatever was resident
+  if (!on_device) ctx->ident_owner = cid != nullptr ? cid->share.get() : nullptr;
   if (rc == TCU_ERR_INCORRECT_SYMBOL) {  // template.h:135-138
     debug.report(ErrorCode::IncorrectSymbol, new std::string[1]{std::string(1, (char)err_byte)});
     return false;

@@ -31,6 +31,17 @@ public:
   tcu_msa *handle = nullptr;
   const void *rows_key = nullptr;  // Alignment::sequences pointer this upload belongs to
   std::mutex mutex;                // a tcu_msa handle serves one thread at a time
+  // Which group of CUDAIdentity objects (IdentityShare*) the identity matrix resident on
+  // the device belongs to; nullptr = none.  Alignment copies share the upload but may
+  // carry different identity objects (different column masks).
+  const void *ident_owner = nullptr;
+};
+
+// State shared by a CUDAIdentity and the copies the mold constructor makes of it (the
+// base class shares `identities` and `refCounter` the same way, Identity.cpp:50-58).
+struct IdentityShare {
+  std::mutex mutex;
+  float *host = nullptr;  // the packed matrix on the host once something asked for it
 };
 
 class CUDASimilarity : public Similarity {
@@ -58,13 +69,45 @@ public:
   std::shared_ptr<CUDAContext> ctx;
 };
 
+// The identity matrix may live on the device only: Cleaner's three walks over it
+// (selectMethod, getCutPointClusters, calculateRepresentativeSeq -- the cuda* functions
+// below, called from patches/Cleaner.cpp.patch) run there, so its 4*P bytes cross PCIe
+// only when host code really reads Identity::identities; every such reader goes through
+// Manager::calculateSeqIdentity, which the Manager patch makes call
+// cudaMaterializeIdentity.
 class CUDAIdentity : public Identity {
 public:
-  CUDAIdentity(Alignment *parent) : Identity(parent) {}
-  CUDAIdentity(Alignment *parent, Identity *parentIdentity) : Identity(parent, parentIdentity) {}
+  CUDAIdentity(Alignment *parent);
+  CUDAIdentity(Alignment *parent, Identity *parentIdentity);
+  ~CUDAIdentity() override;
   void calculateSeqIdentity() override;
+  // Matrix of this object's group resident on the device (computing it there when
+  // neither a device nor a host copy exists).  false: not applicable (masked rows, a
+  // host-only copy) or failed (after debug.report).
+  bool computeOnDevice();
+  // Make `identities` a valid host array (download, or compute as a last resort).
+  void materialize();
   std::shared_ptr<CUDAContext> ctx;
+  std::shared_ptr<IdentityShare> share;
+
+private:
+  bool allocateHost();
+  void computeToHost();
 };
+
+// Cleaner's walks over the identity matrix on the device.  Each
+// returns false / nullptr when it does not apply (masked rows, no device copy); the
+// caller then runs the reference code.
+bool cudaSelectMethod(Alignment *alig, int *method);                         // Cleaner.cpp:46-99
+bool cudaCutPointClusters(Alignment *alig, int clusterNumber, float *cut);   // Cleaner.cpp:1026-1156
+int *cudaRepresentativeSeq(Alignment *alig, float maximumIdent);             // Cleaner.cpp:1398-1466
+// Called by the patched Manager::calculateSeqIdentity when the object already exists.
+void cudaMaterializeIdentity(Identity *identity);
+
+// utils::checkAlignmentType (utils.cpp:476-545) from a byte histogram computed on the
+// device; called from patches/Alignment.cpp.patch.  false = not
+// applicable (trimmed alignment, ragged rows) or failed: the caller runs the reference scan.
+bool cudaAlignmentType(const Alignment *alig, int *type);
 
 // Number of usable devices; 0 makes the Cython layer refuse platform="cuda".
 int cudaPlatformDeviceCount();

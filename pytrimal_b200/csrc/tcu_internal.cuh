@@ -88,6 +88,8 @@ __host__ __device__ inline long long tiles_before2(long long sb, long long nb)
 // launchers (each enqueues on `stream` and returns the launch status)
 cudaError_t launch_byte_presence(const uint8_t *raw, int nseq, int ncol, size_t pitch,
                                  unsigned int *present256, cudaStream_t stream);
+cudaError_t launch_byte_histogram(const uint8_t *raw, int nseq, int ncol, size_t pitch,
+                                  unsigned long long *hist256, int num_sms, cudaStream_t stream);
 cudaError_t launch_pack_planes(const uint8_t *raw, size_t pitch, int ncol, const int *kept_rows,
                                int nk, const uint8_t *col_drop, const uint8_t *lut256, int np,
                                int nb2, int nchunks, uint32_t *planes, uint8_t *gbytes,
@@ -113,6 +115,19 @@ cudaError_t launch_similarity(const uint8_t *codesT, int nseq, int npad, int nco
                               const uint8_t *col_skip, const uint32_t *skipbits,
                               const unsigned long long *nbatches, int group_begin, int group_end,
                               float *num, float *den, int num_sms, cudaStream_t stream);
+
+cudaError_t launch_row_lengths(const uint8_t *raw, int nseq, int ncol, size_t pitch, int *lengths,
+                               cudaStream_t stream);
+
+// consumers of the device-resident identity matrix (clusters.cu)
+cudaError_t launch_identity_bits(const float *id, int n, int W, float thr, uint32_t *bits,
+                                 cudaStream_t stream);
+cudaError_t launch_row_stats(const float *id, int n, bool upper_only, float *row_max,
+                             float *row_min, float *row_sum, cudaStream_t stream);
+int mis_block();
+cudaError_t launch_greedy_clusters(const uint32_t *bits, int W, const int *order, int total,
+                                   uint32_t *rep, uint8_t *alive8, uint32_t *adj, int *clusters,
+                                   int *count, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------
 // PTX helpers: mbarrier + 1-D bulk async copy (TMA unit, SASS: UBLKCP)

@@ -235,6 +235,123 @@ class DeviceAlignment:
         _lib.check(rc)
         return out
 
+    # -- consumers of the device-resident identity matrix (Cleaner.cpp walks) ---
+    def identity_on_device(self, indet=None, save_res=None):
+        """Identity matrix over all rows, left on the device (nothing crosses PCIe)."""
+        indet = self.alignment.indet if indet is None else indet
+        sr = _mask(save_res, self.ncol)
+        _lib.check(self.lib.tcu_identity(self._h, None, _p(sr, _i32p), indet, None, None, None, 1))
+
+    @property
+    def identity_resident(self):
+        return bool(self.lib.tcu_identity_resident(self._h))
+
+    def identity_download(self):
+        out = np.empty(self.nseq * (self.nseq - 1) // 2, np.float32)
+        _lib.check(self.lib.tcu_identity_download(self._h, _p(out, _f32p)))
+        return out
+
+    def identity_row_stats(self, upper_only=False):
+        """(row_max, row_min, row_sum): Cleaner.cpp:68-80 (all j != i) or :1054-1063 (j > i)."""
+        mx, mn, sm = (np.zeros(self.nseq, np.float32) for _ in range(3))
+        _lib.check(self.lib.tcu_identity_row_stats(self._h, 1 if upper_only else 0, _p(mx, _f32p),
+                                                   _p(mn, _f32p), _p(sm, _f32p)))
+        return mx, mn, sm
+
+    def byte_histogram(self):
+        """Occurrences of each byte value over the whole matrix (utils.cpp:487-512)."""
+        out = (C.c_ulonglong * 256)()
+        _lib.check(self.lib.tcu_byte_histogram(self._h, out))
+        return np.array(out[:], np.uint64)
+
+    def sequence_lengths(self):
+        """Alignment::getSequenceLength of every row (Alignment.cpp:296-298)."""
+        out = np.zeros(self.nseq, np.int32)
+        _lib.check(self.lib.tcu_sequence_lengths(self._h, _p(out, _i32p)))
+        return out
+
+    def clusters(self, order, threshold, count_only=False):
+        """Greedy clustering (Cleaner.cpp:1427-1447 / 1100-1118): representatives in
+        creation order, or only their number."""
+        order = np.ascontiguousarray(order, np.int32)
+        out = None if count_only else np.zeros(max(len(order), 1), np.int32)
+        k = C.c_int(0)
+        _lib.check(self.lib.tcu_identity_clusters(self._h, _p(order, _i32p), len(order),
+                                                  C.c_float(threshold), _p(out, _i32p),
+                                                  C.byref(k)))
+        return k.value if count_only else out[: k.value].copy()
+
+    def representatives(self, threshold, indet=None, save_res=None):
+        """Cleaner::calculateRepresentativeSeq (Cleaner.cpp:1398-1466) in one library call."""
+        indet = self.alignment.indet if indet is None else indet
+        sr = _mask(save_res, self.ncol)
+        out = np.zeros(max(self.nseq, 1), np.int32)
+        k = C.c_int(0)
+        _lib.check(self.lib.tcu_representatives(self._h, _p(sr, _i32p), indet, C.c_float(threshold),
+                                                _p(out, _i32p), C.byref(k)))
+        return out[: k.value].copy()
+
+    def select_method(self):
+        """Cleaner::selectMethod (Cleaner.cpp:46-99) on the resident matrix:
+        ("gappyout" | "strict", avgSeq, maxSeq).  The O(n) tail runs here in fp32, in the
+        reference's order."""
+        n = self.nseq
+        mx, _, sm = self.identity_row_stats(upper_only=False)
+        avg_seq, max_seq = np.float32(0), np.float32(0)
+        nm1 = np.float32(n - 1)
+        for i in range(n):
+            avg_seq = np.float32(avg_seq + np.float32(sm[i] / nm1))
+            max_seq = np.float32(max_seq + mx[i])
+        avg_seq = np.float32(avg_seq / np.float32(n))
+        max_seq = np.float32(max_seq / np.float32(n))
+        if float(avg_seq) >= 0.55:
+            r = "gappyout"
+        elif float(avg_seq) <= 0.38:
+            r = "strict"
+        elif n <= 20:
+            r = "gappyout"
+        else:
+            r = "gappyout" if 0.5 <= float(max_seq) <= 0.65 else "strict"
+        return r, avg_seq, max_seq
+
+    def cutpoint_clusters(self, cluster_number, order=None):
+        """Cleaner::getCutPointClusters (Cleaner.cpp:1026-1156): (threshold, clusterings run)."""
+        n = self.nseq
+        if cluster_number == n:
+            return np.float32(1), 0
+        if cluster_number == 1:
+            return np.float32(0), 0
+        mx, mn, sm = self.identity_row_stats(upper_only=True)
+        f = np.float32
+        g_max, g_min, start = f(0), f(1), f(0)
+        for i in range(n):
+            compared = n - 1 - i
+            if compared > 0:
+                start = f(start + f(sm[i] / f(compared)))
+                g_max = max(g_max, mx[i])
+                g_min = min(g_min, mn[i])
+        pairs = n * (n - 1) // 2
+        if pairs > 0:
+            start = f(start / f(pairs))
+        if order is None:
+            order = cluster_order(self.sequence_lengths())
+        prev, it, runs = f(0), 0, 0
+        while True:
+            k = self.clusters(order, start, count_only=True)
+            runs += 1
+            if k == cluster_number or it > 10:
+                break
+            if k > cluster_number:
+                g_max = start
+            else:
+                g_min = start
+            start = f(f(g_max + g_min) / f(2))
+            if prev != f(k):
+                it, prev = 0, f(k)
+            else:
+                it += 1
+        return start, runs
+
     # -- device-resident identity (benchmarks / multi-GPU) ---------------------
     def identity_prepare(self, indet=None, save_seq=None, save_res=None):
         indet = self.alignment.indet if indet is None else indet
@@ -254,6 +371,15 @@ class DeviceAlignment:
     @property
     def stream(self):
         return self.lib.tcu_msa_stream(self._h)
+
+
+def cluster_order(lengths):
+    """Visiting order of the clustering walks (utils.cpp:246-273 + Cleaner.cpp:1413-1426);
+    host only."""
+    lengths = np.ascontiguousarray(lengths, np.int32)
+    out = np.zeros(len(lengths), np.int32)
+    _lib.check(_lib.load().tcu_cluster_order(_p(lengths, _i32p), len(lengths), _p(out, _i32p)))
+    return out
 
 
 def gaps_window(gaps_in_column, half_window):

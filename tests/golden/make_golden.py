@@ -8,7 +8,9 @@ Run in the build container (needs /root/reference and `make -C oracle ref`):
 For every chosen input alignment of the reference's own corpus it stores the
 input bytes and the reference's AVX2 results: gap counts (+window 3), the
 packed identity array, MDK (un-windowed and window 1), the spurious vector at
-two thresholds, and the keep-masks of every trimming method.  Each keep-mask
+two thresholds, the results of the three Cleaner walks over the identity matrix
+(representatives at three thresholds, cluster cut points, selectMethod), and the
+keep-masks of every trimming method.  Each keep-mask
 is first verified against the reference's committed expected output
 (vendor/trimal/dataset/trimmed_msas/<method>/ and src/pytrimal/tests/data/),
 so the fixtures are pinned to the reference's golden files, not just to our
@@ -148,6 +150,16 @@ def main():
             out["similarity_error"] = np.int32(1)
         for ov in (0.5, 0.8):
             out[f"spurious_{int(ov * 100)}"] = oracle.Ref(m).spurious(ov)
+        # the three Cleaner walks over the identity matrix, from the
+        # reference's own Cleaner::calculateRepresentativeSeq / getCutPointClusters /
+        # selectMethod on a fresh alignment each
+        if n >= 2:
+            for thr in (0.5, 0.75, 0.9):
+                out[f"repr_{int(thr * 100)}"] = oracle.Ref(m).representatives(thr)
+            ks_ = sorted({k for k in (2, 3, 5, 10, n // 2) if 1 < k < n})
+            out["cutpoint_k"] = np.array(ks_, np.int32)
+            out["cutpoint_thr"] = np.array([oracle.Ref(m).cutpoint(k) for k in ks_], np.float32)
+            out["select_method"] = np.int32(oracle.Ref(m).select_method())
         status = {}
         stem = name if name.startswith("synthetic.") else os.path.splitext(name)[0]
         for method in AUTO:

@@ -1,0 +1,184 @@
+"""GPU parity of the identity-matrix consumers: per-row statistics,
+greedy clustering, cluster cut point, selectMethod and sequence lengths, through the C
+ABI, against the oracle's restatement of the Cleaner.cpp walks and against the fixtures
+produced by the reference's own Cleaner (tests/golden)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, random_msa
+
+pytestmark = pytest.mark.gpu
+
+X = ord("X")
+FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "*.npz")))
+IDS = [os.path.basename(f)[:-4] for f in FIXTURES]
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def family_msa(n, L, seed):
+    from pytrimal_b200.synthetic import synthetic_msa
+    return synthetic_msa(n, L, seed)
+
+
+@pytest.mark.parametrize("n,L", [(2, 5), (3, 40), (31, 64), (32, 64), (33, 100), (64, 65),
+                                 (65, 300), (257, 129), (1000, 200), (1025, 64), (2100, 96)])
+def test_row_stats_lengths_and_clusters(gpu, port, n, L):
+    rng = np.random.default_rng(n * 31 + L)
+    m = family_msa(n, L, n + L) if n >= 64 else random_msa(rng, n, L)
+    with gpu.DeviceAlignment(m) as d:
+        assert not d.identity_resident
+        d.identity_on_device(X)
+        assert d.identity_resident
+        ident = d.identity_download()
+        oi = port.identity(m, X)
+        assert (bits(ident) == bits(oi)).all()
+        lengths = d.sequence_lengths()
+        assert (lengths == port.sequence_lengths(m)).all()
+        order = gpu.cluster_order(lengths)
+        assert order.tolist() == port.cluster_order(lengths).tolist()
+        for upper in (False, True):
+            mx, mn, sm = d.identity_row_stats(upper_only=upper)
+            omx, omn, osm = port.identity_row_stats(oi, n, upper)
+            assert (bits(mx) == bits(omx)).all()
+            assert (bits(mn) == bits(omn)).all()
+            assert (bits(sm) == bits(osm)).all()
+        qs = np.quantile(oi, [0.0, 0.1, 0.5, 0.9, 0.99, 1.0]) if len(oi) else [0.5]
+        for thr in [0.0, 1.0, 0.8] + [float(q) for q in qs]:
+            want = port.greedy_clusters(oi, n, order, thr)
+            got = d.clusters(order, thr)
+            assert got.tolist() == want.tolist(), thr
+            assert d.clusters(order, thr, count_only=True) == len(want)
+        # any visiting order, not only the length-sorted one
+        perm = rng.permutation(n).astype(np.int32)
+        assert d.clusters(perm, float(qs[len(qs) // 2])).tolist() == \
+            port.greedy_clusters(oi, n, perm, float(qs[len(qs) // 2])).tolist()
+        # a prefix of the order
+        half = order[: max(n // 2, 1)]
+        assert d.clusters(half, 0.5).tolist() == port.greedy_clusters(oi, n, half, 0.5).tolist()
+
+
+def test_consumers_need_a_resident_matrix(gpu):
+    m = family_msa(100, 80, 3)
+    with gpu.DeviceAlignment(m) as d:
+        with pytest.raises(gpu.TrimalCudaError):
+            d.identity_row_stats()
+        ss = np.arange(100, dtype=np.int32)
+        ss[3] = -1
+        d.identity(X, save_seq=ss, keep_on_device=True)      # masked rows: not usable
+        with pytest.raises(gpu.TrimalCudaError):
+            d.clusters(np.arange(100, dtype=np.int32), 0.5)
+        d.identity_on_device(X)
+        with pytest.raises(ValueError):
+            d.clusters(np.array([0, 100], np.int32), 0.5)    # index out of range
+        assert d.clusters(np.zeros(0, np.int32), 0.5).tolist() == []
+
+
+@pytest.mark.parametrize("n,L,seed", [(300, 200, 1), (77, 500, 2), (1200, 150, 3), (2500, 100, 4)])
+def test_select_method_cutpoint_and_representatives(gpu, port, n, L, seed):
+    m = family_msa(n, L, seed)
+    oi = port.identity(m, X)
+    order = port.cluster_order(port.sequence_lengths(m))
+    with gpu.DeviceAlignment(m) as d:
+        for thr in (0.3, 0.8, 0.95):
+            assert d.representatives(thr, indet=X).tolist() == \
+                port.greedy_clusters(oi, n, order, thr).tolist()
+        name, avg_seq, max_seq = d.select_method()
+        code, oavg, omax = port.select_method(oi, n)
+        assert bits(avg_seq) == bits(oavg) and bits(max_seq) == bits(omax)
+        assert name == {1: "gappyout", 2: "strict"}[code]
+        for k in (2, 5, n // 3, n - 1, 1, n):
+            got, runs = d.cutpoint_clusters(k)
+            want, oruns = port.cutpoint_clusters(oi, n, order, k)
+            assert bits(got) == bits(want) and runs == oruns, k
+
+
+def test_representatives_with_column_mask(gpu, port):
+    m = family_msa(400, 300, 9)
+    sr = np.arange(300, dtype=np.int32)
+    sr[np.random.default_rng(1).random(300) < 0.4] = -1
+    oi = port.identity(m, X, None, sr)
+    order = port.cluster_order(port.sequence_lengths(m))
+    with gpu.DeviceAlignment(m) as d:
+        assert d.representatives(0.7, indet=X, save_res=sr).tolist() == \
+            port.greedy_clusters(oi, 400, order, 0.7).tolist()
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=IDS)
+def test_consumers_match_reference_fixture(gpu, path):
+    """Against what the reference's own Cleaner returned (tests/golden/make_golden.py)."""
+    g = np.load(path)
+    if "select_method" not in g:
+        pytest.skip("fewer than two sequences")
+    a = gpu.Alignment.from_matrix(g["matrix"])
+    n = a.nseq
+    with gpu.DeviceAlignment(a) as d:
+        for thr in (0.5, 0.75, 0.9):
+            assert d.representatives(thr).tolist() == g[f"repr_{int(thr * 100)}"].tolist()
+        assert d.select_method()[0] == {1: "gappyout", 2: "strict"}[int(g["select_method"])]
+        for k, want in zip(g["cutpoint_k"], g["cutpoint_thr"]):
+            assert bits(d.cutpoint_clusters(int(k))[0]) == bits(want)
+
+
+def test_representatives_full_size_properties(gpu):
+    """BASELINE configs[3] (50 000 x 1 000, RepresentativeTrimmer 0.8) at full size: the
+    result must be a maximal independent set of the threshold graph in visiting order --
+    checked on the host from the downloaded matrix with vectorised numpy."""
+    from pytrimal_b200.synthetic import CONFIGS
+    n, L, seed = CONFIGS["C4"]
+    m = family_msa(n, L, seed)
+    thr = 0.8
+    with gpu.DeviceAlignment(m) as d:
+        reps = d.representatives(thr, indet=X)
+        ident = d.identity_download()
+        lengths = d.sequence_lengths()
+        order = gpu.cluster_order(lengths)
+    assert (lengths == (m != ord("-")).sum(1)).all()
+    assert len(set(reps.tolist())) == len(reps) and reps[0] == order[0]
+    rank = np.empty(n, np.int64)
+    rank[order] = np.arange(n)
+    assert (np.diff(rank[reps]) > 0).all()              # creation order = visiting order
+    is_rep = np.zeros(n, bool)
+    is_rep[reps] = True
+    rows = np.arange(n, dtype=np.int64)
+    row_base = rows * n - (rows + 1) * (rows + 2) // 2  # + j = packed position of (i, j)
+
+    def ident_row(v):
+        out = np.zeros(n, np.float32)
+        out[v + 1:] = ident[row_base[v] + v + 1: row_base[v] + n]
+        out[:v] = ident[row_base[:v] + v]
+        return out
+
+    rng = np.random.default_rng(0)
+    sample = np.concatenate([reps[:200], rng.choice(n, 1500, replace=False)])
+    for v in sample:
+        adj = ident_row(int(v)) > np.float32(thr)
+        earlier_reps = adj & is_rep & (rank < rank[v])
+        # representative <=> no earlier representative within the threshold
+        assert is_rep[v] == (not earlier_reps.any()), int(v)
+
+
+@pytest.mark.parametrize("n,L", [(1, 1), (3, 15), (7, 16), (9, 17), (100, 333), (2000, 1000)])
+def test_byte_histogram(gpu, n, L):
+    rng = np.random.default_rng(n + L)
+    m = random_msa(rng, n, L, lower=0.1, extra=b"?.*BJZUO")
+    m[rng.random((n, L)) < 0.01] = 0            # NUL bytes are data, the row padding is not
+    m[rng.random((n, L)) < 0.01] = 255
+    with gpu.DeviceAlignment(m) as d:
+        h = d.byte_histogram()
+    assert (h == np.bincount(m.reshape(-1), minlength=256).astype(np.uint64)).all()
+    assert int(h.sum()) == n * L
+
+
+def test_byte_histogram_gap_runs(gpu):
+    """Long runs of one byte (the merged-run path) and a single hot symbol."""
+    m = np.full((513, 777), ord("-"), np.uint8)
+    m[::7, 100:130] = ord("A")
+    with gpu.DeviceAlignment(m) as d:
+        h = d.byte_histogram()
+    assert (h == np.bincount(m.reshape(-1), minlength=256).astype(np.uint64)).all()

@@ -120,3 +120,85 @@ def test_cuda_platform_large_window_is_reported(dropin):
     g = np.load(os.path.join(GOLDEN, "example.001.AA.npz"))
     with pytest.raises(ValueError):
         dropin(g["matrix"], platform=oracle.PLATFORM_CUDA).trim("manual", [1 - 0.9, -1, -1, 100, -1, -1])
+
+
+# ---- Cleaner's walks over the identity matrix on the device ----------
+@pytest.mark.parametrize("path", FIXTURES, ids=IDS)
+def test_cuda_platform_cleaner_walks_match_reference_fixture(dropin, path):
+    """Cleaner::calculateRepresentativeSeq / getCutPointClusters / selectMethod of the
+    patched reference with platform CUDA, against what the unpatched reference returned."""
+    g = np.load(path)
+    if "select_method" not in g:
+        pytest.skip("fewer than two sequences")
+    m = g["matrix"]
+    for thr in (0.5, 0.75, 0.9):
+        r = dropin(m, platform=oracle.PLATFORM_CUDA)
+        assert r.representatives(thr).tolist() == g[f"repr_{int(thr * 100)}"].tolist()
+        assert not r.identity_on_host()          # the matrix never crossed PCIe
+    for k, want in zip(g["cutpoint_k"], g["cutpoint_thr"]):
+        assert bits(dropin(m, platform=oracle.PLATFORM_CUDA).cutpoint(int(k))) == bits(want)
+    assert dropin(m, platform=oracle.PLATFORM_CUDA).select_method() == int(g["select_method"])
+
+
+@pytest.mark.parametrize("shape,seed", [((400, 600), 1), ((1500, 200), 2), ((2300, 128), 3)])
+def test_cuda_platform_cleaner_walks_vs_avx2(dropin, shape, seed):
+    from pytrimal_b200.synthetic import synthetic_msa
+    m = synthetic_msa(shape[0], shape[1], seed)
+    for thr in (0.0, 0.35, 0.8, 1.0):
+        a = dropin(m, platform=oracle.PLATFORM_AVX2).representatives(thr)
+        c = dropin(m, platform=oracle.PLATFORM_CUDA).representatives(thr)
+        assert a.tolist() == c.tolist(), thr
+    for k in (2, 9, shape[0] // 5, shape[0] - 1):
+        a = dropin(m, platform=oracle.PLATFORM_AVX2).cutpoint(k)
+        c = dropin(m, platform=oracle.PLATFORM_CUDA).cutpoint(k)
+        assert bits(a) == bits(c), k
+    assert dropin(m, platform=oracle.PLATFORM_AVX2).select_method() == \
+        dropin(m, platform=oracle.PLATFORM_CUDA).select_method()
+
+
+def test_cuda_platform_identity_materializes_on_demand(dropin):
+    """After a device-side walk the host array does not exist; the first host reader
+    (through Manager::calculateSeqIdentity) downloads it, bit-identical to AVX2; the
+    similarity statistic keeps using the device copy."""
+    from pytrimal_b200.synthetic import synthetic_msa
+    m = synthetic_msa(500, 300, 11)
+    want = dropin(m, platform=oracle.PLATFORM_AVX2).identity()
+    r = dropin(m, platform=oracle.PLATFORM_CUDA)
+    reps = r.representatives(0.8)
+    assert not r.identity_on_host()
+    assert r.select_method() == dropin(m, platform=oracle.PLATFORM_AVX2).select_method()
+    assert not r.identity_on_host()
+    mdk = r.similarity()[0]                      # CUDASimilarity: device copy, no download
+    assert not r.identity_on_host()
+    assert (bits(mdk) == bits(dropin(m, platform=oracle.PLATFORM_AVX2).similarity()[0])).all()
+    got = r.identity()                           # a host reader: materialized now
+    assert r.identity_on_host()
+    assert (bits(got) == bits(want)).all()
+    assert r.representatives(0.8).tolist() == reps.tolist()   # walks still on the device copy
+
+
+# ---- SURVEY 8f rank 2: alignment type from a device byte histogram ----------------------
+@pytest.mark.parametrize("path", FIXTURES, ids=IDS)
+def test_cuda_platform_alignment_type_fixture(dropin, path):
+    g = np.load(path)
+    r = dropin(g["matrix"], platform=oracle.PLATFORM_CUDA)
+    assert r.detect_type() == int(g["alignment_type"])
+
+
+def test_cuda_platform_alignment_type_cases(dropin):
+    """Every branch of utils.cpp:514-545 plus the early NotDefined, against the AVX2 platform
+    (= the reference's own scan)."""
+    rng = np.random.default_rng(8)
+    cases = {
+        "dna": b"ACGT", "rna": b"ACGU", "tie_dna_rna": b"ACG", "deg_dna": b"ACGTRYKM",
+        "deg_rna": b"ACGURYKM", "aa": b"ARNDCQEGHILKMFPSTWYV", "aa_deg": b"ARNDCQEGHILKMFPSTWYVBXZ",
+        "aa_alt": b"ARNDCQEGHILKMFPSTWYVUO", "lower": b"acgtACGT", "undefined": b"ACGT#",
+        "digits": b"ACDE1", "gaps_only": b"-?.",
+    }
+    for name, pool in cases.items():
+        pool = np.frombuffer(pool, np.uint8)
+        m = pool[rng.integers(0, len(pool), (37, 101))].copy()
+        m[rng.random(m.shape) < 0.2] = ord("-")
+        want = dropin(m, platform=oracle.PLATFORM_AVX2, datatype=0).detect_type()
+        got = dropin(m, platform=oracle.PLATFORM_CUDA, datatype=0).detect_type()
+        assert got == want, name

@@ -186,3 +186,23 @@ def test_comm_calls_fail_loudly_without_device(lib):
     h = C.c_void_p()
     rc = lib.tcu_comm_create(C.create_string_buffer(128), 0, 1, 0, C.byref(h))
     assert rc < 0 and not h.value
+
+
+def test_cluster_order_matches_oracle(lib, port):
+    """tcu_cluster_order is host-only: the reference's non-stable quicksort permutation
+    (utils.cpp:246-273) walked from the end, against the oracle's step-by-step restatement."""
+    import pytrimal_b200 as pb
+    rng = np.random.default_rng(3)
+    cases = [np.array([], np.int32), np.array([5], np.int32), np.array([3, 3], np.int32),
+             np.arange(200, dtype=np.int32), np.arange(200, dtype=np.int32)[::-1].copy(),
+             np.full(300, 7, np.int32), rng.integers(0, 10, 1000).astype(np.int32),
+             rng.integers(500, 1000, 50000).astype(np.int32)]
+    for lengths in cases:
+        got = pb.cluster_order(lengths)
+        want = port.cluster_order(lengths)
+        assert got.tolist() == want.tolist()
+        assert sorted(got.tolist()) == list(range(len(lengths)))
+        assert (np.diff(lengths[got]) <= 0).all()     # longest first
+    # iterative: a sorted input must not overflow the stack where the recursion is n deep
+    big = np.arange(200000, dtype=np.int32)
+    assert pb.cluster_order(big)[0] == 199999

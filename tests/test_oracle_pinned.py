@@ -70,6 +70,27 @@ def test_port_matches_reference_fixture(port, path):
             assert (bits(port.similarity_window(mdk, 1)) == bits(g["mdk_w1"])).all()
 
 
+@pytest.mark.parametrize("path", FIXTURES, ids=IDS)
+def test_port_identity_consumers_match_reference_fixture(port, path):
+    """The restated Cleaner walks (calculateRepresentativeSeq, getCutPointClusters,
+    selectMethod) against what the reference's own Cleaner returned."""
+    g = np.load(path)
+    m = g["matrix"]
+    n = m.shape[0]
+    if "select_method" not in g:
+        pytest.skip("fewer than two sequences")
+    ident = g["identity"]
+    order = port.cluster_order(port.sequence_lengths(m))
+    assert sorted(order.tolist()) == list(range(n))
+    for thr in (0.5, 0.75, 0.9):
+        assert port.greedy_clusters(ident, n, order, thr).tolist() == \
+            g[f"repr_{int(thr * 100)}"].tolist()
+    for k, want in zip(g["cutpoint_k"], g["cutpoint_thr"]):
+        got, _ = port.cutpoint_clusters(ident, n, order, int(k))
+        assert bits(got) == bits(want), (int(k), got, want)
+    assert port.select_method(ident, n)[0] == int(g["select_method"])
+
+
 def test_spurious_closed_form_equals_pairwise(port):
     rng = np.random.default_rng(0)
     for n, L in [(2, 3), (7, 50), (40, 33), (120, 64)]:
@@ -114,6 +135,27 @@ def test_port_vs_live_reference_random(port, seed):
         dist, vhash = r.default_matrix()
         mdk, _, _ = port.similarity(m, ord("X"), port.identity(m, ord("X")), g, L, dist, vhash)
         assert (bits(mdk) == bits(r.similarity()[0])).all()
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", range(4))
+def test_port_identity_consumers_vs_live_reference(port, seed):
+    from pytrimal_b200.synthetic import synthetic_msa
+    n, L = [(150, 200), (333, 90), (64, 700), (500, 120)][seed]
+    m = synthetic_msa(n, L, 50 + seed)
+    if seed == 3:
+        m[:, : L // 2] = m[0, : L // 2]        # many equal lengths / high identities
+    ident = oracle.Ref(m, datatype=8).identity()
+    lengths = port.sequence_lengths(m)
+    assert (lengths == (m != ord("-")).sum(1)).all()
+    order = port.cluster_order(lengths)
+    for thr in (0.0, 0.4, 0.8, 1.0):
+        want = oracle.Ref(m, datatype=8).representatives(thr)
+        assert port.greedy_clusters(ident, n, order, thr).tolist() == want.tolist()
+    for k in (2, 7, n // 4):
+        want = oracle.Ref(m, datatype=8).cutpoint(k)
+        assert bits(port.cutpoint_clusters(ident, n, order, k)[0]) == bits(want)
+    assert port.select_method(ident, n)[0] == oracle.Ref(m, datatype=8).select_method()
 
 
 @needs_ref

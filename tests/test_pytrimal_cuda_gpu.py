@@ -126,3 +126,23 @@ def test_error_path_value_error(pytrimal):
     ali = pytrimal.Alignment([b"s1", b"s2"], [b"MKKBO", b"MKKAY"])
     with pytest.raises(ValueError):
         pytrimal.AutomaticTrimmer("strict", platform="cuda").trim(ali)
+
+
+def test_alignment_type_warnings_match(pytrimal):
+    """The type detection moved to a device histogram must raise the same Python warnings
+    (IndeterminateAlignmentType, DegenerateNucleotides, AlternativeAminoAcids) as the scan."""
+    import warnings
+    rng = np.random.default_rng(4)
+    for pool in (b"ACG", b"ACGTRYKM", b"ARNDCQEGHILKMFPSTWYVUO", b"ACGU"):
+        pool = np.frombuffer(pool, np.uint8)
+        m = pool[rng.integers(0, len(pool), (30, 80))].copy()
+        got = {}
+        for platform in ("avx2", "cuda"):
+            ali = _alignment(pytrimal, m)
+            t = pytrimal.AutomaticTrimmer("gappyout", platform=platform)
+            t.trim(ali)                                   # SURVEY F5
+            with warnings.catch_warnings(record=True) as w:
+                warnings.simplefilter("always")
+                r = t.trim(ali)
+            got[platform] = (sorted(str(x.message) for x in w), list(r.sequences))
+        assert got["avx2"] == got["cuda"], bytes(pool)

@@ -32,7 +32,7 @@ def peaks():
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="gaps,spurious,similarity")
+    ap.add_argument("--only", default="gaps,spurious,similarity")  # + "consumers" (C3/C4)
     ap.add_argument("--workloads", default="C2,C3,C5")
     ap.add_argument("--repeats", type=int, default=3)
     ap.add_argument("--rows", type=int, default=0)
@@ -85,6 +85,59 @@ def main():
                                  "frac": byts / (best_k * 1e-3) / 1e9 / hbm, "peak_source": src,
                                  "note": "closed-form column-histogram mode: 2 passes over n*L bytes"},
                     "mean": float(sp.mean())}), flush=True)
+            if "consumers" in only and wl != "C5":
+                # the Cleaner.cpp walks over the resident identity matrix
+                d.identity_on_device(X)
+                lengths = d.sequence_lengths()
+                t_len = d.timings["kernel_ms"]
+                t0 = time.perf_counter()
+                order = pb.cluster_order(lengths)
+                t_order = (time.perf_counter() - t0) * 1e3
+                rec = {"stat": "consumers", "workload": f"{wl} {n}x{L}",
+                       "lengths_kernel_ms": t_len, "cluster_order_host_ms": t_order}
+                for thr in (0.8, 0.5):
+                    best = None
+                    for _ in range(args.repeats):
+                        t0 = time.perf_counter()
+                        k = d.clusters(order, thr, count_only=True)
+                        w = (time.perf_counter() - t0) * 1e3
+                        t = d.timings
+                        if best is None or w < best["call_ms"]:
+                            best = {"clusters": k, "call_ms": w, "bits_kernel_ms": t["pack_ms"],
+                                    "greedy_ms": t["kernel_ms"], "launches": t["kernel_launches"]}
+                    best["bits_roofline"] = {
+                        "bound": "hbm", "achieved": (4 * P + n * n / 8) / (best["bits_kernel_ms"] * 1e-3) / 1e9,
+                        "peak": hbm, "unit": "GB/s",
+                        "frac": (4 * P + n * n / 8) / (best["bits_kernel_ms"] * 1e-3) / 1e9 / hbm}
+                    rec[f"clusters_thr{thr}"] = best
+                for upper in (False, True):
+                    best = 1e30
+                    for _ in range(args.repeats):
+                        d.identity_row_stats(upper_only=upper)
+                        best = min(best, d.timings["kernel_ms"])
+                    reads = (2 if not upper else 1) * 4 * P
+                    rec["row_stats_upper_ms" if upper else "row_stats_full_ms"] = best
+                    rec["row_stats_upper_gbs" if upper else "row_stats_full_gbs"] = reads / (best * 1e-3) / 1e9
+                t0 = time.perf_counter()
+                name, avg_seq, max_seq = d.select_method()
+                rec["select_method"] = {"result": name, "call_ms": (time.perf_counter() - t0) * 1e3}
+                t0 = time.perf_counter()
+                thr_k, runs = d.cutpoint_clusters(max(2, n // 100), order=order)
+                rec["cutpoint_clusters"] = {"clusters": max(2, n // 100), "threshold": float(thr_k),
+                                            "clusterings": runs,
+                                            "call_ms": (time.perf_counter() - t0) * 1e3}
+                # whole Cleaner::calculateRepresentativeSeq through one C-ABI call, host buffers
+                best = None
+                for _ in range(args.repeats):
+                    with pb.DeviceAlignment(m) as d2:
+                        t0 = time.perf_counter()
+                        reps = d2.representatives(0.8, indet=X)
+                        w = (time.perf_counter() - t0) * 1e3
+                        if best is None or w < best["call_ms"]:
+                            best = {"call_ms": w, "representatives": len(reps), **d2.timings}
+                rec["tcu_representatives_thr0.8"] = best
+                rec["pair_col_per_s_through_representatives"] = P * L / (best["call_ms"] * 1e-3)
+                print(json.dumps(rec), flush=True)
             if "similarity" in only and wl != "C5":
                 g, _, _ = d.gaps()
                 t0 = time.perf_counter()
