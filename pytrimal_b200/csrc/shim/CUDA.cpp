@@ -98,7 +98,7 @@ bool cudaAlignmentType(const Alignment *calig, int *type)
   if (!ctx) return false;
   unsigned long long hist[256];
   {
-    std::lock_guard<std::mutex> lk(ctx->mutex);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mutex);
     if (tcu_byte_histogram(ctx->handle, hist) != TCU_OK) {
       report_failure("CUDA platform: byte histogram failed");
       return false;
@@ -161,7 +161,7 @@ void CUDAGaps::CalculateVectors()
   memset(gapsInColumn, 0, sizeof(int) * L);
   if (!ctx) ctx = CUDAContext::acquire(alig);
   if (!ctx) return;
-  std::lock_guard<std::mutex> lk(ctx->mutex);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mutex);
   if (tcu_gaps(ctx->handle, alig->saveSequences, gapsInColumn, numColumnsWithGaps, &maxGaps) !=
       TCU_OK)
     report_failure("CUDA platform: gap statistic failed");
@@ -236,9 +236,10 @@ void CUDAIdentity::computeToHost()
   int kept = 0;
   for (int i = 0; i < n; i++) kept += alig->saveSequences[i] != -1;
   const int keep_on_device = kept == n;
-  std::unique_lock<std::mutex> lk;
-  if (ctx) lk = std::unique_lock<std::mutex>(ctx->mutex);
-  if (!ctx || tcu_identity(ctx->handle, alig->saveSequences, alig->saveResidues, indet_of(alig),
+  const char indet = indet_of(alig);  // before the lock: type detection may use the handle
+  std::unique_lock<std::recursive_mutex> lk;
+  if (ctx) lk = std::unique_lock<std::recursive_mutex>(ctx->mutex);
+  if (!ctx || tcu_identity(ctx->handle, alig->saveSequences, alig->saveResidues, indet,
                            identities, nullptr, nullptr, keep_on_device) != TCU_OK) {
     if (ctx) {
       report_failure("CUDA platform: identity statistic failed");
@@ -265,14 +266,15 @@ bool CUDAIdentity::computeOnDevice()
   if (!all_rows_kept(alig)) return false;
   if (!ctx) ctx = CUDAContext::acquire(alig);
   if (!ctx) return false;
-  std::lock_guard<std::mutex> lk(ctx->mutex);
+  const char indet = indet_of(alig);  // before the lock: type detection may use the handle
+  std::lock_guard<std::recursive_mutex> lk(ctx->mutex);
   if (ctx->ident_owner == share.get() && tcu_identity_resident(ctx->handle)) return true;
   {
     // a host copy without a device copy: let the reference code walk the host array
     std::lock_guard<std::mutex> sl(share->mutex);
     if (identities != nullptr || share->host != nullptr) return false;
   }
-  if (tcu_identity(ctx->handle, alig->saveSequences, alig->saveResidues, indet_of(alig), nullptr,
+  if (tcu_identity(ctx->handle, alig->saveSequences, alig->saveResidues, indet, nullptr,
                    nullptr, nullptr, /*keep_on_device=*/1) != TCU_OK) {
     report_failure("CUDA platform: identity statistic failed");
     ctx->ident_owner = nullptr;
@@ -293,7 +295,7 @@ void CUDAIdentity::materialize()
     }
   }
   if (ctx) {
-    std::unique_lock<std::mutex> lk(ctx->mutex);
+    std::unique_lock<std::recursive_mutex> lk(ctx->mutex);
     if (ctx->ident_owner == share.get() && tcu_identity_resident(ctx->handle)) {
       if (!allocateHost()) return;
       if (tcu_identity_download(ctx->handle, identities) == TCU_OK) {
@@ -338,7 +340,7 @@ bool cluster_order(CUDAContext &ctx, int n, std::vector<int> &order)
 {
   std::vector<int> lengths((size_t)n);
   order.resize((size_t)n);
-  std::lock_guard<std::mutex> lk(ctx.mutex);
+  std::lock_guard<std::recursive_mutex> lk(ctx.mutex);
   return tcu_sequence_lengths(ctx.handle, lengths.data()) == TCU_OK &&
          tcu_cluster_order(lengths.data(), n, order.data()) == TCU_OK;
 }
@@ -353,7 +355,7 @@ bool cudaSelectMethod(Alignment *alig, int *method)
   const int n = alig->numberOfSequences;
   std::vector<float> rowMax((size_t)n), rowSum((size_t)n);
   {
-    std::lock_guard<std::mutex> lk(ci->ctx->mutex);
+    std::lock_guard<std::recursive_mutex> lk(ci->ctx->mutex);
     if (tcu_identity_row_stats(ci->ctx->handle, /*upper_only=*/0, rowMax.data(), nullptr,
                                rowSum.data()) != TCU_OK) {
       report_failure("CUDA platform: identity row statistics failed");
@@ -383,7 +385,7 @@ bool cudaCutPointClusters(Alignment *alig, int clusterNumber, float *cut)
   const int n = alig->numberOfSequences;
   std::vector<float> rowMax((size_t)n), rowMin((size_t)n), rowSum((size_t)n);
   {
-    std::lock_guard<std::mutex> lk(ci->ctx->mutex);
+    std::lock_guard<std::recursive_mutex> lk(ci->ctx->mutex);
     if (tcu_identity_row_stats(ci->ctx->handle, /*upper_only=*/1, rowMax.data(), rowMin.data(),
                                rowSum.data()) != TCU_OK) {
       report_failure("CUDA platform: identity row statistics failed");
@@ -413,7 +415,7 @@ bool cudaCutPointClusters(Alignment *alig, int clusterNumber, float *cut)
   for (;;) {
     int clusterNum = 0;
     {
-      std::lock_guard<std::mutex> lk(ci->ctx->mutex);
+      std::lock_guard<std::recursive_mutex> lk(ci->ctx->mutex);
       if (tcu_identity_clusters(ci->ctx->handle, order.data(), n, startingPoint, nullptr,
                                 &clusterNum) != TCU_OK) {
         report_failure("CUDA platform: clustering failed");
@@ -445,7 +447,7 @@ int *cudaRepresentativeSeq(Alignment *alig, float maximumIdent)
   // on another thread while the device computes the identity matrix
   std::vector<int> lengths((size_t)n), order((size_t)n);
   {
-    std::lock_guard<std::mutex> lk(ctx->mutex);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mutex);
     if (tcu_sequence_lengths(ctx->handle, lengths.data()) != TCU_OK) {
       report_failure("CUDA platform: sequence lengths failed");
       return nullptr;
@@ -466,7 +468,7 @@ int *cudaRepresentativeSeq(Alignment *alig, float maximumIdent)
   std::vector<int> reps((size_t)n);
   int count = 0;
   {
-    std::lock_guard<std::mutex> lk(ci->ctx->mutex);
+    std::lock_guard<std::recursive_mutex> lk(ci->ctx->mutex);
     if (tcu_identity_clusters(ci->ctx->handle, order.data(), n, threshold, reps.data(), &count) !=
         TCU_OK) {
       report_failure("CUDA platform: clustering failed");
@@ -488,8 +490,9 @@ bool CUDAOverlap::calculateSpuriousVector(float overlap, float *spuriousVector)
       uint32_t(ceil(overlap * float(alig->originalNumberOfSequences - 1)));  // template.h:217-218
   if (!ctx) ctx = CUDAContext::acquire(alig);
   if (!ctx) return false;
-  std::lock_guard<std::mutex> lk(ctx->mutex);
-  if (tcu_spurious(ctx->handle, indet_of(alig), ovrlap, spuriousVector) != TCU_OK) {
+  const char indet = indet_of(alig);  // before the lock: type detection may use the handle
+  std::lock_guard<std::recursive_mutex> lk(ctx->mutex);
+  if (tcu_spurious(ctx->handle, indet, ovrlap, spuriousVector) != TCU_OK) {
     report_failure("CUDA platform: overlap statistic failed");
     return false;
   }
@@ -531,7 +534,8 @@ bool CUDASimilarity::calculateVectors(bool cutByGap)
   int err_col = -1, err_row = -1, err_byte = 0;
   if (!ctx) ctx = CUDAContext::acquire(alig);
   if (!ctx) return false;
-  std::unique_lock<std::mutex> lk(ctx->mutex);
+  const char indet = indet_of(alig);  // before the lock: type detection may use the handle
+  std::unique_lock<std::recursive_mutex> lk(ctx->mutex);
   // a CUDAIdentity leaves its result on the device; identities computed by any
   // other platform (or whose device copy was replaced) are uploaded from the host
   auto *cid = dynamic_cast<CUDAIdentity *>(alig->Statistics->identity);
@@ -544,7 +548,7 @@ bool CUDASimilarity::calculateVectors(bool cutByGap)
     identities = alig->Statistics->identity->identities;
     lk.lock();
   }
-  int rc = tcu_similarity(ctx->handle, indet_of(alig), dist.data(), npos, vhash, gaps,
+  int rc = tcu_similarity(ctx->handle, indet, dist.data(), npos, vhash, gaps,
                           gapThreshold, on_device ? nullptr : identities, num.data(), den.data(),
                           MDK, &err_col, &err_row, &err_byte);
   // an uploaded matrix replaces whatever was resident

@@ -30,7 +30,9 @@ public:
   ~CUDAContext();
   tcu_msa *handle = nullptr;
   const void *rows_key = nullptr;  // Alignment::sequences pointer this upload belongs to
-  std::mutex mutex;                // a tcu_msa handle serves one thread at a time
+  // a tcu_msa handle serves one thread at a time; recursive because a statistic may ask for
+  // the alignment type (another user of the handle) while it holds the lock
+  std::recursive_mutex mutex;
   // Which group of CUDAIdentity objects (IdentityShare*) the identity matrix resident on
   // the device belongs to; nullptr = none.  Alignment copies share the upload but may
   // carry different identity objects (different column masks).

@@ -199,6 +199,10 @@ def test_cuda_platform_alignment_type_cases(dropin):
         pool = np.frombuffer(pool, np.uint8)
         m = pool[rng.integers(0, len(pool), (37, 101))].copy()
         m[rng.random(m.shape) < 0.2] = ord("-")
-        want = dropin(m, platform=oracle.PLATFORM_AVX2, datatype=0).detect_type()
+        try:
+            want = dropin(m, platform=oracle.PLATFORM_AVX2, datatype=0).detect_type()
+        except ValueError:      # Alignment::fillMatrices refuses the symbols outright
+            assert name in ("undefined", "digits")
+            continue
         got = dropin(m, platform=oracle.PLATFORM_CUDA, datatype=0).detect_type()
         assert got == want, name
