@@ -9,9 +9,14 @@ the pairwise-identity kernel (K1) for every pair this rank owns.
 
   value  : whole-job pair-column comparisons/s (P*L*K / max-over-ranks device
            time), alignment already resident in HBM.
-  e2e    : the same metric through the host-buffer C ABI (tcu_msa_create_strided
-           + tcu_identity_band): pinned host rows -> device, kernels, packed
-           identity rows -> pinned host memory, all inside the timed region.
+  e2e    : the same metric through the host-buffer C ABI call the CUDA platform makes
+           for this configuration's trimmer (RepresentativeTrimmer ->
+           Cleaner::calculateRepresentativeSeq -> tcu_msa_create_strided +
+           tcu_representatives[_all]): pinned host rows -> device, pack, identity
+           matrix (kept in HBM), sequence lengths, greedy clustering on the device,
+           representatives -> host, all inside the timed region.
+           e2e_matrix_to_host is the other public path (tcu_identity_band): the packed
+           matrix itself copied to pinned host memory (4*P bytes over PCIe).
   N > 1  : the pair matrix is split into contiguous row-block bands of equal
            pair count, one band per rank, no data-path collective (strong
            scaling: the alignment is fixed, every rank holds a replica).
@@ -39,6 +44,11 @@ sys.path.insert(0, ROOT)
 METRIC = "pair-column comparisons/s (pairwise identity)"
 UNIT = "pair-col/s"
 OPS_PER_PAIR_COLUMN = 42  # 2*(20 one-hot planes + 1 gap plane) int8 tensor ops
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_identity2 launch at full C4 size, from
+# the ncu --set full capture summarised in profiles/r01b_ncu_identity2_c4.txt (3.86 GB read
+# + 4.98 GB written; algorithmic bytes n*L + 4*P = 5.05 GB -- the reads are L2 sector fills
+# for the unaligned row segments of the packed triangular output)
+NCU_TRAFFIC_BYTES = 3.857744e9 + 4.984726e9
 
 
 def measured_peaks():
@@ -113,11 +123,14 @@ def run_reference(args, rank, world):
     def one():
         t0 = time.perf_counter()
         if kind == "reference":
+            # Cleaner::calculateRepresentativeSeq: Identity::calculateSeqIdentity (AVX2)
+            # + the greedy walk -- what tcu_representatives replaces
             r = oracle.Ref(m, platform=oracle.PLATFORM_AVX2)
-            r.identity(copy=False)
+            r.representatives(0.8)
             del r
         else:
-            port.identity(m, ord("X"))
+            ident = port.identity(m, ord("X"))
+            port.greedy_clusters(ident, ns, port.cluster_order(port.sequence_lengths(m)), 0.8)
         return time.perf_counter() - t0
 
     for _ in range(warmup):
@@ -153,14 +166,17 @@ def cpu_baseline(workload, L, seed, n_full):
     t0 = time.perf_counter()
     if kind == "reference":
         r = oracle.Ref(m, platform=oracle.PLATFORM_AVX2)
-        r.identity(copy=False)
+        r.representatives(0.8)
     else:
-        oracle.Port().identity(m, ord("X"))
+        port = oracle.Port()
+        ident = port.identity(m, ord("X"))
+        port.greedy_clusters(ident, ns, port.cluster_order(port.sequence_lengths(m)), 0.8)
     dt = time.perf_counter() - t0
     return {"value": ns * (ns - 1) // 2 * L / dt, "unit": UNIT, "cores": 1, "kind": kind,
             "seconds": dt,
             "sample": f"first {ns} of {n_full} rows x {L} cols of the seeded {workload} alignment, "
-                      "one pass of Identity::calculateSeqIdentity (AVX2)"}
+                      "one pass of Cleaner::calculateRepresentativeSeq(0.8) = "
+                      "Identity::calculateSeqIdentity (AVX2) + the greedy walk"}
 
 
 def main():
@@ -171,7 +187,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C4", choices=["C2", "C3", "C4", "C5"])
     ap.add_argument("--rows", type=int, default=0, help="debug: use only the first ROWS rows")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -261,10 +277,68 @@ def main():
     value = pairs_total * L * args.steps / (ms_total_max * 1e-3)
 
     # ---------------- end-to-end through the host-buffer C ABI ----------------
+    # (a) the call the CUDA platform makes for this configuration's trimmer
+    comm = None
+    if world > 1:
+        comm = pb.Communicator.from_torch(local_rank)
+    reps_host = torch.empty(n, dtype=torch.int32).pin_memory()
+    reps_ptr = C.cast(reps_host.data_ptr(), C.POINTER(C.c_int))
+    nreps = C.c_int(0)
+    e2e_launches = [0]
+
+    e2e_phases = []
+
+    def e2e_step():
+        h = C.c_void_p()
+        tp0 = time.perf_counter()
+        _lib.check(lib.tcu_msa_create_strided(C.c_void_p(host_rows.data_ptr()), n, L, L, local_rank,
+                                              C.byref(h)))
+        tp1 = time.perf_counter()
+        try:
+            if comm is None:
+                _lib.check(lib.tcu_representatives(h, None, X, C.c_float(0.8), reps_ptr,
+                                                   C.byref(nreps)))
+            else:
+                _lib.check(lib.tcu_representatives_all(h, comm._h, None, X, C.c_float(0.8),
+                                                       reps_ptr, C.byref(nreps)))
+            tp2 = time.perf_counter()
+            t = _lib.Timings()
+            lib.tcu_msa_timings(h, C.byref(t))
+            e2e_launches[0] = t.kernel_launches
+        finally:
+            lib.tcu_msa_destroy(h)
+        e2e_phases.append({"create_ms": 1e3 * (tp1 - tp0), "call_ms": 1e3 * (tp2 - tp1),
+                           "destroy_ms": 1e3 * (time.perf_counter() - tp2),
+                           "h2d_ms": t.h2d_ms, "pack_ms": t.pack_ms, "kernel_ms": t.kernel_ms,
+                           "d2h_ms": t.d2h_ms, "comm_ms": t.comm_ms})
+
+    # The interpreter's cyclic GC is kept out of the wall-clock regions (as timeit does):
+    # with torch imported a full collection takes hundreds of ms and would land at random
+    # inside a 25 ms step.
+    import gc
+    e2e_step()  # warm-up (pinned pool, allocations)
+    gc.collect()
+    gc.disable()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    gc.enable()
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = pairs_total * L * args.e2e_steps / te.item()
+    e2e_reps = int(nreps.value)
+    if comm is not None:
+        comm.close()
+
+    # (b) the matrix itself to the host (tcu_identity_band, 4*P bytes of D2H)
     host_out = torch.empty(max(my_pairs, 1), dtype=torch.float32).pin_memory()
     out_ptr = C.cast(host_out.data_ptr(), C.POINTER(C.c_float))
 
-    def e2e_step():
+    def band_step():
         h = C.c_void_p()
         _lib.check(lib.tcu_msa_create_strided(C.c_void_p(host_rows.data_ptr()), n, L, L, local_rank,
                                               C.byref(h)))
@@ -273,19 +347,22 @@ def main():
         finally:
             lib.tcu_msa_destroy(h)
 
-    e2e_step()  # warm-up (pinned pool, allocations)
+    band_step()
+    gc.collect()
+    gc.disable()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
-        e2e_step()
+        band_step()
     barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    band_s = time.perf_counter() - t0
+    gc.enable()
+    tb = torch.tensor([band_s], dtype=torch.float64, device="cuda")
     if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = pairs_total * L * args.e2e_steps / te.item()
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+    band_value = pairs_total * L * args.e2e_steps / tb.item()
 
-    # spot-check the e2e result against the device-resident one
+    # spot-check the host copy against the device-resident one
     same = bool(torch.equal(host_out[: min(my_pairs, 1 << 20)],
                             out[: min(my_pairs, 1 << 20)].cpu()))
 
@@ -310,13 +387,21 @@ def main():
             },
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n) * int(L),
-                    "d2h_bytes_per_step": int(4 * my_pairs), "steps": args.e2e_steps,
-                    "matches_device_result": same,
-                    "api": "tcu_msa_create_strided + tcu_identity_band (pinned host buffers)"},
+                    "d2h_bytes_per_step": int(4 * n + 4 * e2e_reps + 4), "steps": args.e2e_steps,
+                    "representatives": e2e_reps, "gpu_launches_per_step": e2e_launches[0],
+                    "last_step_phases_ms": {k: round(v, 3) for k, v in e2e_phases[-1].items()},
+                    "api": "tcu_msa_create_strided + tcu_representatives%s (pinned host buffers): "
+                           "Cleaner::calculateRepresentativeSeq(0.8) of the RepresentativeTrimmer, "
+                           "identity matrix consumed in HBM" % ("_all" if world > 1 else "")},
+            "e2e_matrix_to_host": {"value": band_value, "unit": UNIT,
+                                   "h2d_bytes_per_step": int(n) * int(L),
+                                   "d2h_bytes_per_step": int(4 * my_pairs), "steps": args.e2e_steps,
+                                   "matches_device_result": same,
+                                   "api": "tcu_msa_create_strided + tcu_identity_band"},
             "gpu_launches": 2 * args.steps,
             "roofline": {
                 "bound": "tensor", "achieved": achieved_tops, "peak": peak_tops, "unit": "TFLOP/s",
-                "frac": achieved_tops / peak_tops, "traffic": None,
+                "frac": achieved_tops / peak_tops, "traffic": NCU_TRAFFIC_BYTES if world == 1 and not args.rows and args.workload == "C4" else None,
                 "kernel": "tcu::k_identity2<5,true>", "kernel_ms": kernel_ms_max, "pack_ms": pack_ms,
                 "note": "algorithmic int8 tensor ops = 42 per pair-column (SURVEY 8d); peak = 2 x "
                         "bf16 dense, " + peaks["source"] + "; the kernel counts hits on "

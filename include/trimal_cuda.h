@@ -78,8 +78,10 @@ int tcu_msa_create_strided(const uint8_t *data, int nseq, int ncol, size_t strid
 void tcu_msa_destroy(tcu_msa *msa);
 
 /*
- * The library keeps the largest freed identity buffer per device and its pinned
- * staging buffers for reuse by later handles; this returns them to the driver.
+ * The library keeps the large device buffers of destroyed handles (at most 16 per
+ * device: identity matrix, threshold bit matrix, packed planes, raw rows) and its pinned
+ * staging buffers for reuse by later handles, so that a create / compute / destroy
+ * cycle does not go through cudaMalloc / cudaFree; this returns them to the driver.
  */
 void tcu_release_cached_memory(void);
 
@@ -308,6 +310,10 @@ int tcu_gaps_all(tcu_msa *msa, tcu_comm *comm, const int *save_seq, int *gaps_in
                  int *num_cols_with_gaps, int *max_gaps);
 int tcu_spurious_all(tcu_msa *msa, tcu_comm *comm, uint8_t indet, uint32_t ovrlap,
                      float *spurious);
+/* tcu_representatives with the identity matrix computed in row bands across the ranks
+ * (tcu_identity_all); the clustering itself is sequential and runs on every rank. */
+int tcu_representatives_all(tcu_msa *msa, tcu_comm *comm, const int *save_res, uint8_t indet,
+                            float threshold, int *clusters, int *n_clusters);
 
 /* ---- test-only -------------------------------------------------------------
  * Same contract as tcu_identity (without keep_on_device), computed by a slow

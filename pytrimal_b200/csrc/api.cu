@@ -118,30 +118,37 @@ void stage_release(void *p)
 }  // namespace
 
 // ---------------------------------------------------------------------------
-// device buffer cache: the packed identity array is the one multi-GB allocation
-// (5 GB at 50 000 rows); cudaMalloc / cudaFree of it cost ~10 ms per call, so the
-// largest freed one is kept per device for the next handle
-// (tcu_release_cached_memory() returns it to the driver).
+// device buffer cache.  cudaMalloc / cudaFree synchronise the device and cost
+// milliseconds for the large buffers (the packed identity array is 5 GB at 50 000 rows,
+// the threshold bit matrix 313 MB), sometimes hundreds of milliseconds inside a process
+// that holds other big allocations.  Every device buffer of a handle therefore comes
+// from, and on tcu_msa_destroy goes back to, a small per-device pool of freed buffers
+// (at most POOL_SLOTS of them; tcu_release_cached_memory() returns them to the driver),
+// so that a create / compute / destroy cycle on same-sized alignments allocates nothing.
 // ---------------------------------------------------------------------------
 namespace {
 struct DevSlot {
     void *ptr = nullptr;
     size_t cap = 0;
 };
+constexpr int POOL_SLOTS = 16;
 std::mutex g_dev_cache_mutex;
-DevSlot g_dev_cache[64];
+DevSlot g_dev_cache[64][POOL_SLOTS];
 
+// best fit: the smallest cached buffer that holds `need` without wasting more than
+// half of itself (plus 64 MB of slack for the small ones)
 void *dev_cache_take(int device, size_t need, size_t *cap)
 {
     std::lock_guard<std::mutex> lk(g_dev_cache_mutex);
-    DevSlot &s = g_dev_cache[device & 63];
-    if (s.ptr && s.cap >= need && s.cap <= 2 * need + (64u << 20)) {
-        void *p = s.ptr;
-        *cap = s.cap;
-        s = DevSlot{};
-        return p;
-    }
-    return nullptr;
+    DevSlot *best = nullptr;
+    for (DevSlot &s : g_dev_cache[device & 63])
+        if (s.ptr && s.cap >= need && s.cap <= 2 * need + (64u << 20) && (!best || s.cap < best->cap))
+            best = &s;
+    if (!best) return nullptr;
+    void *p = best->ptr;
+    *cap = best->cap;
+    *best = DevSlot{};
+    return p;
 }
 void dev_cache_give(int device, void *ptr, size_t cap)
 {
@@ -149,11 +156,20 @@ void dev_cache_give(int device, void *ptr, size_t cap)
     void *drop = ptr;
     {
         std::lock_guard<std::mutex> lk(g_dev_cache_mutex);
-        DevSlot &s = g_dev_cache[device & 63];
-        if (cap >= (16u << 20) && cap > s.cap) {
-            drop = s.ptr;
-            s.ptr = ptr;
-            s.cap = cap;
+        DevSlot *slot = nullptr, *smallest = nullptr;
+        for (DevSlot &s : g_dev_cache[device & 63]) {
+            if (!s.ptr) {
+                slot = &s;
+                break;
+            }
+            if (!smallest || s.cap < smallest->cap) smallest = &s;
+        }
+        if (slot) {
+            *slot = DevSlot{ptr, cap};
+            drop = nullptr;
+        } else if (smallest && smallest->cap < cap) {  // full: keep the larger buffers
+            drop = smallest->ptr;
+            *smallest = DevSlot{ptr, cap};
         }
     }
     if (drop) cudaFree(drop);
@@ -165,15 +181,17 @@ extern "C" void tcu_release_cached_memory(void)
     int cur = 0;
     cudaGetDevice(&cur);
     for (int d = 0; d < 64; d++) {
-        void *p = nullptr;
-        {
-            std::lock_guard<std::mutex> lk(g_dev_cache_mutex);
-            p = g_dev_cache[d].ptr;
-            g_dev_cache[d] = DevSlot{};
-        }
-        if (p) {
-            cudaSetDevice(d);
-            cudaFree(p);
+        for (int k = 0; k < POOL_SLOTS; k++) {
+            void *p = nullptr;
+            {
+                std::lock_guard<std::mutex> lk(g_dev_cache_mutex);
+                p = g_dev_cache[d][k].ptr;
+                g_dev_cache[d][k] = DevSlot{};
+            }
+            if (p) {
+                cudaSetDevice(d);
+                cudaFree(p);
+            }
         }
     }
     cudaSetDevice(cur);
@@ -195,6 +213,7 @@ struct tcu_msa {
     int nseq = 0, ncol = 0;
     size_t pitch = 0;
     uint8_t *d_raw = nullptr;
+    size_t raw_cap = 0;
 
     // byte presence (mask independent)
     bool have_present = false;
@@ -230,13 +249,21 @@ struct tcu_msa {
     bool pending_device_timing = false;  // ev[2]..ev[3] bracket an async tcu_identity_device
 };
 
-static int ensure(void **p, size_t *cap, size_t need)
+// grow-only device buffer, pooled (see the device buffer cache above)
+static int ensure_dev(int device, void **p, size_t *cap, size_t need)
 {
     if (*cap >= need && *p) return TCU_OK;
-    if (*p) cudaFree(*p);
+    if (*p) cudaDeviceSynchronize();  // growth: queued work may still read the old buffer
+    dev_cache_give(device, *p, *cap);
     *p = nullptr;
     *cap = 0;
-    if (need == 0) need = 16;
+    need = (std::max<size_t>(need, 1) + (1u << 20) - 1) >> 20 << 20;  // 1 MB granules: poolable
+    size_t got = 0;
+    if (void *q = dev_cache_take(device, need, &got)) {
+        *p = q;
+        *cap = got;
+        return TCU_OK;
+    }
     CK(cudaMalloc(p, need));
     *cap = need;
     return TCU_OK;
@@ -244,17 +271,7 @@ static int ensure(void **p, size_t *cap, size_t need)
 
 static int ensure_ident(tcu_msa *m, size_t need)
 {
-    if (m->ident_cap >= need && m->d_ident) return TCU_OK;
-    dev_cache_give(m->device, m->d_ident, m->ident_cap);
-    m->d_ident = nullptr;
-    m->ident_cap = 0;
-    size_t cap = 0;
-    if (void *p = dev_cache_take(m->device, need, &cap)) {
-        m->d_ident = (float *)p;
-        m->ident_cap = cap;
-        return TCU_OK;
-    }
-    return ensure((void **)&m->d_ident, &m->ident_cap, need);
+    return ensure_dev(m->device, (void **)&m->d_ident, &m->ident_cap, need);
 }
 
 static float ev_ms(cudaEvent_t a, cudaEvent_t b)
@@ -441,12 +458,59 @@ static int msa_alloc(int nseq, int ncol, int device, tcu_msa **out)
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventCreate(&m->ev[i]);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreate(&m->cev[i]);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_raw, std::max<size_t>(1, (size_t)nseq) * m->pitch);
     if (e != cudaSuccess) {
         tcu_msa_destroy(m);
         return cuda_fail(e, "tcu_msa_create");
     }
+    int rc = ensure_dev(device, (void **)&m->d_raw, &m->raw_cap,
+                        std::max<size_t>(1, (size_t)nseq) * m->pitch);
+    if (rc != TCU_OK) {
+        tcu_msa_destroy(m);
+        return rc;
+    }
     *out = m;
+    return TCU_OK;
+}
+
+static size_t gather_threads()
+{
+    static const size_t n = [] {
+        unsigned hc = std::thread::hardware_concurrency();
+        return (size_t)std::max(1u, std::min(8u, hc ? hc / 2 : 1u));
+    }();
+    return n;
+}
+
+// One strided host buffer that is page-locked (cudaHostAlloc / cudaHostRegister): the DMA
+// engine reads it in place, no staging copy.
+static bool is_pinned_host(const void *p)
+{
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// Page-locked source: ONE linear DMA of the whole strided block into scratch (a 2-D copy
+// would issue a descriptor per 1000-byte row), then a device kernel lays the rows out at
+// the device pitch and zero-fills the padding.
+static int upload_strided_pinned(tcu_msa *m, const uint8_t *data, size_t stride)
+{
+    CK(cudaSetDevice(m->device));
+    const size_t bytes = (size_t)(m->nseq - 1) * stride + (size_t)m->ncol;
+    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, bytes);
+    if (rc != TCU_OK) return rc;
+    CK(cudaEventRecord(m->ev[0], m->stream));
+    CK(cudaMemcpyAsync(m->d_scratch, data, bytes, cudaMemcpyHostToDevice, m->stream));
+    CK(launch_repitch_rows((const uint8_t *)m->d_scratch, stride, m->nseq, m->ncol, m->d_raw,
+                           m->pitch, m->stream));
+    CK(cudaEventRecord(m->ev[1], m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    m->timings = tcu_timings{};
+    m->timings.h2d_ms = ev_ms(m->ev[0], m->ev[1]);
+    m->timings.kernel_launches = 1;
     return TCU_OK;
 }
 
@@ -482,9 +546,30 @@ static int upload_rows(tcu_msa *m, RowPtr row_of)
                 rc = cuda_fail(cudaGetLastError(), "staging wait");
                 break;
             }
-            for (size_t r = 0; r < nr; r++) {
-                memcpy(s + r * pitch, row_of((int)(r0 + r)), m->ncol);
-                if (pitch > (size_t)m->ncol) memset(s + r * pitch + m->ncol, 0, pitch - m->ncol);
+            // gather the rows (separate heap strings in trimAl) into the stage; split over
+            // a few threads when the stage is large -- one core copies ~5 GB/s, PCIe takes 50
+            auto gather = [&](size_t a, size_t b) {
+                for (size_t r = a; r < b; r++) {
+                    memcpy(s + r * pitch, row_of((int)(r0 + r)), m->ncol);
+                    if (pitch > (size_t)m->ncol)
+                        memset(s + r * pitch + m->ncol, 0, pitch - m->ncol);
+                }
+            };
+            const size_t workers = nr * pitch >= (4u << 20) ? gather_threads() : 1;
+            if (workers <= 1) {
+                gather(0, nr);
+            } else {
+                std::vector<std::thread> pool;
+                size_t started = 1;  // share 0 is this thread's
+                try {
+                    for (; started < workers; started++)
+                        pool.emplace_back(gather, nr * started / workers,
+                                          nr * (started + 1) / workers);
+                } catch (...) {  // no more threads to be had: the rest is done here
+                }
+                gather(0, nr / workers);
+                if (started < workers) gather(nr * started / workers, nr);
+                for (auto &t : pool) t.join();
             }
             cudaError_t e = cudaMemcpyAsync(m->d_raw + r0 * pitch, s, nr * pitch,
                                             cudaMemcpyHostToDevice, m->stream);
@@ -528,7 +613,10 @@ extern "C" int tcu_msa_create_strided(const uint8_t *data, int nseq, int ncol, s
     tcu_msa *m = nullptr;
     int rc = msa_alloc(nseq, ncol, device, &m);
     if (rc != TCU_OK) return rc;
-    rc = upload_rows(m, [&](int r) { return (const void *)(data + (size_t)r * stride); });
+    if (nseq > 0 && ncol > 0 && stride <= 2 * (size_t)ncol + 64 && is_pinned_host(data))
+        rc = upload_strided_pinned(m, data, stride);
+    else
+        rc = upload_rows(m, [&](int r) { return (const void *)(data + (size_t)r * stride); });
     if (rc != TCU_OK) {
         tcu_msa_destroy(m);
         return rc;
@@ -543,14 +631,14 @@ extern "C" void tcu_msa_destroy(tcu_msa *m)
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     if (m->copy_stream) cudaStreamSynchronize(m->copy_stream);
-    cudaFree(m->d_raw);
-    cudaFree(m->d_planes);
-    cudaFree(m->d_gbytes);
+    dev_cache_give(m->device, m->d_raw, m->raw_cap);
+    dev_cache_give(m->device, m->d_planes, m->planes_cap);
+    dev_cache_give(m->device, m->d_gbytes, m->gbytes_cap);
+    dev_cache_give(m->device, m->d_ident, m->ident_cap);
+    dev_cache_give(m->device, m->d_scratch, m->scratch_cap);
     cudaFree(m->d_kept_rows);
     cudaFree(m->d_col_drop);
     cudaFree(m->d_lut);
-    dev_cache_give(m->device, m->d_ident, m->ident_cap);
-    cudaFree(m->d_scratch);
     for (auto &e : m->ev)
         if (e) cudaEventDestroy(e);
     for (auto &e : m->cev)
@@ -610,7 +698,7 @@ static int gaps_impl(tcu_msa *m, tcu_comm *comm, const int *save_seq, int *gaps_
     const int n = m->nseq, L = m->ncol;
     if (L == 0) return TCU_OK;
     const size_t cnt_bytes = ((size_t)L * sizeof(int) + 255) / 256 * 256;
-    int rc = ensure(&m->d_scratch, &m->scratch_cap, cnt_bytes + (size_t)n + 256);
+    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, cnt_bytes + (size_t)n + 256);
     if (rc != TCU_OK) return rc;
     int *d_cnt = (int *)m->d_scratch;
     uint8_t *d_drop = nullptr;
@@ -707,7 +795,7 @@ extern "C" int tcu_identity_prepare(tcu_msa *m, const int *save_seq, const int *
     CK(cudaEventRecord(m->ev[0], m->stream));
     if (!m->have_present) {
         unsigned int *d_present = nullptr;
-        int rc = ensure(&m->d_scratch, &m->scratch_cap, 256 * sizeof(unsigned int));
+        int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, 256 * sizeof(unsigned int));
         if (rc != TCU_OK) return rc;
         d_present = (unsigned int *)m->d_scratch;
         CK(cudaMemsetAsync(d_present, 0, 256 * sizeof(unsigned int), m->stream));
@@ -751,9 +839,9 @@ extern "C" int tcu_identity_prepare(tcu_msa *m, const int *save_seq, const int *
     if (L) CK(cudaMemcpyAsync(m->d_col_drop, drop.data(), L, cudaMemcpyHostToDevice, m->stream));
     CK(cudaStreamSynchronize(m->stream));  // the host vectors go out of scope
 
-    int rc = ensure((void **)&m->d_planes, &m->planes_cap, (size_t)m->nb2 * m->nchunks * tile2_bytes(np));
+    int rc = ensure_dev(m->device, (void **)&m->d_planes, &m->planes_cap, (size_t)m->nb2 * m->nchunks * tile2_bytes(np));
     if (rc != TCU_OK) return rc;
-    rc = ensure((void **)&m->d_gbytes, &m->gbytes_cap,
+    rc = ensure_dev(m->device, (void **)&m->d_gbytes, &m->gbytes_cap,
                 (size_t)m->nb2 * m->nchunks * G_STAGES_PER_CHUNK * G_BLOCK_BYTES);
     if (rc != TCU_OK) return rc;
     CK(cudaEventRecord(m->ev[1], m->stream));
@@ -912,7 +1000,7 @@ static int identity_host(tcu_msa *m, const int *save_seq, const int *save_res, u
     int *d_hit = nullptr, *d_dst = nullptr;
     if (hit_out || dst_out) {
         // the kernel writes both or neither
-        rc = ensure(&m->d_scratch, &m->scratch_cap, 2 * npairs * sizeof(int));
+        rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, 2 * npairs * sizeof(int));
         if (rc != TCU_OK) return rc;
         d_hit = (int *)m->d_scratch;
         d_dst = d_hit + npairs;
@@ -1060,7 +1148,7 @@ extern "C" int tcu_identity_row_stats(tcu_msa *m, int upper_only, float *row_max
     const int n = m->nseq;
     if (n == 0) return TCU_OK;
     const size_t vec = ((size_t)n * sizeof(float) + 255) / 256 * 256;
-    rc = ensure(&m->d_scratch, &m->scratch_cap, 3 * vec);
+    rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, 3 * vec);
     if (rc != TCU_OK) return rc;
     float *d_max = (float *)m->d_scratch;
     float *d_min = (float *)((uint8_t *)m->d_scratch + vec);
@@ -1098,7 +1186,7 @@ extern "C" int tcu_identity_clusters(tcu_msa *m, const int *order, int count, fl
     const size_t bits_b = up((size_t)n * W * 4), rep_b = up((size_t)W * 4 + 4);
     const size_t ord_b = up((size_t)count * 4), alive_b = up((size_t)mis_block());
     const size_t adj_b = up((size_t)mis_block() * 32 * 4);
-    rc = ensure(&m->d_scratch, &m->scratch_cap, bits_b + rep_b + 2 * ord_b + alive_b + adj_b);
+    rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, bits_b + rep_b + 2 * ord_b + alive_b + adj_b);
     if (rc != TCU_OK) return rc;
     uint8_t *p = (uint8_t *)m->d_scratch;
     uint32_t *d_bits = (uint32_t *)p;
@@ -1146,7 +1234,7 @@ extern "C" int tcu_byte_histogram(tcu_msa *m, unsigned long long *hist256)
     m->timings = tcu_timings{};
     memset(hist256, 0, 256 * sizeof(unsigned long long));
     if (m->nseq == 0 || m->ncol == 0) return TCU_OK;
-    int rc = ensure(&m->d_scratch, &m->scratch_cap, 256 * sizeof(unsigned long long));
+    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, 256 * sizeof(unsigned long long));
     if (rc != TCU_OK) return rc;
     unsigned long long *d_hist = (unsigned long long *)m->d_scratch;
     CK(cudaMemsetAsync(d_hist, 0, 256 * sizeof(unsigned long long), m->stream));
@@ -1169,7 +1257,7 @@ extern "C" int tcu_sequence_lengths(tcu_msa *m, int *lengths)
     CK(cudaSetDevice(m->device));
     m->timings = tcu_timings{};
     if (m->nseq == 0) return TCU_OK;
-    int rc = ensure(&m->d_scratch, &m->scratch_cap, (size_t)m->nseq * sizeof(int));
+    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, (size_t)m->nseq * sizeof(int));
     if (rc != TCU_OK) return rc;
     CK(cudaEventRecord(m->ev[1], m->stream));
     CK(launch_row_lengths(m->d_raw, m->nseq, m->ncol, m->pitch, (int *)m->d_scratch, m->stream));
@@ -1227,9 +1315,11 @@ extern "C" int tcu_cluster_order(const int *lengths, int nseq, int *order)
 }
 
 // Cleaner::calculateRepresentativeSeq in one call: identity matrix (left on the device),
-// sequence lengths, visiting order, greedy clustering.
-extern "C" int tcu_representatives(tcu_msa *m, const int *save_res, uint8_t indet, float threshold,
-                                   int *clusters, int *n_clusters)
+// sequence lengths, visiting order, greedy clustering.  With a communicator the matrix is
+// computed in row bands across the ranks and all-gathered (tcu_identity_all); every rank
+// then runs the (sequential, cheap) clustering on its own copy and returns the full result.
+static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res, uint8_t indet,
+                                float threshold, int *clusters, int *n_clusters)
 {
     if (!m || !n_clusters) return fail(TCU_ERR_INVALID, "NULL argument");
     tcu_timings total{};
@@ -1238,6 +1328,7 @@ extern "C" int tcu_representatives(tcu_msa *m, const int *save_res, uint8_t inde
         total.pack_ms += t.pack_ms;
         total.kernel_ms += t.kernel_ms;
         total.d2h_ms += t.d2h_ms;
+        total.comm_ms += t.comm_ms;
         total.kernel_launches += t.kernel_launches;
     };
     // lengths first (one tiny kernel), so that the host-side sort of the visiting order
@@ -1258,7 +1349,8 @@ extern "C" int tcu_representatives(tcu_msa *m, const int *save_res, uint8_t inde
     } catch (...) {  // no thread to be had: sort here, nothing may escape the C ABI
         sort();
     }
-    rc = tcu_identity(m, nullptr, save_res, indet, nullptr, nullptr, nullptr, 1);
+    rc = comm ? tcu_identity_all(m, comm, nullptr, save_res, indet, nullptr)
+              : tcu_identity(m, nullptr, save_res, indet, nullptr, nullptr, nullptr, 1);
     if (sorter.joinable()) sorter.join();
     if (rc != TCU_OK) return rc;
     add(m->timings);
@@ -1268,6 +1360,20 @@ extern "C" int tcu_representatives(tcu_msa *m, const int *save_res, uint8_t inde
     add(m->timings);
     m->timings = total;
     return TCU_OK;
+}
+
+extern "C" int tcu_representatives(tcu_msa *m, const int *save_res, uint8_t indet, float threshold,
+                                   int *clusters, int *n_clusters)
+{
+    return representatives_impl(m, nullptr, save_res, indet, threshold, clusters, n_clusters);
+}
+
+extern "C" int tcu_representatives_all(tcu_msa *m, tcu_comm *comm, const int *save_res,
+                                       uint8_t indet, float threshold, int *clusters,
+                                       int *n_clusters)
+{
+    if (!comm) return fail(TCU_ERR_INVALID, "comm is NULL");
+    return representatives_impl(m, comm, save_res, indet, threshold, clusters, n_clusters);
 }
 
 // ---------------------------------------------------------------------------
@@ -1290,7 +1396,7 @@ static int spurious_impl(tcu_msa *m, tcu_comm *comm, uint8_t indet, uint32_t ovr
     }
     const size_t cnt_bytes = ((size_t)L * sizeof(int) + 255) / 256 * 256;
     const size_t out_bytes = ((size_t)n * sizeof(float) + 255) / 256 * 256;
-    int rc = ensure(&m->d_scratch, &m->scratch_cap, 2 * cnt_bytes + out_bytes + m->pitch);
+    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, 2 * cnt_bytes + out_bytes + m->pitch);
     if (rc != TCU_OK) return rc;
     int *d_cg = (int *)m->d_scratch;
     int *d_cx = (int *)((uint8_t *)m->d_scratch + cnt_bytes);
@@ -1403,7 +1509,7 @@ static int similarity_impl(tcu_msa *m, tcu_comm *comm, uint8_t indet, const floa
     const size_t nb_bytes = ((size_t)ngroups * sizeof(unsigned long long) + 255) / 256 * 256;
     const size_t need = codes_bytes + 2 * vec_bytes + dist_bytes + m->pitch + 256 + 64 + skip_bytes +
                         nb_bytes;
-    int rc = ensure(&m->d_scratch, &m->scratch_cap, need);
+    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, need);
     if (rc != TCU_OK) return rc;
     uint8_t *base = (uint8_t *)m->d_scratch;
     float *d_num = (float *)base;

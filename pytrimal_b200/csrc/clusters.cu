@@ -193,8 +193,10 @@ cudaError_t launch_row_stats(const float *id, int n, bool upper_only, float *row
 
 // ---------------------------------------------------------------------------
 // K7: one warp per sequence t of the current block (order[base .. base+cnt)).
-//   alive8[t] = no representative found so far (bitset `rep`) is adjacent to it
-//   adj[t][l] = adjacency bits to the block's sequences 32*l .. 32*l+31 that precede t
+//   alive8[t]  = no representative found so far (bitset `rep`) is adjacent to it
+//   adj[l][t]  = adjacency bits to the block's sequences 32*l .. 32*l+31 that precede t
+//                (word-major, so that K8 reads one word of 32 consecutive sequences
+//                without bank conflicts); zero for a sequence that is not alive
 // ---------------------------------------------------------------------------
 constexpr int MIS_NB = 1024;
 
@@ -220,10 +222,9 @@ __global__ void __launch_bounds__(256) k_mis_scan(const uint32_t *__restrict__ b
     for (; w < W; w += 32) acc |= row[w] & rep[w];
     const bool dead = __any_sync(0xffffffffu, acc != 0);
     if (lane == 0) alive8[t] = dead ? 0 : 1;
-    if (dead) return;
     uint32_t word = 0;
     const int a0 = lane * 32;
-    if (a0 < t) {
+    if (!dead && a0 < t) {
         const int amax = min(32, t - a0);
         if (amax == 32) {
             uint32_t g[32];
@@ -238,14 +239,20 @@ __global__ void __launch_bounds__(256) k_mis_scan(const uint32_t *__restrict__ b
             }
         }
     }
-    adj[t * 32 + lane] = word;
+    adj[lane * MIS_NB + t] = word;
 }
 
-// K8: one CTA; warp 0 walks the block's live sequences in order.  Lane l keeps the
-// representatives found among the block's sequences 32*l .. 32*l+31.  The adjacency
-// word of the NEXT live sequence is fetched from shared memory before the vote on the
-// current one, so a step costs one vote, not a load plus a vote.
-constexpr int MIS_SMEM = MIS_NB * 32 * 4 + MIS_NB * 4 + 32 * 4;
+// K8: one CTA copies the block's adjacency into shared memory; warp 0 then resolves the
+// block 32 sequences at a time, lane l owning sequence 32*g + l of group g:
+//   1. killed by a representative of an earlier group of this block?  One AND per
+//      earlier group, lanes in parallel (the representatives of group w live in lane w).
+//   2. inside the group the greedy rule is iterated to its fixed point with ballots: a
+//      sequence with an adjacent representative is out; one whose earlier neighbours
+//      are all decided and none of them a representative becomes one.  The lowest
+//      undecided lane always decides, so this ends after at most 32 rounds (2-3 in practice)
+//      and gives exactly the sequential answer.
+//   3. the new representatives are appended in visiting order (prefix popcount).
+constexpr int MIS_SMEM = MIS_NB * 32 * 4 + MIS_NB * 4 + MIS_NB;
 
 __global__ void __launch_bounds__(1024) k_mis_resolve(const uint32_t *__restrict__ adj,
                                                       const uint8_t *__restrict__ alive8,
@@ -255,57 +262,49 @@ __global__ void __launch_bounds__(1024) k_mis_resolve(const uint32_t *__restrict
                                                       int *__restrict__ count)
 {
     extern __shared__ uint32_t sm[];
-    uint32_t *s_adj = sm;                       // [MIS_NB][32]
-    int *s_ord = (int *)(sm + MIS_NB * 32);     // [MIS_NB]
-    uint32_t *s_alive = sm + MIS_NB * 33;       // [32]
+    uint32_t *s_adj = sm;                    // [32][MIS_NB]
+    int *s_ord = (int *)(sm + MIS_NB * 32);  // [MIS_NB]
+    uint8_t *s_alive = (uint8_t *)(s_ord + MIS_NB);  // [MIS_NB]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool a = tid < cnt && alive8[tid];
-    const uint32_t aw = __ballot_sync(0xffffffffu, a);
-    if (lane == 0) s_alive[warp] = aw;
-    if (tid < cnt) s_ord[tid] = order[base + tid];
-    __syncthreads();
-    for (int idx = tid; idx < cnt * 32; idx += 1024) {
-        const int t = idx >> 5;
-        if ((s_alive[t >> 5] >> (t & 31)) & 1u) s_adj[idx] = adj[idx];
+    const int ngroups = (cnt + 31) >> 5;
+    // word w of sequence t only matters for w <= t/32: copy the lower triangle of groups
+    for (int w = warp; w < ngroups; w += 32)
+        for (int t = w * 32 + lane; t < cnt; t += 32) s_adj[w * MIS_NB + t] = adj[w * MIS_NB + t];
+    if (tid < cnt) {
+        s_ord[tid] = order[base + tid];
+        s_alive[tid] = alive8[tid];
     }
     __syncthreads();
     if (warp != 0) return;
     int c = *count;
-    uint32_t repw = 0;
-    // lane l holds the live mask of word l; the walk pulls them out with shuffles
-    const uint32_t my_alive = s_alive[lane];
-    int wq = 0;
-    uint32_t live = __shfl_sync(0xffffffffu, my_alive, 0);
-    auto next_live = [&]() -> int {  // next live t or -1; warp-uniform
-        while (live == 0) {
-            if (++wq >= 32) return -1;
-            live = __shfl_sync(0xffffffffu, my_alive, wq);
+    uint32_t repw = 0;  // lane w: representatives of group w
+    for (int g = 0; g < ngroups; g++) {
+        const int t = g * 32 + lane;
+        bool undec = t < cnt && s_alive[t] != 0;
+        uint32_t killed = 0;
+        for (int w = 0; w < g; w++)
+            killed |= s_adj[w * MIS_NB + min(t, cnt - 1)] & __shfl_sync(0xffffffffu, repw, w);
+        undec = undec && killed == 0;
+        const uint32_t a = t < cnt ? s_adj[g * MIS_NB + t] : 0;  // bits of earlier lanes only
+        uint32_t reps = 0, und = __ballot_sync(0xffffffffu, undec);
+        while (und) {
+            const bool out = undec && (a & reps) != 0;
+            const bool in = undec && !out && (a & und) == 0;
+            const uint32_t nin = __ballot_sync(0xffffffffu, in);
+            const uint32_t nout = __ballot_sync(0xffffffffu, out);
+            reps |= nin;
+            und &= ~(nin | nout);
+            undec = undec && !in && !out;
         }
-        const int b = __ffs(live) - 1;
-        live &= live - 1;
-        return wq * 32 + b;
-    };
-    int t = next_live();
-    uint32_t cur = t >= 0 ? s_adj[t * 32 + lane] : 0;
-    while (t >= 0) {
-        const int tn = next_live();
-        const uint32_t nxt = tn >= 0 ? s_adj[tn * 32 + lane] : 0;
-        const bool hit = __any_sync(0xffffffffu, (cur & repw) != 0);
-        if (!hit) {
-            if (lane == (t >> 5)) repw |= 1u << (t & 31);
-            if (lane == 0 && clusters) clusters[c] = s_ord[t];
-            c++;
+        if ((reps >> lane) & 1u) {
+            const int v = s_ord[t];
+            if (clusters) clusters[c + __popc(reps & ((1u << lane) - 1u))] = v;
+            atomicOr(&rep[v >> 5], 1u << (v & 31));
         }
-        t = tn;
-        cur = nxt;
+        c += __popc(reps);
+        repw = lane == g ? reps : repw;
     }
     if (lane == 0) *count = c;
-    while (repw) {
-        const int b = __ffs(repw) - 1;
-        repw &= repw - 1;
-        const int v = s_ord[lane * 32 + b];
-        atomicOr(&rep[v >> 5], 1u << (v & 31));
-    }
 }
 
 int mis_block() { return MIS_NB; }

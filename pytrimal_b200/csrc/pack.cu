@@ -48,6 +48,39 @@ cudaError_t launch_byte_presence(const uint8_t *raw, int nseq, int ncol, size_t 
 }
 
 // ---------------------------------------------------------------------------
+// Rows at an arbitrary host stride (as they arrived in one linear copy) -> rows at the
+// device pitch (a multiple of 128), padding zeroed.  One warp per row, 4 bytes per lane
+// per step on the destination side (pitch and dst are 4-byte aligned; the source is not).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_repitch_rows(const uint8_t *__restrict__ src,
+                                                      size_t stride, int nseq, int ncol,
+                                                      uint8_t *__restrict__ dst, size_t pitch)
+{
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= nseq) return;
+    const uint8_t *s = src + (size_t)row * stride;
+    uint32_t *d = reinterpret_cast<uint32_t *>(dst + (size_t)row * pitch);
+    for (int k = lane * 4; k < (int)pitch; k += 128) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+            if (k + b < ncol) w |= (uint32_t)s[k + b] << (8 * b);
+        d[k >> 2] = w;
+    }
+}
+
+cudaError_t launch_repitch_rows(const uint8_t *src, size_t stride, int nseq, int ncol, uint8_t *dst,
+                                size_t pitch, cudaStream_t stream)
+{
+    if (nseq == 0) return cudaSuccess;
+    const long long threads = (long long)nseq * 32;
+    k_repitch_rows<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(src, stride, nseq, ncol,
+                                                                          dst, pitch);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // 256-bin histogram of the bytes in columns [0, ncol) of every row: everything
 // utils::checkAlignmentType (source/utils.cpp:476-545) derives from its scan of the
 // alignment is a sum of these bins.  16 bytes per thread per step; runs of equal bytes

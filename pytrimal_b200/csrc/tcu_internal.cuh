@@ -88,6 +88,8 @@ __host__ __device__ inline long long tiles_before2(long long sb, long long nb)
 // launchers (each enqueues on `stream` and returns the launch status)
 cudaError_t launch_byte_presence(const uint8_t *raw, int nseq, int ncol, size_t pitch,
                                  unsigned int *present256, cudaStream_t stream);
+cudaError_t launch_repitch_rows(const uint8_t *src, size_t stride, int nseq, int ncol, uint8_t *dst,
+                                size_t pitch, cudaStream_t stream);
 cudaError_t launch_byte_histogram(const uint8_t *raw, int nseq, int ncol, size_t pitch,
                                   unsigned long long *hist256, int num_sms, cudaStream_t stream);
 cudaError_t launch_pack_planes(const uint8_t *raw, size_t pitch, int ncol, const int *kept_rows,

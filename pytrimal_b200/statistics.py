@@ -281,14 +281,19 @@ class DeviceAlignment:
                                                   C.byref(k)))
         return k.value if count_only else out[: k.value].copy()
 
-    def representatives(self, threshold, indet=None, save_res=None):
+    def representatives(self, threshold, indet=None, save_res=None, comm=None):
         """Cleaner::calculateRepresentativeSeq (Cleaner.cpp:1398-1466) in one library call."""
         indet = self.alignment.indet if indet is None else indet
         sr = _mask(save_res, self.ncol)
         out = np.zeros(max(self.nseq, 1), np.int32)
         k = C.c_int(0)
-        _lib.check(self.lib.tcu_representatives(self._h, _p(sr, _i32p), indet, C.c_float(threshold),
-                                                _p(out, _i32p), C.byref(k)))
+        if comm is None:
+            rc = self.lib.tcu_representatives(self._h, _p(sr, _i32p), indet, C.c_float(threshold),
+                                              _p(out, _i32p), C.byref(k))
+        else:
+            rc = self.lib.tcu_representatives_all(self._h, comm._h, _p(sr, _i32p), indet,
+                                                  C.c_float(threshold), _p(out, _i32p), C.byref(k))
+        _lib.check(rc)
         return out[: k.value].copy()
 
     def select_method(self):

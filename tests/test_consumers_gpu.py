@@ -182,3 +182,36 @@ def test_byte_histogram_gap_runs(gpu):
     with gpu.DeviceAlignment(m) as d:
         h = d.byte_histogram()
     assert (h == np.bincount(m.reshape(-1), minlength=256).astype(np.uint64)).all()
+
+
+@pytest.mark.parametrize("n,L", [(1, 1), (5, 127), (33, 128), (40, 129), (1000, 1000), (64, 4100)])
+def test_pinned_strided_upload_equals_staged(gpu, port, n, L):
+    """tcu_msa_create_strided from page-locked memory (one linear DMA + device re-pitch)
+    must give the same device rows as the staged path: same histogram, lengths, gaps."""
+    import ctypes as C
+    import torch
+    from pytrimal_b200 import _lib
+    rng = np.random.default_rng(n * 7 + L)
+    for stride in (L, L + 3, L + 64):
+        buf = torch.zeros(n * stride + 8, dtype=torch.uint8).pin_memory()
+        view = buf.numpy()[: n * stride].reshape(n, stride)
+        m = random_msa(rng, n, L)
+        view[:, :L] = m
+        view[:, L:] = ord("-")                      # bytes between rows must never be read as data
+        lib = gpu.load()
+        h = C.c_void_p()
+        _lib.check(lib.tcu_msa_create_strided(C.c_void_p(buf.data_ptr()), n, L, stride, 0,
+                                              C.byref(h)))
+        try:
+            hist = (C.c_ulonglong * 256)()
+            _lib.check(lib.tcu_byte_histogram(h, hist))
+            lengths = np.zeros(n, np.int32)
+            _lib.check(lib.tcu_sequence_lengths(h, lengths.ctypes.data_as(C.POINTER(C.c_int))))
+            gaps = np.zeros(L, np.int32)
+            _lib.check(lib.tcu_gaps(h, None, gaps.ctypes.data_as(C.POINTER(C.c_int)), None, None))
+        finally:
+            lib.tcu_msa_destroy(h)
+        assert (np.array(hist[:], np.uint64) ==
+                np.bincount(m.reshape(-1), minlength=256).astype(np.uint64)).all()
+        assert (lengths == port.sequence_lengths(m)).all()
+        assert (gaps == port.gaps(m)[0]).all()

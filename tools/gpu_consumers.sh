@@ -1,11 +1,11 @@
 #!/bin/bash
-# identity-matrix consumers: GPU parity tests, timings, optional ncu
+# identity-matrix consumers: timings, ncu launch list, ncu --set full of K5..K8 + histogram
 TAG=${1:-cons}
 mkdir -p gpurun_out
-( time timeout 900 python -m pytest tests/test_consumers_gpu.py -m gpu -x -q ) > gpurun_out/pytest_$TAG.log 2>&1; tail -15 gpurun_out/pytest_$TAG.log
-timeout 600 python tools/bench_stats.py --only consumers --workloads C3,C4 --repeats 3 | tee gpurun_out/stats_$TAG.log
-if [ -n "$2" ]; then
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_identity_bits|k_row_stats|k_mis' -c 8 \
+timeout 600 python tools/bench_stats.py --only consumers --workloads C4 --repeats 3 | tee gpurun_out/stats_$TAG.log | cut -c1-1200
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv \
+    python tools/bench_stats.py --only consumers --workloads C4 --repeats 1 > gpurun_out/launches_$TAG.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_identity_bits|k_row_stats|k_mis_scan|k_mis_resolve|k_row_lengths' -c 12 \
     -o gpurun_out/prof_$TAG -f python tools/bench_stats.py --only consumers --workloads C4 --repeats 1 > gpurun_out/ncu_$TAG.log 2>&1
 tail -2 gpurun_out/ncu_$TAG.log
-fi
+ls -la gpurun_out

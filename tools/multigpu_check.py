@@ -50,6 +50,7 @@ def main():
                 id1 = d.identity(X, keep_on_device=True)
                 mdk1, num1, den1 = d.similarity(smx, gaps=g1, indet=X)
                 idm1 = d.identity(X, save_seq=save_seq)
+                rep1 = d.representatives(0.6, indet=X)
             with pb.DeviceAlignment(m, device=local) as d:
                 g2, h2, mx2 = d.gaps(comm=comm)
                 gm2, _, _ = d.gaps(save_seq=save_seq, comm=comm)
@@ -59,7 +60,9 @@ def main():
                 mdk2, num2, den2 = d.similarity(smx, gaps=g2, indet=X, comm=comm)
                 t_sim = d.timings
                 idm2 = d.identity(X, save_seq=save_seq, comm=comm)
+                rep2 = d.representatives(0.6, indet=X, comm=comm)
             checks = {
+                "representatives": rep1.tolist() == rep2.tolist(),
                 "gaps": (g1 == g2).all() and (h1 == h2).all() and mx1 == mx2,
                 "gaps_masked": (gm1 == gm2).all(),
                 "spurious": (bits(sp1) == bits(sp2)).all(),
