@@ -390,6 +390,9 @@ def main():
                     "d2h_bytes_per_step": int(4 * n + 4 * e2e_reps + 4), "steps": args.e2e_steps,
                     "representatives": e2e_reps, "gpu_launches_per_step": e2e_launches[0],
                     "last_step_phases_ms": {k: round(v, 3) for k, v in e2e_phases[-1].items()},
+                    "step_ms": [round(ph["create_ms"] + ph["call_ms"] + ph["destroy_ms"], 2)
+                                for ph in e2e_phases[1:]],
+                    "create_ms_per_step": [round(ph["create_ms"], 2) for ph in e2e_phases[1:]],
                     "api": "tcu_msa_create_strided + tcu_representatives%s (pinned host buffers): "
                            "Cleaner::calculateRepresentativeSeq(0.8) of the RepresentativeTrimmer, "
                            "identity matrix consumed in HBM" % ("_all" if world > 1 else "")},

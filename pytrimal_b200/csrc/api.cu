@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <mutex>
@@ -60,15 +61,31 @@ extern "C" const char *tcu_version(void) { return "trimal_cuda 0.1 (sm_100a)"; }
 // ---------------------------------------------------------------------------
 // devices
 // ---------------------------------------------------------------------------
+// cudaGetDeviceProperties queries the whole device (it took 9-300 ms per call inside a
+// busy process): two attributes are all that is needed, and they are looked up once.
 static bool device_usable(int dev, int *sms)
 {
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
+    struct Info {
+        int state = 0;  // 0 unknown, 1 usable, 2 not
+        int sms = 0;
+    };
+    static Info info[64];
+    static std::mutex mu;
+    if (dev < 0 || dev >= 64) return false;
+    std::lock_guard<std::mutex> lk(mu);
+    Info &i = info[dev];
+    if (i.state == 0) {
+        int major = 0, n = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+            cudaGetLastError();
+            return false;  // not cached: the driver may come up later
+        }
+        i.sms = n;
+        i.state = major == 10 ? 1 : 2;  // the library carries sm_100a code only
     }
-    if (sms) *sms = prop.multiProcessorCount;
-    return prop.major == 10;  // the library carries sm_100a code only
+    if (sms) *sms = i.sms;
+    return i.state == 1;
 }
 
 extern "C" int tcu_device_count(void)
@@ -605,18 +622,35 @@ extern "C" int tcu_msa_create(const char *const *rows, int nseq, int ncol, int d
     return TCU_OK;
 }
 
+static double now_ms()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 extern "C" int tcu_msa_create_strided(const uint8_t *data, int nseq, int ncol, size_t stride,
                                       int device, tcu_msa **out)
 {
     if (nseq > 0 && ncol > 0 && !data) return fail(TCU_ERR_INVALID, "data is NULL");
     if (stride < (size_t)ncol) return fail(TCU_ERR_INVALID, "stride smaller than ncol");
+    static const bool trace = getenv("TCU_TRACE") != nullptr;
+    const double t0 = trace ? now_ms() : 0;
     tcu_msa *m = nullptr;
     int rc = msa_alloc(nseq, ncol, device, &m);
     if (rc != TCU_OK) return rc;
-    if (nseq > 0 && ncol > 0 && stride <= 2 * (size_t)ncol + 64 && is_pinned_host(data))
+    const double t1 = trace ? now_ms() : 0;
+    const bool pinned =
+        nseq > 0 && ncol > 0 && stride <= 2 * (size_t)ncol + 64 && is_pinned_host(data);
+    const double t2 = trace ? now_ms() : 0;
+    if (pinned)
         rc = upload_strided_pinned(m, data, stride);
     else
         rc = upload_rows(m, [&](int r) { return (const void *)(data + (size_t)r * stride); });
+    if (trace)
+        fprintf(stderr, "[tcu] create: alloc %.2f ms, attr %.2f ms, upload(%s) %.2f ms (h2d events %.2f)\n",
+                t1 - t0, t2 - t1, pinned ? "pinned" : "staged", now_ms() - t2,
+                rc == TCU_OK ? m->timings.h2d_ms : -1.f);
     if (rc != TCU_OK) {
         tcu_msa_destroy(m);
         return rc;
@@ -1168,11 +1202,16 @@ extern "C" int tcu_identity_row_stats(tcu_msa *m, int upper_only, float *row_max
     return TCU_OK;
 }
 
-extern "C" int tcu_identity_clusters(tcu_msa *m, const int *order, int count, float threshold,
-                                     int *clusters, int *n_clusters)
+// Threshold bit matrix from rows [row_begin, row_end) of the identity matrix whose packed
+// offset 0 would be at `id0` (a rank that holds only its band passes band - band offset),
+// OR-combined across the ranks of `comm` (every word is written by exactly one rank -- bands
+// are multiples of 32 rows -- so an integer sum over zero-initialised matrices is the OR),
+// then the greedy clustering in the given order.
+static int clusters_impl(tcu_msa *m, tcu_comm *comm, const float *id0, int row_begin, int row_end,
+                         const int *order, int count, float threshold, int *clusters,
+                         int *n_clusters)
 {
-    int rc = need_resident(m);
-    if (rc != TCU_OK) return rc;
+    int rc = TCU_OK;
     if (!n_clusters || (count > 0 && !order)) return fail(TCU_ERR_INVALID, "NULL argument");
     const int n = m->nseq;
     if (count < 0 || count > n) return fail(TCU_ERR_INVALID, "count %d outside [0,%d]", count, n);
@@ -1204,8 +1243,14 @@ extern "C" int tcu_identity_clusters(tcu_msa *m, const int *order, int count, fl
     CK(cudaEventRecord(m->ev[0], m->stream));
     CK(cudaMemcpyAsync(d_order, order, (size_t)count * 4, cudaMemcpyHostToDevice, m->stream));
     CK(cudaMemsetAsync(d_rep, 0, rep_b, m->stream));
+    if (comm) CK(cudaMemsetAsync(d_bits, 0, (size_t)n * W * 4, m->stream));
     CK(cudaEventRecord(m->ev[1], m->stream));
-    CK(launch_identity_bits(m->d_ident, n, W, threshold, d_bits, m->stream));
+    CK(launch_identity_bits(id0, n, W, threshold, d_bits, row_begin, row_end, m->stream));
+    CK(cudaEventRecord(m->ev[5], m->stream));
+    if (comm) {
+        rc = comm_allreduce_i32(comm, (int *)d_bits, (size_t)n * W, m->stream);
+        if (rc != TCU_OK) return rc;
+    }
     CK(cudaEventRecord(m->ev[2], m->stream));
     CK(launch_greedy_clusters(d_bits, W, d_order, count, d_rep, d_alive, d_adj, d_clusters, d_count,
                               m->stream));
@@ -1220,11 +1265,21 @@ extern "C" int tcu_identity_clusters(tcu_msa *m, const int *order, int count, fl
     CK(cudaStreamSynchronize(m->stream));
     *n_clusters = found;
     m->timings.h2d_ms = ev_ms(m->ev[0], m->ev[1]);
-    m->timings.pack_ms = ev_ms(m->ev[1], m->ev[2]);    // threshold -> bit matrix
+    m->timings.pack_ms = ev_ms(m->ev[1], m->ev[5]);    // threshold -> bit matrix
+    m->timings.comm_ms = ev_ms(m->ev[5], m->ev[2]);    // OR across ranks
     m->timings.kernel_ms = ev_ms(m->ev[2], m->ev[3]);  // greedy clustering
     m->timings.d2h_ms = ev_ms(m->ev[3], m->ev[4]);
     m->timings.kernel_launches = 1 + 2 * ((count + mis_block() - 1) / mis_block());
     return TCU_OK;
+}
+
+extern "C" int tcu_identity_clusters(tcu_msa *m, const int *order, int count, float threshold,
+                                     int *clusters, int *n_clusters)
+{
+    int rc = need_resident(m);
+    if (rc != TCU_OK) return rc;
+    return clusters_impl(m, nullptr, m->d_ident, 0, m->nseq, order, count, threshold, clusters,
+                         n_clusters);
 }
 
 extern "C" int tcu_byte_histogram(tcu_msa *m, unsigned long long *hist256)
@@ -1315,9 +1370,10 @@ extern "C" int tcu_cluster_order(const int *lengths, int nseq, int *order)
 }
 
 // Cleaner::calculateRepresentativeSeq in one call: identity matrix (left on the device),
-// sequence lengths, visiting order, greedy clustering.  With a communicator the matrix is
-// computed in row bands across the ranks and all-gathered (tcu_identity_all); every rank
-// then runs the (sequential, cheap) clustering on its own copy and returns the full result.
+// sequence lengths, visiting order, greedy clustering.  With a communicator every rank
+// computes its row band of the matrix and thresholds it; the bit matrices (n^2/8 bytes, 32x
+// smaller than the floats) are OR-ed across the ranks with one NCCL all-reduce and every
+// rank runs the (sequential, cheap) clustering and returns the full result.
 static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res, uint8_t indet,
                                 float threshold, int *clusters, int *n_clusters)
 {
@@ -1349,13 +1405,46 @@ static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res,
     } catch (...) {  // no thread to be had: sort here, nothing may escape the C ABI
         sort();
     }
-    rc = comm ? tcu_identity_all(m, comm, nullptr, save_res, indet, nullptr)
-              : tcu_identity(m, nullptr, save_res, indet, nullptr, nullptr, nullptr, 1);
+    const float *id0 = nullptr;
+    int row_begin = 0, row_end = m->nseq;
+    if (comm) {
+        // this rank's band only (no float all-gather: the ranks exchange the 32x smaller
+        // bit matrix instead); the band sits at the start of d_ident
+        rc = comm_check(m, comm);
+        if (rc == TCU_OK) {
+            m->timings = tcu_timings{};
+            m->ident_full = false;
+            rc = tcu_identity_prepare(m, nullptr, save_res, indet, nullptr);
+        }
+        if (rc == TCU_OK) {
+            int b0 = 0, b1 = 0;
+            tcu_shard_blocks(m->nk, comm->rank, comm->world, &b0, &b1);
+            row_begin = std::min(b0 * IB, m->nk);
+            row_end = std::min(b1 * IB, m->nk);
+            const size_t lo = tcu_identity_row_offset(m->nk, row_begin);
+            const size_t hi = tcu_identity_row_offset(m->nk, row_end);
+            rc = ensure_ident(m, std::max<size_t>(hi - lo, 1) * sizeof(float));
+            if (rc == TCU_OK) rc = identity_launch(m, b0, b1, m->d_ident, nullptr, nullptr);
+            if (rc == TCU_OK) {
+                id0 = m->d_ident - lo;
+                cudaError_t e = cudaEventRecord(m->ev[3], m->stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+                if (e != cudaSuccess) rc = cuda_fail(e, "identity band");
+                m->timings.h2d_ms = ev_ms(m->ev[0], m->ev[1]);
+                m->timings.pack_ms = ev_ms(m->ev[1], m->ev[2]);
+                m->timings.kernel_ms = ev_ms(m->ev[2], m->ev[3]);
+            }
+        }
+    } else {
+        rc = tcu_identity(m, nullptr, save_res, indet, nullptr, nullptr, nullptr, 1);
+        id0 = m->d_ident;
+    }
     if (sorter.joinable()) sorter.join();
     if (rc != TCU_OK) return rc;
     add(m->timings);
     if (sort_rc != TCU_OK) return fail(sort_rc, "%s", sort_err.c_str());
-    rc = tcu_identity_clusters(m, order.data(), m->nseq, threshold, clusters, n_clusters);
+    rc = clusters_impl(m, comm, id0, row_begin, row_end, order.data(), m->nseq, threshold, clusters,
+                       n_clusters);
     if (rc != TCU_OK) return rc;
     add(m->timings);
     m->timings = total;

@@ -43,10 +43,11 @@ __device__ __forceinline__ long long pair_row_base(long long i, long long n)
 // accumulated bits the words of the transposed block.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_identity_bits(const float *__restrict__ id, int n, int W,
-                                                       float thr, uint32_t *__restrict__ bits)
+                                                       float thr, uint32_t *__restrict__ bits,
+                                                       int rb_begin)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int rb = blockIdx.y;             // 32-row block
+    const int rb = rb_begin + blockIdx.y;  // 32-row block
     const int jw = blockIdx.x * 8 + warp;  // 32-column word
     if (jw < rb || jw >= W) return;        // below the diagonal: written as a transpose
     const int i0 = rb * 32, j = jw * 32 + lane;
@@ -79,12 +80,16 @@ __global__ void __launch_bounds__(256) k_identity_bits(const float *__restrict__
     }
 }
 
+// Rows [row_begin, row_end) of the matrix (multiples of 32, or n): `id` is the address
+// packed offset 0 WOULD have, so a rank that holds only its band passes band - band_offset.
+// Every word of `bits` that belongs to these rows' pairs is written; a caller that covers
+// only part of the rows must zero `bits` first.
 cudaError_t launch_identity_bits(const float *id, int n, int W, float thr, uint32_t *bits,
-                                 cudaStream_t stream)
+                                 int row_begin, int row_end, cudaStream_t stream)
 {
-    if (n <= 0) return cudaSuccess;
-    dim3 grid((W + 7) / 8, (n + 31) / 32);
-    k_identity_bits<<<grid, 256, 0, stream>>>(id, n, W, thr, bits);
+    if (n <= 0 || row_end <= row_begin) return cudaSuccess;
+    dim3 grid((W + 7) / 8, (row_end - row_begin + 31) / 32);
+    k_identity_bits<<<grid, 256, 0, stream>>>(id, n, W, thr, bits, row_begin / 32);
     return cudaGetLastError();
 }
 

@@ -123,7 +123,7 @@ cudaError_t launch_row_lengths(const uint8_t *raw, int nseq, int ncol, size_t pi
 
 // consumers of the device-resident identity matrix (clusters.cu)
 cudaError_t launch_identity_bits(const float *id, int n, int W, float thr, uint32_t *bits,
-                                 cudaStream_t stream);
+                                 int row_begin, int row_end, cudaStream_t stream);
 cudaError_t launch_row_stats(const float *id, int n, bool upper_only, float *row_max,
                              float *row_min, float *row_sum, cudaStream_t stream);
 int mis_block();
