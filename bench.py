@@ -264,7 +264,21 @@ def main():
     e1.record(stream)
     dev.sync()
     barrier()
+    clock_note = None
+    if rank == 0 and len(sampler.rows) < 3:
+        # the timed region was shorter than a few 100 ms sampling periods (many GPUs):
+        # keep the same steps running, untimed, until the sampler has seen the clocks
+        # under this load
+        clock_note = ("timed region shorter than the sampling period: clocks sampled over the "
+                      "same steps repeated untimed right after it")
+        t_end = time.perf_counter() + 1.5
+        while len(sampler.rows) < 4 and time.perf_counter() < t_end:
+            step()
+            dev.sync()
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None and clock_note:
+        clocks["note"] = clock_note
+    barrier()
     ms_total = e0.elapsed_time(e1)
     # duration of the dominant kernel alone (last step), CUDA events inside the library
     t = dev.timings
