@@ -167,6 +167,20 @@ void CUDAGaps::CalculateVectors()
     report_failure("CUDA platform: gap statistic failed");
 }
 
+// Order of a similarity matrix.  numPositions is private in vanilla trimAl and public in
+// pytrimal's build (patches/similarityMatrix.h.patch): read it where it is accessible
+// (access failure in a decltype is a substitution failure), else report -1.
+template <class M>
+static auto matrix_order(M *m, int) -> decltype(m->numPositions)
+{
+  return m->numPositions;
+}
+template <class M>
+static int matrix_order(M *, long)
+{
+  return -1;
+}
+
 // Set while the caller only needs the matrix on the device (the cuda* walks below and
 // CUDASimilarity): CUDAIdentity::calculateSeqIdentity then skips the host array.
 static thread_local int t_device_only = 0;
@@ -518,12 +532,21 @@ bool CUDASimilarity::calculateVectors(bool cutByGap)
   }
   const float gapThreshold = 0.8F * alig->numberOfResidues;  // template.h:108 (sic: residues)
 
-  // public accessors only (the raw members are private in vanilla trimAl)
+  // public accessors only (the raw members are private in vanilla trimAl).  pytrimal's
+  // SimilarityMatrix.__init__ (src/pytrimal/_trimal.pyx:1973-1981) fills vhash for the
+  // letters of its alphabet only and leaves the other entries of the fresh `new int[]`
+  // uninitialised, so an index is trusted only inside [0, order): everything else is
+  // "no row" (UndefinedSymbol if the letter occurs, template.h:140-144).
+  const int order = matrix_order(simMatrix, 0);
+  const int limit = order >= 0 ? order : 28;  // 28 = pytrimal's alphabet limit (_trimal.pyx:1969)
   int vhash[26], npos = 0;
   for (int c = 0; c < 26; c++) {
-    vhash[c] = simMatrix->getLetterIndex((char)('A' + c));
+    const int v = simMatrix->getLetterIndex((char)('A' + c));
+    vhash[c] = (v >= 0 && v < limit) ? v : -1;
     if (vhash[c] + 1 > npos) npos = vhash[c] + 1;
   }
+  if (order >= 0) npos = order;
+  if (npos < 1) return false;
   const float **distMat = simMatrix->getDistanceMatrix();
   std::vector<float> dist((size_t)npos * npos);
   for (int i = 0; i < npos; i++)

@@ -29,12 +29,12 @@ namespace tcu {
 // 64-bit atomicMin on ((col*nseq + row) << 8 | byte).
 //
 // Output layout: codesT[group][row][32] -- the 32 columns of one column group
-// are contiguous per row, rows padded to a multiple of 32 -- holding 8 * code
+// are contiguous per row, rows padded to a multiple of 32 -- holding 4 * code
 // (the byte offset of the code's entry in a table row); the gap class, skipped
-// columns and all padding hold SIM2_GAP8 = 8 * 31.
+// columns and all padding hold SIM2_GAP8 = 4 * 31.
 // ---------------------------------------------------------------------------
 constexpr uint32_t SIM2_GAPIDX = 31;
-constexpr uint32_t SIM2_GAP8 = 8 * SIM2_GAPIDX;
+constexpr uint32_t SIM2_GAP8 = 4 * SIM2_GAPIDX;
 
 __global__ void __launch_bounds__(256) k_sim_codes(const uint8_t *__restrict__ raw, int nseq,
                                                    int ncol, size_t pitch, int npad,
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) k_sim_codes(const uint8_t *__restrict__ r
                         uint32_t up = (byte >= 'a' && byte <= 'z') ? byte - 32 : byte;
                         atomicMin(first_error, (((unsigned long long)col * nseq + r) << 8) | up);
                     } else if (code != SIM_GAP) {
-                        out = code * 8;
+                        out = code * 4;
                     }
                 }
                 ow |= out << (8 * b);
@@ -101,7 +101,8 @@ cudaError_t launch_sim_codes(const uint8_t *raw, int nseq, int ncol, size_t pitc
 // nothing in any lane (template.h:157-160) and is skipped by every warp of the
 // main kernel: skipbits[group][j / 32] bit j % 32.  Row nseq-1 (never an outer
 // row) and padding are marked too.  nbatches[group] = number of 32-k batches
-// the main kernel exchanges for the group.
+// the main kernel exchanges for the group.  ngmask[group][row] = the row's
+// non-gap columns of the group as a bit mask (the denominator's operand).
 // ---------------------------------------------------------------------------
 constexpr int SIM2_KB = 32;  // inner rows (k) per batch
 
@@ -110,9 +111,21 @@ __device__ __forceinline__ int sim2_row_batches(int j, int nseq)
     return ((nseq - 1) >> 5) - ((j + 1) >> 5) + 1;  // aligned batches covering k = j+1 .. nseq-1
 }
 
+// non-gap bytes of a word of codes as a 4-bit mask.  Codes are 4 * index with
+// index <= 31, the gap class is index 31: a byte is a gap iff bits 2..6 are all set.
+__device__ __forceinline__ uint32_t sim2_nongap4(uint32_t w)
+{
+    const uint32_t x1 = w & (w >> 1);
+    const uint32_t x2 = x1 & (x1 >> 2);
+    const uint32_t g = x2 & (w >> 4);                 // bit 2 of each byte: gap
+    const uint32_t y = (~g >> 2) & 0x01010101u;       // bit 0 of each byte: non-gap
+    return (y * 0x01020408u) >> 24;                   // byte b -> bit b
+}
+
 __global__ void __launch_bounds__(256) k_sim_rows(const uint8_t *__restrict__ codesT, int nseq,
                                                   int npad, uint32_t *__restrict__ skipbits,
-                                                  unsigned long long *__restrict__ nbatches)
+                                                  unsigned long long *__restrict__ nbatches,
+                                                  uint32_t *__restrict__ ngmask)
 {
     const int group = blockIdx.y;
     const int nwords = npad >> 5;
@@ -122,10 +135,12 @@ __global__ void __launch_bounds__(256) k_sim_rows(const uint8_t *__restrict__ co
     const int j = word * 32 + lane;
     const uint4 *cp = reinterpret_cast<const uint4 *>(codesT + ((size_t)group * npad + j) * 32);
     const uint4 a = __ldg(cp), b = __ldg(cp + 1);
-    const uint32_t G = SIM2_GAP8 * 0x01010101u;
-    const bool allgap = (a.x & a.y & a.z & a.w & b.x & b.y & b.z & b.w) == G &&
-                        (a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) == G;
-    const bool skip = allgap || j >= nseq - 1;
+    const uint32_t mask = sim2_nongap4(a.x) | sim2_nongap4(a.y) << 4 | sim2_nongap4(a.z) << 8 |
+                          sim2_nongap4(a.w) << 12 | sim2_nongap4(b.x) << 16 |
+                          sim2_nongap4(b.y) << 20 | sim2_nongap4(b.z) << 24 |
+                          sim2_nongap4(b.w) << 28;
+    ngmask[(size_t)group * npad + j] = mask;
+    const bool skip = mask == 0 || j >= nseq - 1;
     const uint32_t bits = __ballot_sync(0xffffffffu, skip);
     unsigned long long nb = skip ? 0ull : (unsigned long long)sim2_row_batches(j, nseq);
 #pragma unroll
@@ -139,35 +154,46 @@ __global__ void __launch_bounds__(256) k_sim_rows(const uint8_t *__restrict__ co
 // ---------------------------------------------------------------------------
 // Main kernel: one CTA per group of 32 adjacent columns.
 //
-// The chain  num += w * d;  den += w  of a column must run in the reference's
-// order, one rounded fp32 add after the other, but its TERMS are independent.
-// So the CTA splits the work:
-//   6 producer warps   lane = inner row k of a 32-k batch.  Per batch a lane
-//                      loads its row's 32 codes (32 contiguous bytes) and
-//                      id[j,k] (coalesced), forms w = 1 - id once, and for each
-//                      of the 32 columns looks up {D[a_j][a_k], pair counted ?
-//                      1 : 0} (one 8-byte shared-memory load; the table has an
-//                      all-zero row/column for gaps), multiplies by w and
-//                      stores {w*d, w*e} to a ring slot in shared memory.
-//                      Terms of pairs the reference skips are exact +0.
-//   1 consumer warp    lane = column.  Waits for a slot, then does nothing but
-//                      LDS.64 + FADD + FADD per inner row: the two dependent
-//                      add chains (4-cycle FADD latency each) are the critical
-//                      path of the whole kernel, everything else runs beside
-//                      them on the other three SM sub-partitions.
-// Slots are handed over with mbarriers (full/empty, one arrival each).
+// The chains  num += w * d;  den += w  of a column must run in the reference's
+// order, one rounded fp32 add after the other, but the two chains are
+// independent of each other and their TERMS are independent.  The four SM
+// sub-partitions (warp id % 4) get different jobs:
+//   numerator warp     lane = column.  Nothing but LDS.128 (four consecutive inner
+//                      rows of its column) and one FADD per inner row: the dependent
+//                      add (4 cycles) is the critical path.  Alone on its
+//                      sub-partition.
+//   denominator warp   lane = column.  Per inner row: the row's weight w and the
+//                      bit mask of the columns whose pair is counted (uniform
+//                      LDS.128), one predicated FADD.  Alone on its sub-partition.
+//   6 producer warps   (the two other sub-partitions) lane = inner row k of a
+//                      32-k batch.  Per batch a lane loads its row's 32 codes
+//                      (32 contiguous bytes), id[j,k] (coalesced) and the two
+//                      non-gap masks, forms w = 1 - id once, and for each of the
+//                      32 columns looks up D[a_j][a_k] (one PRMT forms the table
+//                      offset; the table has an all-zero row/column for gaps),
+//                      multiplies by w and stores the term to a ring slot in
+//                      shared memory ([column][k] so the consumer reads vectors),
+//                      plus w and mask_j & mask_k once per row.
+// Terms of pairs the reference skips are exact +0 (w * 0, or not added).
+// A single warp can start one shared-memory load every ~4 cycles, which is what
+// limited the first version of this kernel (one warp, LDS.64 + two FADDs per row:
+// 10.6 cycles per row); hence the vector loads and the chain split over two warps.
+// Slots are handed over with mbarriers (full: one arrival; empty: two).
 // ---------------------------------------------------------------------------
 constexpr int SIM2_NPROD = 6;
-constexpr int SIM2_MAX_SLOTS = 12;
-constexpr int SIM2_RS = 33;                         // float2 per k row of a slot (odd: no bank conflicts)
-constexpr int SIM2_SLOT_F2 = SIM2_KB * SIM2_RS;     // float2 per slot
-constexpr int SIM2_THREADS = 256;
-constexpr int SIM2_TABLE_F2 = 32 * 32;
-constexpr int SIM2_PREFETCH_BATCHES = 4;            // own batches ahead (x SIM2_NPROD in array order)
+constexpr int SIM2_MAX_SLOTS = 18;
+constexpr int SIM2_CS = 36;                          // floats per column of a slot: [column][k], 16-byte rows,
+                                                     // 8 lanes x LDS.128 cover the 32 banks (36 % 32 == 4)
+constexpr int SIM2_SLOT_D = 32 * SIM2_CS;            // numerator terms per slot
+constexpr int SIM2_SLOT_WORDS = SIM2_SLOT_D + 2 * SIM2_KB;  // + w[32] + mask[32]
+constexpr int SIM2_THREADS = 384;                    // 3 warps per sub-partition
+constexpr int SIM2_TROW = 64;                        // table row stride in floats (256 B: offset = a_j << 8 | 4 a_k)
+constexpr int SIM2_TABLE_WORDS = 32 * SIM2_TROW;
+constexpr int SIM2_PREFETCH_BATCHES = 4;             // own batches ahead (x SIM2_NPROD in array order)
 
 __host__ __device__ constexpr size_t sim2_smem_bytes(int slots)
 {
-    return (size_t)slots * SIM2_SLOT_F2 * 8 + SIM2_TABLE_F2 * 8 + 2 * SIM2_MAX_SLOTS * 8;
+    return (size_t)slots * SIM2_SLOT_WORDS * 4 + SIM2_TABLE_WORDS * 4 + 2 * SIM2_MAX_SLOTS * 8;
 }
 
 struct Sim2Params {
@@ -176,36 +202,117 @@ struct Sim2Params {
     const float *dist;
     const uint8_t *col_skip;
     const uint32_t *skipbits;
+    const uint32_t *ngmask;
     const unsigned long long *nbatches;
     float *num_out, *den_out;
     int nseq, npad, ncol, npos;
     int group_begin;
-    int slots;      // SIM2_NPROD or 2 * SIM2_NPROD
+    int slots;      // multiple of SIM2_NPROD
     int num_sms;
 };
+
+// One consumer warp's walk over the ring: IS_NUM ? sum of w * d : sum of w over counted pairs.
+template <bool IS_NUM>
+__device__ __forceinline__ float sim2_consume(const float *ring, uint64_t *full, uint64_t *empty,
+                                              int slots, unsigned long long btot, int lane)
+{
+    float acc = 0.0f;
+    float4 v4[2][IS_NUM ? 4 : 1];  // numerator: the column's terms w * d of half a batch
+    float4 w4[2][IS_NUM ? 1 : 4];  // denominator: the rows' weights (uniform loads)
+    uint4 m4[2][IS_NUM ? 1 : 4];   //              and column masks (uniform loads)
+    const uint32_t lanebit = 1u << lane;
+    auto loadh = [&](int buf, int slot, int h) {
+        const float *s = ring + (size_t)slot * SIM2_SLOT_WORDS;
+        if constexpr (IS_NUM) {
+            // one LDS.128 = four consecutive inner rows of the lane's column
+            const float4 *src = reinterpret_cast<const float4 *>(s + lane * SIM2_CS) + h * 4;
+#pragma unroll
+            for (int q = 0; q < 4; q++) v4[buf][q] = src[q];
+        } else {
+            const float4 *ws = reinterpret_cast<const float4 *>(s + SIM2_SLOT_D) + h * 4;
+            const uint4 *ms = reinterpret_cast<const uint4 *>(s + SIM2_SLOT_D + SIM2_KB) + h * 4;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                w4[buf][q] = ws[q];
+                m4[buf][q] = ms[q];
+            }
+        }
+    };
+    auto addh = [&](int buf) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if constexpr (IS_NUM) {
+                acc = __fadd_rn(acc, v4[buf][q].x);
+                acc = __fadd_rn(acc, v4[buf][q].y);
+                acc = __fadd_rn(acc, v4[buf][q].z);
+                acc = __fadd_rn(acc, v4[buf][q].w);
+            } else {
+                const float wq[4] = {w4[buf][q].x, w4[buf][q].y, w4[buf][q].z, w4[buf][q].w};
+                const uint32_t mq[4] = {m4[buf][q].x, m4[buf][q].y, m4[buf][q].z, m4[buf][q].w};
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                    if (mq[r] & lanebit) acc = __fadd_rn(acc, wq[r]);
+            }
+        }
+    };
+    int slot = 0;
+    uint32_t par = 0;
+    if (btot) {
+        mbar_wait(&full[0], 0);
+        loadh(0, 0, 0);
+    }
+    // (32-bit loop counter: the 64-bit compare chain costs the in-order warp ~25 cycles a batch)
+    for (unsigned long long left = btot; left;) {
+      const uint32_t nb = (uint32_t)min(left, 1ull << 30);
+      left -= nb;
+      for (uint32_t b = 0; b < nb; b++) {
+        int nslot = slot + 1;
+        uint32_t npar = par;
+        if (nslot == slots) {
+            nslot = 0;
+            npar ^= 1u;
+        }
+        // probe the next slot now (the probe takes ~90 cycles), look at the answer
+        // after the first half of this batch has been added
+        const bool more = b + 1 < nb || left != 0;
+        const uint32_t ready = more ? mbar_try_wait(&full[nslot], npar) : 1u;
+        loadh(1, slot, 1);
+        addh(0);
+        if (more) {
+            if (!ready) mbar_wait(&full[nslot], npar);
+            loadh(0, nslot, 0);
+        }
+        addh(1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);
+        slot = nslot;
+        par = npar;
+      }
+    }
+    return acc;
+}
 
 __global__ void __launch_bounds__(SIM2_THREADS, 2) k_similarity2(const Sim2Params p)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    float2 *ring = reinterpret_cast<float2 *>(smem);
-    float2 *T = ring + (size_t)p.slots * SIM2_SLOT_F2;
-    uint64_t *full = reinterpret_cast<uint64_t *>(T + SIM2_TABLE_F2);
+    float *ring = reinterpret_cast<float *>(smem);
+    float *T = ring + (size_t)p.slots * SIM2_SLOT_WORDS;
+    uint64_t *full = reinterpret_cast<uint64_t *>(T + SIM2_TABLE_WORDS);
     uint64_t *empty = full + SIM2_MAX_SLOTS;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int group = p.group_begin + blockIdx.x;
     const int n = p.nseq;
 
-    // table: T[a * 32 + b] = {D[a][b], 1}; row / column 31 (gap) and unused codes are zero
-    for (int i = threadIdx.x; i < SIM2_TABLE_F2; i += SIM2_THREADS) {
-        const int a = i >> 5, b = i & 31;
-        T[i] = (a < p.npos && b < p.npos) ? make_float2(p.dist[a * p.npos + b], 1.0f)
-                                          : make_float2(0.0f, 0.0f);
+    // table: T[a * 64 + b] = D[a][b]; row / column 31 (gap) and unused codes are zero
+    for (int i = threadIdx.x; i < SIM2_TABLE_WORDS; i += SIM2_THREADS) {
+        const int a = i / SIM2_TROW, b = i % SIM2_TROW;
+        T[i] = (a < p.npos && b < p.npos) ? p.dist[a * p.npos + b] : 0.0f;
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.slots; s++) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], 2);
         }
         fence_mbar_init();
     }
@@ -213,69 +320,29 @@ __global__ void __launch_bounds__(SIM2_THREADS, 2) k_similarity2(const Sim2Param
 
     // When more groups than SMs are launched two CTAs share an SM: put their consumer
     // warps on different sub-partitions (warp id % 4).
-    const int cw = (blockIdx.x / max(p.num_sms, 1)) & 3;
+    const int cn = (2 * (blockIdx.x / max(p.num_sms, 1))) & 3;  // numerator's sub-partition
+    const int cd = cn + 1;                                      // denominator's
+    const int sp = warp & 3;
     const uint8_t *gc = p.codesT + (size_t)group * p.npad * 32;
 
-    if (warp == cw) {
-        // ------------------------------ consumer ------------------------------
-        const unsigned long long btot = p.nbatches[group];
-        float num = 0.0f, den = 0.0f;
-        float2 va[16], vb[16];
-        auto loadh = [&](float2(&v)[16], int slot, int h) {
-            const float2 *src = ring + (size_t)slot * SIM2_SLOT_F2 + h * 16 * SIM2_RS + lane;
-#pragma unroll
-            for (int u = 0; u < 16; u++) v[u] = src[u * SIM2_RS];
-        };
-        auto addh = [&](const float2(&v)[16]) {
-#pragma unroll
-            for (int u = 0; u < 16; u++) {
-                num = __fadd_rn(num, v[u].x);
-                den = __fadd_rn(den, v[u].y);
-            }
-        };
-        int slot = 0;
-        uint32_t par = 0;
-        if (btot) {
-            mbar_wait(&full[0], 0);
-            loadh(va, 0, 0);
-        }
-        for (unsigned long long b = 0; b < btot; b++) {
-            int nslot = slot + 1;
-            uint32_t npar = par;
-            if (nslot == p.slots) {
-                nslot = 0;
-                npar ^= 1u;
-            }
-            // probe the next slot now (the probe takes ~90 cycles), look at the answer
-            // after the first half of this batch has been added
-            const bool more = b + 1 < btot;
-            const uint32_t ready = more ? mbar_try_wait(&full[nslot], npar) : 1u;
-            loadh(vb, slot, 1);
-            addh(va);
-            if (more) {
-                if (!ready) mbar_wait(&full[nslot], npar);
-                loadh(va, nslot, 0);
-            }
-            addh(vb);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[slot]);
-            slot = nslot;
-            par = npar;
-        }
+    if (warp == cn || warp == cd) {
+        // ------------------------------ consumers -----------------------------
+        float acc;
+        if (warp == cn) acc = sim2_consume<true>(ring, full, empty, p.slots, p.nbatches[group], lane);
+        else acc = sim2_consume<false>(ring, full, empty, p.slots, p.nbatches[group], lane);
         const int col = group * 32 + lane;
-        if (col < p.ncol && !p.col_skip[col]) {
-            p.num_out[col] = num;
-            p.den_out[col] = den;
-        }
-    } else if (warp != cw + 4) {
+        if (col < p.ncol && !p.col_skip[col]) (warp == cn ? p.num_out : p.den_out)[col] = acc;
+    } else if (sp != cn && sp != cd) {
         // ------------------------------ producers -----------------------------
-        // producer index 0..5: the six warps that are neither the consumer nor the
-        // (idle) warp sharing its sub-partition
+        // producer index 0..5: the six warps of the two sub-partitions without a consumer
+        // (the other warps of the consumers' sub-partitions exit: a consumer shares its
+        // issue slots with nobody)
         int pi = 0;
-        for (int w = 0; w < warp; w++) pi += (w != cw && w != cw + 4);
+        for (int w = 0; w < warp; w++) pi += ((w & 3) != cn && (w & 3) != cd);
         const int spp = p.slots / SIM2_NPROD;  // slots per producer
         const int nwords = p.npad >> 5;
         const uint32_t *skipw = p.skipbits + (size_t)group * nwords;
+        const uint32_t *ngm = p.ngmask + (size_t)group * p.npad;
         const unsigned long long nn = (unsigned long long)n;
         const unsigned long long npairs = nn * (nn - 1) / 2;
 
@@ -311,6 +378,7 @@ __global__ void __launch_bounds__(SIM2_THREADS, 2) k_similarity2(const Sim2Param
         struct Loaded {
             uint4 c0, c1, j0, j1;
             float id;
+            uint32_t mask;
         };
         auto fetch = [&](int fj, int fkb, Loaded &L) {
             const int k = fkb + lane;
@@ -320,6 +388,7 @@ __global__ void __launch_bounds__(SIM2_THREADS, 2) k_similarity2(const Sim2Param
             L.c1 = __ldg(cp + 1);
             L.j0 = __ldg(jp);
             L.j1 = __ldg(jp + 1);
+            L.mask = __ldg(ngm + k) & __ldg(ngm + fj);
             // identities[(fj, k)], packed upper triangle without diagonal (template.h:158,171,181)
             const unsigned long long rowbase =
                 (unsigned long long)fj * nn - ((unsigned long long)fj * (fj + 1)) / 2 - fj - 1;
@@ -345,32 +414,34 @@ __global__ void __launch_bounds__(SIM2_THREADS, 2) k_similarity2(const Sim2Param
             const uint32_t par = (uint32_t)((i / spp) & 1);
             mbar_wait(&empty[slot], par ^ 1u);
 
-            const float w = __fsub_rn(1.0f, cur.id);  // 0 for k <= j and padding
             const uint32_t cw8[8] = {cur.c0.x, cur.c0.y, cur.c0.z, cur.c0.w,
                                      cur.c1.x, cur.c1.y, cur.c1.z, cur.c1.w};
             const uint32_t jw8[8] = {cur.j0.x, cur.j0.y, cur.j0.z, cur.j0.w,
                                      cur.j1.x, cur.j1.y, cur.j1.z, cur.j1.w};
-            float2 *dst = ring + (size_t)slot * SIM2_SLOT_F2 + lane * SIM2_RS;
+            float *sl = ring + (size_t)slot * SIM2_SLOT_WORDS;
+            float *dst = sl + lane;
+            const float w = __fsub_rn(1.0f, cur.id);  // 0 for k <= j and padding
+            sl[SIM2_SLOT_D + lane] = w;
+            reinterpret_cast<uint32_t *>(sl)[SIM2_SLOT_D + SIM2_KB + lane] = cur.mask;
             const char *Tb = reinterpret_cast<const char *>(T);
             // 16 table loads in flight, then 16 stores (the compiler must assume that the
             // ring stores alias the table and would otherwise serialise load -> store)
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                float2 t[16];
+                float t[16];
 #pragma unroll
                 for (int u = 0; u < 16; u++) {
                     const int wd = h * 4 + (u >> 2), b = u & 3;
                     // row-j codes (uniform): bytes [c0, 0, c2, 0] and [c1, 0, c3, 0] of code index
-                    const uint32_t cjs = (jw8[wd] >> 3) & 0x1F1F1F1Fu;
+                    const uint32_t cjs = (jw8[wd] >> 2) & 0x1F1F1F1Fu;
                     const uint32_t y = (b & 1) ? ((cjs >> 8) & 0x00FF00FFu) : (cjs & 0x00FF00FFu);
-                    // table byte offset = a_j * 256 + 8 * a_k: one PRMT
+                    // table byte offset = a_j * 256 + 4 * a_k: one PRMT
                     const uint32_t sel = 0x5500u | ((b & 2) ? 0x60u : 0x40u) | (uint32_t)b;
                     const uint32_t off = __byte_perm(cw8[wd], y, sel);
-                    t[u] = *reinterpret_cast<const float2 *>(Tb + off);
+                    t[u] = *reinterpret_cast<const float *>(Tb + off);
                 }
 #pragma unroll
-                for (int u = 0; u < 16; u++)
-                    dst[h * 16 + u] = make_float2(__fmul_rn(w, t[u].x), __fmul_rn(w, t[u].y));
+                for (int u = 0; u < 16; u++) dst[(h * 16 + u) * SIM2_CS] = __fmul_rn(w, t[u]);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[slot]);
@@ -384,13 +455,14 @@ __global__ void __launch_bounds__(SIM2_THREADS, 2) k_similarity2(const Sim2Param
 }
 
 cudaError_t launch_sim_rows(const uint8_t *codesT, int nseq, int npad, int ngroups,
-                            uint32_t *skipbits, unsigned long long *nbatches, cudaStream_t stream)
+                            uint32_t *skipbits, unsigned long long *nbatches, uint32_t *ngmask,
+                            cudaStream_t stream)
 {
     if (nseq == 0 || ngroups == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(nbatches, 0, (size_t)ngroups * sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
     dim3 grid(((npad >> 5) + 7) / 8, ngroups);
-    k_sim_rows<<<grid, 256, 0, stream>>>(codesT, nseq, npad, skipbits, nbatches);
+    k_sim_rows<<<grid, 256, 0, stream>>>(codesT, nseq, npad, skipbits, nbatches, ngmask);
     return cudaGetLastError();
 }
 
@@ -398,7 +470,8 @@ cudaError_t launch_sim_rows(const uint8_t *codesT, int nseq, int npad, int ngrou
 cudaError_t launch_similarity(const uint8_t *codesT, int nseq, int npad, int ncol,
                               const float *identities, const float *dist, int npos,
                               const uint8_t *col_skip, const uint32_t *skipbits,
-                              const unsigned long long *nbatches, int group_begin, int group_end,
+                              const uint32_t *ngmask, const unsigned long long *nbatches,
+                              int group_begin, int group_end,
                               float *num, float *den, int num_sms, cudaStream_t stream)
 {
     if (nseq == 0 || ncol == 0 || group_end <= group_begin) return cudaSuccess;
@@ -408,6 +481,7 @@ cudaError_t launch_similarity(const uint8_t *codesT, int nseq, int npad, int nco
     p.dist = dist;
     p.col_skip = col_skip;
     p.skipbits = skipbits;
+    p.ngmask = ngmask;
     p.nbatches = nbatches;
     p.num_out = num;
     p.den_out = den;
@@ -418,8 +492,7 @@ cudaError_t launch_similarity(const uint8_t *codesT, int nseq, int npad, int nco
     p.group_begin = group_begin;
     p.num_sms = num_sms;
     const int ngroups = group_end - group_begin;
-    // two CTAs per SM only when there are more groups than SMs; a deep ring otherwise
-    p.slots = SIM2_MAX_SLOTS;
+    p.slots = SIM2_MAX_SLOTS;  // 89 KB: two CTAs fit an SM when there are more groups than SMs
     const size_t smem = sim2_smem_bytes(p.slots);
     cudaError_t e = cudaFuncSetAttribute(k_similarity2, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);

@@ -72,6 +72,7 @@ struct Identity2Params {
     unsigned long long out_base;
     long long tile_begin;    // linear tile range [begin, end), see tiles_before2()
     long long tile_end;
+    int sb_begin, sb_end;    // the super-block rows the range covers (tile order, identity2.cu)
     int nb;                  // 64-row blocks holding kept rows
     int nb2;                 // blocks allocated (even)
     int nchunks;             // 128-column chunks
@@ -111,11 +112,13 @@ cudaError_t launch_sim_codes(const uint8_t *raw, int nseq, int ncol, size_t pitc
                              const uint8_t *lut256, const uint8_t *col_skip, uint8_t *codesT,
                              unsigned long long *first_error, cudaStream_t stream);
 cudaError_t launch_sim_rows(const uint8_t *codesT, int nseq, int npad, int ngroups,
-                            uint32_t *skipbits, unsigned long long *nbatches, cudaStream_t stream);
+                            uint32_t *skipbits, unsigned long long *nbatches, uint32_t *ngmask,
+                            cudaStream_t stream);
 cudaError_t launch_similarity(const uint8_t *codesT, int nseq, int npad, int ncol,
                               const float *identities, const float *dist, int npos,
                               const uint8_t *col_skip, const uint32_t *skipbits,
-                              const unsigned long long *nbatches, int group_begin, int group_end,
+                              const uint32_t *ngmask, const unsigned long long *nbatches,
+                              int group_begin, int group_end,
                               float *num, float *den, int num_sms, cudaStream_t stream);
 
 cudaError_t launch_row_lengths(const uint8_t *raw, int nseq, int ncol, size_t pitch, int *lengths,

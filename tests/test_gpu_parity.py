@@ -126,10 +126,11 @@ def test_identity_very_long_rows_unpacked_counters(gpu, port, n, L):
 
 
 @pytest.mark.parametrize("n,L", [(127, 129), (128, 128), (129, 127), (191, 64), (193, 65),
-                                 (600, 130), (1100, 70)])
+                                 (600, 130), (1100, 70), (2500, 140), (2700, 33)])
 def test_identity_tile_edges(gpu, port, n, L):
-    """Row counts around the 128-row super-block / 64-row block edges and several
-    tiles per CTA (both TMEM accumulator buffers, ring wrap-around)."""
+    """Row counts around the 128-row super-block / 64-row block edges, several
+    tiles per CTA (both TMEM accumulator buffers, ring wrap-around) and several
+    groups of super-block rows in the grouped tile order (full, partial, single)."""
     rng = np.random.default_rng(n * 31 + L)
     m = random_msa(rng, n, L, gap=0.4)
     with gpu.DeviceAlignment(m) as d:
