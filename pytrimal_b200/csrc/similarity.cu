@@ -102,7 +102,8 @@ cudaError_t launch_sim_codes(const uint8_t *raw, int nseq, int ncol, size_t pitc
 // main kernel: skipbits[group][j / 32] bit j % 32.  Row nseq-1 (never an outer
 // row) and padding are marked too.  nbatches[group] = number of 32-k batches
 // the main kernel exchanges for the group.  ngmask[group][row] = the row's
-// non-gap columns of the group as a bit mask (the denominator's operand).
+// non-gap columns of the group as a bit mask; colng[group][block][column] = the
+// non-gap rows of a 32-row block in one column (the denominator's operand).
 // ---------------------------------------------------------------------------
 constexpr int SIM2_KB = 32;  // inner rows (k) per batch
 
@@ -125,7 +126,8 @@ __device__ __forceinline__ uint32_t sim2_nongap4(uint32_t w)
 __global__ void __launch_bounds__(256) k_sim_rows(const uint8_t *__restrict__ codesT, int nseq,
                                                   int npad, uint32_t *__restrict__ skipbits,
                                                   unsigned long long *__restrict__ nbatches,
-                                                  uint32_t *__restrict__ ngmask)
+                                                  uint32_t *__restrict__ ngmask,
+                                                  uint32_t *__restrict__ colng)
 {
     const int group = blockIdx.y;
     const int nwords = npad >> 5;
@@ -140,6 +142,15 @@ __global__ void __launch_bounds__(256) k_sim_rows(const uint8_t *__restrict__ co
                           sim2_nongap4(b.y) << 20 | sim2_nongap4(b.z) << 24 |
                           sim2_nongap4(b.w) << 28;
     ngmask[(size_t)group * npad + j] = mask;
+    // the same bits transposed: for column `lane` of the group, the non-gap rows of this
+    // 32-row block (the denominator warp's operand, one word per column and batch)
+    uint32_t mine = 0;
+#pragma unroll
+    for (int c = 0; c < 32; c++) {
+        const uint32_t col = __ballot_sync(0xffffffffu, (mask >> c) & 1u);
+        if (lane == c) mine = col;
+    }
+    colng[(size_t)group * npad + j] = mine;
     const bool skip = mask == 0 || j >= nseq - 1;
     const uint32_t bits = __ballot_sync(0xffffffffu, skip);
     unsigned long long nb = skip ? 0ull : (unsigned long long)sim2_row_batches(j, nseq);
@@ -162,9 +173,10 @@ __global__ void __launch_bounds__(256) k_sim_rows(const uint8_t *__restrict__ co
 //                      rows of its column) and one FADD per inner row: the dependent
 //                      add (4 cycles) is the critical path.  Alone on its
 //                      sub-partition.
-//   denominator warp   lane = column.  Per inner row: the row's weight w and the
-//                      bit mask of the columns whose pair is counted (uniform
-//                      LDS.128), one predicated FADD.  Alone on its sub-partition.
+//   denominator warp   lane = column.  Per batch: the rows' weights w (uniform
+//                      LDS.128) and one word with the rows whose pair counts in its
+//                      column; per inner row one predicated FADD.  Alone on its
+//                      sub-partition.
 //   6 producer warps   (the two other sub-partitions) lane = inner row k of a
 //                      32-k batch.  Per batch a lane loads its row's 32 codes
 //                      (32 contiguous bytes), id[j,k] (coalesced) and the two
@@ -173,7 +185,8 @@ __global__ void __launch_bounds__(256) k_sim_rows(const uint8_t *__restrict__ co
 //                      offset; the table has an all-zero row/column for gaps),
 //                      multiplies by w and stores the term to a ring slot in
 //                      shared memory ([column][k] so the consumer reads vectors),
-//                      plus w and mask_j & mask_k once per row.
+//                      plus w once per row and, lane as a column, the mask of the
+//                      batch's rows that count in that column.
 // Terms of pairs the reference skips are exact +0 (w * 0, or not added).
 // A single warp can start one shared-memory load every ~4 cycles, which is what
 // limited the first version of this kernel (one warp, LDS.64 + two FADDs per row:
@@ -185,11 +198,11 @@ constexpr int SIM2_MAX_SLOTS = 18;
 constexpr int SIM2_CS = 36;                          // floats per column of a slot: [column][k], 16-byte rows,
                                                      // 8 lanes x LDS.128 cover the 32 banks (36 % 32 == 4)
 constexpr int SIM2_SLOT_D = 32 * SIM2_CS;            // numerator terms per slot
-constexpr int SIM2_SLOT_WORDS = SIM2_SLOT_D + 2 * SIM2_KB;  // + w[32] + mask[32]
+constexpr int SIM2_SLOT_WORDS = SIM2_SLOT_D + 2 * SIM2_KB;  // + w[32 rows] + counted-rows mask[32 columns]
 constexpr int SIM2_THREADS = 384;                    // 3 warps per sub-partition
 constexpr int SIM2_TROW = 64;                        // table row stride in floats (256 B: offset = a_j << 8 | 4 a_k)
 constexpr int SIM2_TABLE_WORDS = 32 * SIM2_TROW;
-constexpr int SIM2_PREFETCH_BATCHES = 4;             // own batches ahead (x SIM2_NPROD in array order)
+constexpr int SIM2_PREFETCH_BATCHES = 6;             // own batches ahead (x SIM2_NPROD in array order)
 
 __host__ __device__ constexpr size_t sim2_smem_bytes(int slots)
 {
@@ -203,91 +216,179 @@ struct Sim2Params {
     const uint8_t *col_skip;
     const uint32_t *skipbits;
     const uint32_t *ngmask;
+    const uint32_t *colng;
     const unsigned long long *nbatches;
     float *num_out, *den_out;
     int nseq, npad, ncol, npos;
     int group_begin;
     int slots;      // multiple of SIM2_NPROD
+    uint32_t zero;  // 0 (opaque to the compiler, see sim2_consume)
     int num_sms;
 };
 
-// One consumer warp's walk over the ring: IS_NUM ? sum of w * d : sum of w over counted pairs.
-template <bool IS_NUM>
-__device__ __forceinline__ float sim2_consume(const float *ring, uint64_t *full, uint64_t *empty,
-                                              int slots, unsigned long long btot, int lane)
+// The consumer warps' walk over the ring.  Common scheme: the data of a batch (32 inner
+// rows) are loaded into registers well before they are added, because a shared-memory load
+// takes 40-100 cycles to return while the producers keep the pipe busy; the loads follow
+// the first addition of the block they are issued in -- their address is tied to its
+// result through `zero`, a kernel argument that is 0 -- so that (a) that addition waits
+// for its own operands only, not for the new loads on the same scoreboard, and (b) the
+// loads (one per ~4 cycles from one warp) issue in the shadow of the dependent additions.
+// The barrier of the batch after the next is probed at the top of a batch (the answer takes
+// ~90 cycles) and looked at after the chain; the last three batches run without probes.
+struct Sim2Walk {
+    const float *ring;
+    uint64_t *full, *empty;
+    int slots;
+    int s0 = 0, s1 = 1, s2 = 2;   // slots of the current batch and the two after it
+    uint32_t p1 = 0, p2 = 0;      // phase parities of s1 and s2
+    __device__ __forceinline__ void rotate()
+    {
+        s0 = s1;
+        s1 = s2;
+        p1 = p2;
+        if (++s2 == slots) {
+            s2 = 0;
+            p2 ^= 1u;
+        }
+    }
+};
+
+// ---- numerator: acc += term, 32 terms of the lane's column per batch, [column][k] layout
+struct Sim2NumBatch {
+    float4 a[8];
+};
+__device__ __forceinline__ void sim2_num_load(Sim2NumBatch &B, const float *ring, int slot, int lane,
+                                              uint32_t dep)
+{
+    // one LDS.128 = four consecutive inner rows of the lane's column; dep is always 0
+    const float4 *src =
+        reinterpret_cast<const float4 *>(ring + (size_t)slot * SIM2_SLOT_WORDS + lane * SIM2_CS + dep);
+#pragma unroll
+    for (int q = 0; q < 8; q++) B.a[q] = src[q];
+}
+template <int K0, int K1>
+__device__ __forceinline__ float sim2_num_add(float acc, const Sim2NumBatch &B)
+{
+#pragma unroll
+    for (int k = K0; k < K1; k++) {
+        const float4 v = B.a[k >> 2];
+        acc = __fadd_rn(acc, (k & 3) == 0 ? v.x : (k & 3) == 1 ? v.y : (k & 3) == 2 ? v.z : v.w);
+    }
+    return acc;
+}
+
+__device__ __forceinline__ float sim2_consume_num(Sim2Walk W, unsigned long long btot, int lane,
+                                                  uint32_t zero)
 {
     float acc = 0.0f;
-    float4 v4[2][IS_NUM ? 4 : 1];  // numerator: the column's terms w * d of half a batch
-    float4 w4[2][IS_NUM ? 1 : 4];  // denominator: the rows' weights (uniform loads)
-    uint4 m4[2][IS_NUM ? 1 : 4];   //              and column masks (uniform loads)
-    const uint32_t lanebit = 1u << lane;
-    auto loadh = [&](int buf, int slot, int h) {
-        const float *s = ring + (size_t)slot * SIM2_SLOT_WORDS;
-        if constexpr (IS_NUM) {
-            // one LDS.128 = four consecutive inner rows of the lane's column
-            const float4 *src = reinterpret_cast<const float4 *>(s + lane * SIM2_CS) + h * 4;
-#pragma unroll
-            for (int q = 0; q < 4; q++) v4[buf][q] = src[q];
-        } else {
-            const float4 *ws = reinterpret_cast<const float4 *>(s + SIM2_SLOT_D) + h * 4;
-            const uint4 *ms = reinterpret_cast<const uint4 *>(s + SIM2_SLOT_D + SIM2_KB) + h * 4;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                w4[buf][q] = ws[q];
-                m4[buf][q] = ms[q];
-            }
-        }
-    };
-    auto addh = [&](int buf) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            if constexpr (IS_NUM) {
-                acc = __fadd_rn(acc, v4[buf][q].x);
-                acc = __fadd_rn(acc, v4[buf][q].y);
-                acc = __fadd_rn(acc, v4[buf][q].z);
-                acc = __fadd_rn(acc, v4[buf][q].w);
-            } else {
-                const float wq[4] = {w4[buf][q].x, w4[buf][q].y, w4[buf][q].z, w4[buf][q].w};
-                const uint32_t mq[4] = {m4[buf][q].x, m4[buf][q].y, m4[buf][q].z, m4[buf][q].w};
-#pragma unroll
-                for (int r = 0; r < 4; r++)
-                    if (mq[r] & lanebit) acc = __fadd_rn(acc, wq[r]);
-            }
-        }
-    };
-    int slot = 0;
-    uint32_t par = 0;
-    if (btot) {
-        mbar_wait(&full[0], 0);
-        loadh(0, 0, 0);
-    }
-    // (32-bit loop counter: the 64-bit compare chain costs the in-order warp ~25 cycles a batch)
-    for (unsigned long long left = btot; left;) {
-      const uint32_t nb = (uint32_t)min(left, 1ull << 30);
-      left -= nb;
-      for (uint32_t b = 0; b < nb; b++) {
-        int nslot = slot + 1;
-        uint32_t npar = par;
-        if (nslot == slots) {
-            nslot = 0;
-            npar ^= 1u;
-        }
-        // probe the next slot now (the probe takes ~90 cycles), look at the answer
-        // after the first half of this batch has been added
-        const bool more = b + 1 < nb || left != 0;
-        const uint32_t ready = more ? mbar_try_wait(&full[nslot], npar) : 1u;
-        loadh(1, slot, 1);
-        addh(0);
-        if (more) {
-            if (!ready) mbar_wait(&full[nslot], npar);
-            loadh(0, nslot, 0);
-        }
-        addh(1);
+    if (btot == 0) return acc;
+    Sim2NumBatch A, B;
+    mbar_wait(&W.full[0], 0);
+    sim2_num_load(A, W.ring, 0, lane, 0);
+    if (btot > 1) mbar_wait(&W.full[1], 0);
+    // invariant at the top of a batch: its terms are in registers (X), the barrier of the
+    // next batch (if any) has been seen complete
+    auto iter = [&](const Sim2NumBatch &X, Sim2NumBatch &Y) {   // batches b+1 and b+2 exist
+        const uint32_t ready2 = mbar_try_wait(&W.full[W.s2], W.p2);
+        acc = sim2_num_add<0, 1>(acc, X);
+        sim2_num_load(Y, W.ring, W.s1, lane, __float_as_uint(acc) & zero);
+        acc = sim2_num_add<1, 32>(acc, X);
+        if (!ready2) mbar_wait(&W.full[W.s2], W.p2);
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[slot]);
-        slot = nslot;
-        par = npar;
-      }
+        if (lane == 0) mbar_arrive(&W.empty[W.s0]);
+        W.rotate();
+    };
+    unsigned long long remaining = btot;
+    while (remaining > 3) {
+        iter(A, B);
+        iter(B, A);
+        remaining -= 2;
+    }
+    auto tail = [&](const Sim2NumBatch &X, Sim2NumBatch &Y) {
+        if (remaining > 1) sim2_num_load(Y, W.ring, W.s1, lane, 0);
+        acc = sim2_num_add<0, 32>(acc, X);
+        if (remaining > 2) mbar_wait(&W.full[W.s2], W.p2);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&W.empty[W.s0]);
+        W.rotate();
+        remaining--;
+    };
+    tail(A, B);
+    if (remaining) tail(B, A);
+    if (remaining) tail(A, B);
+    return acc;
+}
+
+// ---- denominator: acc += w[k] where the pair (j, k) counts in the lane's column.  Per inner
+// row one uniform weight and one uniform word with the counted columns; half a batch (16
+// rows) per register block.
+struct Sim2DenHalf {
+    float4 w[4];
+    uint4 m[4];
+};
+__device__ __forceinline__ void sim2_den_load(Sim2DenHalf &H, const float *ring, int slot, int h,
+                                              uint32_t dep)
+{
+    const float *s = ring + (size_t)slot * SIM2_SLOT_WORDS + SIM2_SLOT_D + dep;
+    const float4 *ws = reinterpret_cast<const float4 *>(s) + h * 4;
+    const uint4 *ms = reinterpret_cast<const uint4 *>(s + SIM2_KB) + h * 4;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        H.w[q] = ws[q];
+        H.m[q] = ms[q];
+    }
+}
+template <int K0, int K1>
+__device__ __forceinline__ float sim2_den_add(float acc, const Sim2DenHalf &H, uint32_t lanebit)
+{
+#pragma unroll
+    for (int k = K0; k < K1; k++) {
+        const float4 w = H.w[k >> 2];
+        const uint4 m = H.m[k >> 2];
+        const float wk = (k & 3) == 0 ? w.x : (k & 3) == 1 ? w.y : (k & 3) == 2 ? w.z : w.w;
+        const uint32_t mk = (k & 3) == 0 ? m.x : (k & 3) == 1 ? m.y : (k & 3) == 2 ? m.z : m.w;
+        if (mk & lanebit) acc = __fadd_rn(acc, wk);
+    }
+    return acc;
+}
+
+__device__ __forceinline__ float sim2_consume_den(Sim2Walk W, unsigned long long btot, int lane,
+                                                  uint32_t zero)
+{
+    float acc = 0.0f;
+    if (btot == 0) return acc;
+    const uint32_t lanebit = 1u << lane;
+    Sim2DenHalf H0, H1;
+    mbar_wait(&W.full[0], 0);
+    sim2_den_load(H0, W.ring, 0, 0, 0);
+    if (btot > 1) mbar_wait(&W.full[1], 0);
+    unsigned long long remaining = btot;
+    // invariant at the top of a batch: its first half is in H0, the barrier of the next
+    // batch (if any) has been seen complete
+    while (remaining > 2) {   // batches b+1 and b+2 exist
+        const uint32_t ready2 = mbar_try_wait(&W.full[W.s2], W.p2);
+        acc = sim2_den_add<0, 1>(acc, H0, lanebit);
+        sim2_den_load(H1, W.ring, W.s0, 1, __float_as_uint(acc) & zero);
+        acc = sim2_den_add<1, 16>(acc, H0, lanebit);
+        acc = sim2_den_add<0, 1>(acc, H1, lanebit);
+        sim2_den_load(H0, W.ring, W.s1, 0, __float_as_uint(acc) & zero);
+        acc = sim2_den_add<1, 16>(acc, H1, lanebit);
+        if (!ready2) mbar_wait(&W.full[W.s2], W.p2);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&W.empty[W.s0]);
+        W.rotate();
+        remaining--;
+    }
+    while (remaining) {
+        sim2_den_load(H1, W.ring, W.s0, 1, 0);
+        acc = sim2_den_add<0, 16>(acc, H0, lanebit);
+        if (remaining > 1) sim2_den_load(H0, W.ring, W.s1, 0, 0);
+        acc = sim2_den_add<0, 16>(acc, H1, lanebit);
+        if (remaining > 2) mbar_wait(&W.full[W.s2], W.p2);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&W.empty[W.s0]);
+        W.rotate();
+        remaining--;
     }
     return acc;
 }
@@ -327,9 +428,13 @@ __global__ void __launch_bounds__(SIM2_THREADS, 2) k_similarity2(const Sim2Param
 
     if (warp == cn || warp == cd) {
         // ------------------------------ consumers -----------------------------
-        float acc;
-        if (warp == cn) acc = sim2_consume<true>(ring, full, empty, p.slots, p.nbatches[group], lane);
-        else acc = sim2_consume<false>(ring, full, empty, p.slots, p.nbatches[group], lane);
+        Sim2Walk W;
+        W.ring = ring;
+        W.full = full;
+        W.empty = empty;
+        W.slots = p.slots;
+        const float acc = warp == cn ? sim2_consume_num(W, p.nbatches[group], lane, p.zero)
+                                     : sim2_consume_den(W, p.nbatches[group], lane, p.zero);
         const int col = group * 32 + lane;
         if (col < p.ncol && !p.col_skip[col]) (warp == cn ? p.num_out : p.den_out)[col] = acc;
     } else if (sp != cn && sp != cd) {
@@ -388,7 +493,7 @@ __global__ void __launch_bounds__(SIM2_THREADS, 2) k_similarity2(const Sim2Param
             L.c1 = __ldg(cp + 1);
             L.j0 = __ldg(jp);
             L.j1 = __ldg(jp + 1);
-            L.mask = __ldg(ngm + k) & __ldg(ngm + fj);
+            L.mask = __ldg(ngm + k) & __ldg(ngm + fj);  // columns in which the pair counts
             // identities[(fj, k)], packed upper triangle without diagonal (template.h:158,171,181)
             const unsigned long long rowbase =
                 (unsigned long long)fj * nn - ((unsigned long long)fj * (fj + 1)) / 2 - fj - 1;
@@ -456,13 +561,13 @@ __global__ void __launch_bounds__(SIM2_THREADS, 2) k_similarity2(const Sim2Param
 
 cudaError_t launch_sim_rows(const uint8_t *codesT, int nseq, int npad, int ngroups,
                             uint32_t *skipbits, unsigned long long *nbatches, uint32_t *ngmask,
-                            cudaStream_t stream)
+                            uint32_t *colng, cudaStream_t stream)
 {
     if (nseq == 0 || ngroups == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(nbatches, 0, (size_t)ngroups * sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
     dim3 grid(((npad >> 5) + 7) / 8, ngroups);
-    k_sim_rows<<<grid, 256, 0, stream>>>(codesT, nseq, npad, skipbits, nbatches, ngmask);
+    k_sim_rows<<<grid, 256, 0, stream>>>(codesT, nseq, npad, skipbits, nbatches, ngmask, colng);
     return cudaGetLastError();
 }
 
@@ -470,8 +575,8 @@ cudaError_t launch_sim_rows(const uint8_t *codesT, int nseq, int npad, int ngrou
 cudaError_t launch_similarity(const uint8_t *codesT, int nseq, int npad, int ncol,
                               const float *identities, const float *dist, int npos,
                               const uint8_t *col_skip, const uint32_t *skipbits,
-                              const uint32_t *ngmask, const unsigned long long *nbatches,
-                              int group_begin, int group_end,
+                              const uint32_t *ngmask, const uint32_t *colng,
+                              const unsigned long long *nbatches, int group_begin, int group_end,
                               float *num, float *den, int num_sms, cudaStream_t stream)
 {
     if (nseq == 0 || ncol == 0 || group_end <= group_begin) return cudaSuccess;
@@ -482,6 +587,7 @@ cudaError_t launch_similarity(const uint8_t *codesT, int nseq, int npad, int nco
     p.col_skip = col_skip;
     p.skipbits = skipbits;
     p.ngmask = ngmask;
+    p.colng = colng;
     p.nbatches = nbatches;
     p.num_out = num;
     p.den_out = den;
@@ -492,7 +598,7 @@ cudaError_t launch_similarity(const uint8_t *codesT, int nseq, int npad, int nco
     p.group_begin = group_begin;
     p.num_sms = num_sms;
     const int ngroups = group_end - group_begin;
-    p.slots = SIM2_MAX_SLOTS;  // 89 KB: two CTAs fit an SM when there are more groups than SMs
+    p.slots = SIM2_MAX_SLOTS;  // 96 KB: two CTAs fit an SM when there are more groups than SMs
     const size_t smem = sim2_smem_bytes(p.slots);
     cudaError_t e = cudaFuncSetAttribute(k_similarity2, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
