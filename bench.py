@@ -45,10 +45,10 @@ METRIC = "pair-column comparisons/s (pairwise identity)"
 UNIT = "pair-col/s"
 OPS_PER_PAIR_COLUMN = 42  # 2*(20 one-hot planes + 1 gap plane) int8 tensor ops
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_identity2 launch at full C4 size, from
-# the ncu --set full capture summarised in profiles/r01b_ncu_identity2_c4.txt (3.86 GB read
-# + 4.98 GB written; algorithmic bytes n*L + 4*P = 5.05 GB -- the reads are L2 sector fills
-# for the unaligned row segments of the packed triangular output)
-NCU_TRAFFIC_BYTES = 3.857744e9 + 4.984726e9
+# the ncu --set full capture summarised in profiles/r01k_ncu_identity2_c4.txt (1.62 GB read
+# + 5.06 GB written; algorithmic bytes n*L + 4*P = 5.05 GB -- the reads are operand blocks
+# that miss L2, once per group of 8 super-block rows)
+NCU_TRAFFIC_BYTES = 1.618266e9 + 5.061914e9
 
 
 def measured_peaks():

@@ -1600,7 +1600,7 @@ static int similarity_impl(tcu_msa *m, tcu_comm *comm, uint8_t indet, const floa
     const size_t nb_bytes = ((size_t)ngroups * sizeof(unsigned long long) + 255) / 256 * 256;
     const size_t ngm_bytes = (size_t)ngroups * npad * sizeof(uint32_t);
     const size_t need = codes_bytes + 2 * vec_bytes + dist_bytes + m->pitch + 256 + 64 + skip_bytes +
-                        nb_bytes + 2 * ngm_bytes;
+                        nb_bytes + ngm_bytes;
     int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, need);
     if (rc != TCU_OK) return rc;
     uint8_t *base = (uint8_t *)m->d_scratch;
@@ -1614,7 +1614,6 @@ static int similarity_impl(tcu_msa *m, tcu_comm *comm, uint8_t indet, const floa
     unsigned long long *d_nbatches = (unsigned long long *)((uint8_t *)d_rowskip + skip_bytes);
     uint8_t *d_codes = (uint8_t *)d_nbatches + nb_bytes;
     uint32_t *d_ngmask = (uint32_t *)(d_codes + codes_bytes);
-    uint32_t *d_colng = d_ngmask + (size_t)ngroups * npad;
 
     const unsigned long long no_err = ~0ull;
     unsigned long long first_err = no_err;
@@ -1627,7 +1626,7 @@ static int similarity_impl(tcu_msa *m, tcu_comm *comm, uint8_t indet, const floa
     CK(cudaMemcpyAsync(d_err, &no_err, sizeof no_err, cudaMemcpyHostToDevice, m->stream));
     CK(cudaEventRecord(m->ev[1], m->stream));
     CK(launch_sim_codes(m->d_raw, n, L, m->pitch, npad, d_lut, d_skip, d_codes, d_err, m->stream));
-    CK(launch_sim_rows(d_codes, n, npad, ngroups, d_rowskip, d_nbatches, d_ngmask, d_colng, m->stream));
+    CK(launch_sim_rows(d_codes, n, npad, ngroups, d_rowskip, d_nbatches, d_ngmask, m->stream));
     CK(cudaEventRecord(m->ev[2], m->stream));
     CK(cudaMemcpyAsync(&first_err, d_err, sizeof first_err, cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
@@ -1655,7 +1654,7 @@ static int similarity_impl(tcu_msa *m, tcu_comm *comm, uint8_t indet, const floa
     if (comm) tcu_shard_range(col_groups, 1, comm->rank, comm->world, &g0, &g1);
     CK(cudaEventRecord(m->ev[2], m->stream));
     CK(launch_similarity(d_codes, n, npad, L, m->d_ident, d_dist, npos, d_skip, d_rowskip,
-                         d_ngmask, d_colng, d_nbatches, g0, g1, d_num, d_den, m->num_sms, m->stream));
+                         d_ngmask, d_nbatches, g0, g1, d_num, d_den, m->num_sms, m->stream));
     CK(cudaEventRecord(m->ev[3], m->stream));
     if (comm) {
         for (int v = 0; v < 2; v++) {

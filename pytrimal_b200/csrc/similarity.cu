@@ -102,8 +102,8 @@ cudaError_t launch_sim_codes(const uint8_t *raw, int nseq, int ncol, size_t pitc
 // main kernel: skipbits[group][j / 32] bit j % 32.  Row nseq-1 (never an outer
 // row) and padding are marked too.  nbatches[group] = number of 32-k batches
 // the main kernel exchanges for the group.  ngmask[group][row] = the row's
-// non-gap columns of the group as a bit mask; colng[group][block][column] = the
-// non-gap rows of a 32-row block in one column (the denominator's operand).
+// non-gap columns of the group as a bit mask (two of them ANDed say in which
+// columns a pair counts for the denominator).
 // ---------------------------------------------------------------------------
 constexpr int SIM2_KB = 32;  // inner rows (k) per batch
 
@@ -126,8 +126,7 @@ __device__ __forceinline__ uint32_t sim2_nongap4(uint32_t w)
 __global__ void __launch_bounds__(256) k_sim_rows(const uint8_t *__restrict__ codesT, int nseq,
                                                   int npad, uint32_t *__restrict__ skipbits,
                                                   unsigned long long *__restrict__ nbatches,
-                                                  uint32_t *__restrict__ ngmask,
-                                                  uint32_t *__restrict__ colng)
+                                                  uint32_t *__restrict__ ngmask)
 {
     const int group = blockIdx.y;
     const int nwords = npad >> 5;
@@ -142,15 +141,6 @@ __global__ void __launch_bounds__(256) k_sim_rows(const uint8_t *__restrict__ co
                           sim2_nongap4(b.y) << 20 | sim2_nongap4(b.z) << 24 |
                           sim2_nongap4(b.w) << 28;
     ngmask[(size_t)group * npad + j] = mask;
-    // the same bits transposed: for column `lane` of the group, the non-gap rows of this
-    // 32-row block (the denominator warp's operand, one word per column and batch)
-    uint32_t mine = 0;
-#pragma unroll
-    for (int c = 0; c < 32; c++) {
-        const uint32_t col = __ballot_sync(0xffffffffu, (mask >> c) & 1u);
-        if (lane == c) mine = col;
-    }
-    colng[(size_t)group * npad + j] = mine;
     const bool skip = mask == 0 || j >= nseq - 1;
     const uint32_t bits = __ballot_sync(0xffffffffu, skip);
     unsigned long long nb = skip ? 0ull : (unsigned long long)sim2_row_batches(j, nseq);
@@ -169,36 +159,30 @@ __global__ void __launch_bounds__(256) k_sim_rows(const uint8_t *__restrict__ co
 // order, one rounded fp32 add after the other, but the two chains are
 // independent of each other and their TERMS are independent.  The four SM
 // sub-partitions (warp id % 4) get different jobs:
-//   numerator warp     lane = column.  Nothing but LDS.128 (four consecutive inner
-//                      rows of its column) and one FADD per inner row: the dependent
-//                      add (4 cycles) is the critical path.  Alone on its
-//                      sub-partition.
-//   denominator warp   lane = column.  Per batch: the rows' weights w (uniform
-//                      LDS.128) and one word with the rows whose pair counts in its
-//                      column; per inner row one predicated FADD.  Alone on its
-//                      sub-partition.
+//   numerator warp,    lane = column.  Nothing but LDS.128 (four consecutive inner
+//   denominator warp   rows of the lane's column) and one FADD per inner row: the
+//                      dependent add (4 cycles) is the critical path.  Each is alone
+//                      on its sub-partition.  The denominator's terms are w where the
+//                      pair counts in the column and +0 elsewhere.
 //   6 producer warps   (the two other sub-partitions) lane = inner row k of a
 //                      32-k batch.  Per batch a lane loads its row's 32 codes
 //                      (32 contiguous bytes), id[j,k] (coalesced) and the two
 //                      non-gap masks, forms w = 1 - id once, and for each of the
 //                      32 columns looks up D[a_j][a_k] (one PRMT forms the table
 //                      offset; the table has an all-zero row/column for gaps),
-//                      multiplies by w and stores the term to a ring slot in
-//                      shared memory ([column][k] so the consumer reads vectors),
-//                      plus w once per row and, lane as a column, the mask of the
-//                      batch's rows that count in that column.
-// Terms of pairs the reference skips are exact +0 (w * 0, or not added).
+//                      multiplies by w and stores both terms to a ring slot in
+//                      shared memory ([column][k], so the consumers read vectors).
+// Terms of pairs the reference skips are exact +0.
 // A single warp can start one shared-memory load every ~4 cycles, which is what
 // limited the first version of this kernel (one warp, LDS.64 + two FADDs per row:
-// 10.6 cycles per row); hence the vector loads and the chain split over two warps.
+// 10.6 cycles per row); hence the vector loads and one chain per warp.
 // Slots are handed over with mbarriers (full: one arrival; empty: two).
 // ---------------------------------------------------------------------------
 constexpr int SIM2_NPROD = 6;
-constexpr int SIM2_MAX_SLOTS = 18;
-constexpr int SIM2_CS = 36;                          // floats per column of a slot: [column][k], 16-byte rows,
-                                                     // 8 lanes x LDS.128 cover the 32 banks (36 % 32 == 4)
-constexpr int SIM2_SLOT_D = 32 * SIM2_CS;            // numerator terms per slot
-constexpr int SIM2_SLOT_WORDS = SIM2_SLOT_D + 2 * SIM2_KB;  // + w[32 rows] + counted-rows mask[32 columns]
+constexpr int SIM2_MAX_SLOTS = 12;
+constexpr int SIM2_CS = 68;                          // floats per column of a slot: [column][num 32 | den 32 | pad 4],
+                                                     // 8 lanes x LDS.128 cover the 32 banks (68 % 32 == 4)
+constexpr int SIM2_SLOT_WORDS = 32 * SIM2_CS;
 constexpr int SIM2_THREADS = 384;                    // 3 warps per sub-partition
 constexpr int SIM2_TROW = 64;                        // table row stride in floats (256 B: offset = a_j << 8 | 4 a_k)
 constexpr int SIM2_TABLE_WORDS = 32 * SIM2_TROW;
@@ -216,7 +200,6 @@ struct Sim2Params {
     const uint8_t *col_skip;
     const uint32_t *skipbits;
     const uint32_t *ngmask;
-    const uint32_t *colng;
     const unsigned long long *nbatches;
     float *num_out, *den_out;
     int nseq, npad, ncol, npos;
@@ -253,16 +236,18 @@ struct Sim2Walk {
     }
 };
 
-// ---- numerator: acc += term, 32 terms of the lane's column per batch, [column][k] layout
+// ---- one chain: acc += term, 32 terms of the lane's column per batch.  `off` selects the
+// numerator (0) or denominator (SIM2_KB) terms of the [column][2][k] slot layout.
 struct Sim2NumBatch {
     float4 a[8];
 };
 __device__ __forceinline__ void sim2_num_load(Sim2NumBatch &B, const float *ring, int slot, int lane,
                                               uint32_t dep)
 {
-    // one LDS.128 = four consecutive inner rows of the lane's column; dep is always 0
+    // one LDS.128 = four consecutive inner rows of the lane's column; `lane` is the word
+    // offset of the lane's terms inside a slot, dep is always 0
     const float4 *src =
-        reinterpret_cast<const float4 *>(ring + (size_t)slot * SIM2_SLOT_WORDS + lane * SIM2_CS + dep);
+        reinterpret_cast<const float4 *>(ring + (size_t)slot * SIM2_SLOT_WORDS + lane + dep);
 #pragma unroll
     for (int q = 0; q < 8; q++) B.a[q] = src[q];
 }
@@ -277,9 +262,11 @@ __device__ __forceinline__ float sim2_num_add(float acc, const Sim2NumBatch &B)
     return acc;
 }
 
-__device__ __forceinline__ float sim2_consume_num(Sim2Walk W, unsigned long long btot, int lane,
-                                                  uint32_t zero)
+__device__ __forceinline__ float sim2_consume(Sim2Walk W, unsigned long long btot, int lane, int off,
+                                              uint32_t zero)
 {
+    const bool lane0 = lane == 0;
+    lane = lane * SIM2_CS + off;  // word offset of the lane's terms inside a slot
     float acc = 0.0f;
     if (btot == 0) return acc;
     Sim2NumBatch A, B;
@@ -295,7 +282,7 @@ __device__ __forceinline__ float sim2_consume_num(Sim2Walk W, unsigned long long
         acc = sim2_num_add<1, 32>(acc, X);
         if (!ready2) mbar_wait(&W.full[W.s2], W.p2);
         __syncwarp();
-        if (lane == 0) mbar_arrive(&W.empty[W.s0]);
+        if (lane0) mbar_arrive(&W.empty[W.s0]);
         W.rotate();
     };
     unsigned long long remaining = btot;
@@ -309,87 +296,13 @@ __device__ __forceinline__ float sim2_consume_num(Sim2Walk W, unsigned long long
         acc = sim2_num_add<0, 32>(acc, X);
         if (remaining > 2) mbar_wait(&W.full[W.s2], W.p2);
         __syncwarp();
-        if (lane == 0) mbar_arrive(&W.empty[W.s0]);
+        if (lane0) mbar_arrive(&W.empty[W.s0]);
         W.rotate();
         remaining--;
     };
     tail(A, B);
     if (remaining) tail(B, A);
     if (remaining) tail(A, B);
-    return acc;
-}
-
-// ---- denominator: acc += w[k] where the pair (j, k) counts in the lane's column.  Per inner
-// row one uniform weight and one uniform word with the counted columns; half a batch (16
-// rows) per register block.
-struct Sim2DenHalf {
-    float4 w[4];
-    uint4 m[4];
-};
-__device__ __forceinline__ void sim2_den_load(Sim2DenHalf &H, const float *ring, int slot, int h,
-                                              uint32_t dep)
-{
-    const float *s = ring + (size_t)slot * SIM2_SLOT_WORDS + SIM2_SLOT_D + dep;
-    const float4 *ws = reinterpret_cast<const float4 *>(s) + h * 4;
-    const uint4 *ms = reinterpret_cast<const uint4 *>(s + SIM2_KB) + h * 4;
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        H.w[q] = ws[q];
-        H.m[q] = ms[q];
-    }
-}
-template <int K0, int K1>
-__device__ __forceinline__ float sim2_den_add(float acc, const Sim2DenHalf &H, uint32_t lanebit)
-{
-#pragma unroll
-    for (int k = K0; k < K1; k++) {
-        const float4 w = H.w[k >> 2];
-        const uint4 m = H.m[k >> 2];
-        const float wk = (k & 3) == 0 ? w.x : (k & 3) == 1 ? w.y : (k & 3) == 2 ? w.z : w.w;
-        const uint32_t mk = (k & 3) == 0 ? m.x : (k & 3) == 1 ? m.y : (k & 3) == 2 ? m.z : m.w;
-        if (mk & lanebit) acc = __fadd_rn(acc, wk);
-    }
-    return acc;
-}
-
-__device__ __forceinline__ float sim2_consume_den(Sim2Walk W, unsigned long long btot, int lane,
-                                                  uint32_t zero)
-{
-    float acc = 0.0f;
-    if (btot == 0) return acc;
-    const uint32_t lanebit = 1u << lane;
-    Sim2DenHalf H0, H1;
-    mbar_wait(&W.full[0], 0);
-    sim2_den_load(H0, W.ring, 0, 0, 0);
-    if (btot > 1) mbar_wait(&W.full[1], 0);
-    unsigned long long remaining = btot;
-    // invariant at the top of a batch: its first half is in H0, the barrier of the next
-    // batch (if any) has been seen complete
-    while (remaining > 2) {   // batches b+1 and b+2 exist
-        const uint32_t ready2 = mbar_try_wait(&W.full[W.s2], W.p2);
-        acc = sim2_den_add<0, 1>(acc, H0, lanebit);
-        sim2_den_load(H1, W.ring, W.s0, 1, __float_as_uint(acc) & zero);
-        acc = sim2_den_add<1, 16>(acc, H0, lanebit);
-        acc = sim2_den_add<0, 1>(acc, H1, lanebit);
-        sim2_den_load(H0, W.ring, W.s1, 0, __float_as_uint(acc) & zero);
-        acc = sim2_den_add<1, 16>(acc, H1, lanebit);
-        if (!ready2) mbar_wait(&W.full[W.s2], W.p2);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&W.empty[W.s0]);
-        W.rotate();
-        remaining--;
-    }
-    while (remaining) {
-        sim2_den_load(H1, W.ring, W.s0, 1, 0);
-        acc = sim2_den_add<0, 16>(acc, H0, lanebit);
-        if (remaining > 1) sim2_den_load(H0, W.ring, W.s1, 0, 0);
-        acc = sim2_den_add<0, 16>(acc, H1, lanebit);
-        if (remaining > 2) mbar_wait(&W.full[W.s2], W.p2);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&W.empty[W.s0]);
-        W.rotate();
-        remaining--;
-    }
     return acc;
 }
 
@@ -433,8 +346,7 @@ __global__ void __launch_bounds__(SIM2_THREADS, 2) k_similarity2(const Sim2Param
         W.full = full;
         W.empty = empty;
         W.slots = p.slots;
-        const float acc = warp == cn ? sim2_consume_num(W, p.nbatches[group], lane, p.zero)
-                                     : sim2_consume_den(W, p.nbatches[group], lane, p.zero);
+        const float acc = sim2_consume(W, p.nbatches[group], lane, warp == cn ? 0 : SIM2_KB, p.zero);
         const int col = group * 32 + lane;
         if (col < p.ncol && !p.col_skip[col]) (warp == cn ? p.num_out : p.den_out)[col] = acc;
     } else if (sp != cn && sp != cd) {
@@ -444,7 +356,7 @@ __global__ void __launch_bounds__(SIM2_THREADS, 2) k_similarity2(const Sim2Param
         // issue slots with nobody)
         int pi = 0;
         for (int w = 0; w < warp; w++) pi += ((w & 3) != cn && (w & 3) != cd);
-        const int spp = p.slots / SIM2_NPROD;  // slots per producer
+        constexpr int spp = SIM2_MAX_SLOTS / SIM2_NPROD;  // slots per producer (p.slots == SIM2_MAX_SLOTS)
         const int nwords = p.npad >> 5;
         const uint32_t *skipw = p.skipbits + (size_t)group * nwords;
         const uint32_t *ngm = p.ngmask + (size_t)group * p.npad;
@@ -523,13 +435,10 @@ __global__ void __launch_bounds__(SIM2_THREADS, 2) k_similarity2(const Sim2Param
                                      cur.c1.x, cur.c1.y, cur.c1.z, cur.c1.w};
             const uint32_t jw8[8] = {cur.j0.x, cur.j0.y, cur.j0.z, cur.j0.w,
                                      cur.j1.x, cur.j1.y, cur.j1.z, cur.j1.w};
-            float *sl = ring + (size_t)slot * SIM2_SLOT_WORDS;
-            float *dst = sl + lane;
+            float *dst = ring + (size_t)slot * SIM2_SLOT_WORDS + lane;
             const float w = __fsub_rn(1.0f, cur.id);  // 0 for k <= j and padding
-            sl[SIM2_SLOT_D + lane] = w;
-            reinterpret_cast<uint32_t *>(sl)[SIM2_SLOT_D + SIM2_KB + lane] = cur.mask;
             const char *Tb = reinterpret_cast<const char *>(T);
-            // 16 table loads in flight, then 16 stores (the compiler must assume that the
+            // 16 table loads in flight, then the stores (the compiler must assume that the
             // ring stores alias the table and would otherwise serialise load -> store)
 #pragma unroll
             for (int h = 0; h < 2; h++) {
@@ -546,7 +455,11 @@ __global__ void __launch_bounds__(SIM2_THREADS, 2) k_similarity2(const Sim2Param
                     t[u] = *reinterpret_cast<const float *>(Tb + off);
                 }
 #pragma unroll
-                for (int u = 0; u < 16; u++) dst[(h * 16 + u) * SIM2_CS] = __fmul_rn(w, t[u]);
+                for (int u = 0; u < 16; u++) {
+                    const int c = h * 16 + u;
+                    dst[c * SIM2_CS] = __fmul_rn(w, t[u]);                              // numerator term
+                    dst[c * SIM2_CS + SIM2_KB] = (cur.mask & (1u << c)) ? w : 0.0f;     // denominator term
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[slot]);
@@ -561,13 +474,13 @@ __global__ void __launch_bounds__(SIM2_THREADS, 2) k_similarity2(const Sim2Param
 
 cudaError_t launch_sim_rows(const uint8_t *codesT, int nseq, int npad, int ngroups,
                             uint32_t *skipbits, unsigned long long *nbatches, uint32_t *ngmask,
-                            uint32_t *colng, cudaStream_t stream)
+                            cudaStream_t stream)
 {
     if (nseq == 0 || ngroups == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(nbatches, 0, (size_t)ngroups * sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
     dim3 grid(((npad >> 5) + 7) / 8, ngroups);
-    k_sim_rows<<<grid, 256, 0, stream>>>(codesT, nseq, npad, skipbits, nbatches, ngmask, colng);
+    k_sim_rows<<<grid, 256, 0, stream>>>(codesT, nseq, npad, skipbits, nbatches, ngmask);
     return cudaGetLastError();
 }
 
@@ -575,8 +488,8 @@ cudaError_t launch_sim_rows(const uint8_t *codesT, int nseq, int npad, int ngrou
 cudaError_t launch_similarity(const uint8_t *codesT, int nseq, int npad, int ncol,
                               const float *identities, const float *dist, int npos,
                               const uint8_t *col_skip, const uint32_t *skipbits,
-                              const uint32_t *ngmask, const uint32_t *colng,
-                              const unsigned long long *nbatches, int group_begin, int group_end,
+                              const uint32_t *ngmask, const unsigned long long *nbatches,
+                              int group_begin, int group_end,
                               float *num, float *den, int num_sms, cudaStream_t stream)
 {
     if (nseq == 0 || ncol == 0 || group_end <= group_begin) return cudaSuccess;
@@ -587,7 +500,6 @@ cudaError_t launch_similarity(const uint8_t *codesT, int nseq, int npad, int nco
     p.col_skip = col_skip;
     p.skipbits = skipbits;
     p.ngmask = ngmask;
-    p.colng = colng;
     p.nbatches = nbatches;
     p.num_out = num;
     p.den_out = den;
@@ -598,7 +510,7 @@ cudaError_t launch_similarity(const uint8_t *codesT, int nseq, int npad, int nco
     p.group_begin = group_begin;
     p.num_sms = num_sms;
     const int ngroups = group_end - group_begin;
-    p.slots = SIM2_MAX_SLOTS;  // 96 KB: two CTAs fit an SM when there are more groups than SMs
+    p.slots = SIM2_MAX_SLOTS;  // 110 KB: two CTAs fit an SM when there are more groups than SMs
     const size_t smem = sim2_smem_bytes(p.slots);
     cudaError_t e = cudaFuncSetAttribute(k_similarity2, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);

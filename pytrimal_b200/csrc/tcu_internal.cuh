@@ -113,12 +113,12 @@ cudaError_t launch_sim_codes(const uint8_t *raw, int nseq, int ncol, size_t pitc
                              unsigned long long *first_error, cudaStream_t stream);
 cudaError_t launch_sim_rows(const uint8_t *codesT, int nseq, int npad, int ngroups,
                             uint32_t *skipbits, unsigned long long *nbatches, uint32_t *ngmask,
-                            uint32_t *colng, cudaStream_t stream);
+                            cudaStream_t stream);
 cudaError_t launch_similarity(const uint8_t *codesT, int nseq, int npad, int ncol,
                               const float *identities, const float *dist, int npos,
                               const uint8_t *col_skip, const uint32_t *skipbits,
-                              const uint32_t *ngmask, const uint32_t *colng,
-                              const unsigned long long *nbatches, int group_begin, int group_end,
+                              const uint32_t *ngmask, const unsigned long long *nbatches,
+                              int group_begin, int group_end,
                               float *num, float *den, int num_sms, cudaStream_t stream);
 
 cudaError_t launch_row_lengths(const uint8_t *raw, int nseq, int ncol, size_t pitch, int *lengths,

@@ -56,7 +56,8 @@ def main():
                "alignment_build_s": build_s, "cuda_trim_s_first": times[0],
                "cuda_trim_s_best": min(times[1:]), "kept_sequences": len(out.sequences),
                "kept_columns": len(out.sequences[0]) if len(out.sequences) else 0}
-        rows = min(n, args.avx2_rows)
+        # C3 also runs the scalar similarity loop on the CPU (1e9 pair-col/s): fewer rows there
+        rows = min(n, args.avx2_rows if cfg != "C3" else min(args.avx2_rows, 1500))
         sub = pytrimal.Alignment(names[:rows], [bytes(r) for r in m[:rows]])
         cpu = getattr(pytrimal, cls)(platform="avx2", **kwargs)
         cpu.trim(sub)                       # platform applies from the 2nd call
