@@ -395,7 +395,8 @@ __global__ void __launch_bounds__(SIM2_THREADS, 2) k_similarity2(const Sim2Param
         struct Loaded {
             uint4 c0, c1, j0, j1;
             float id;
-            uint32_t mask;
+            uint32_t mk, mj;  // non-gap columns of row k and of row j (ANDed at use: combining them
+                              // here would make the prefetch wait for both loads)
         };
         auto fetch = [&](int fj, int fkb, Loaded &L) {
             const int k = fkb + lane;
@@ -405,7 +406,8 @@ __global__ void __launch_bounds__(SIM2_THREADS, 2) k_similarity2(const Sim2Param
             L.c1 = __ldg(cp + 1);
             L.j0 = __ldg(jp);
             L.j1 = __ldg(jp + 1);
-            L.mask = __ldg(ngm + k) & __ldg(ngm + fj);  // columns in which the pair counts
+            L.mk = __ldg(ngm + k);
+            L.mj = __ldg(ngm + fj);
             // identities[(fj, k)], packed upper triangle without diagonal (template.h:158,171,181)
             const unsigned long long rowbase =
                 (unsigned long long)fj * nn - ((unsigned long long)fj * (fj + 1)) / 2 - fj - 1;
@@ -437,6 +439,7 @@ __global__ void __launch_bounds__(SIM2_THREADS, 2) k_similarity2(const Sim2Param
                                      cur.j1.x, cur.j1.y, cur.j1.z, cur.j1.w};
             float *dst = ring + (size_t)slot * SIM2_SLOT_WORDS + lane;
             const float w = __fsub_rn(1.0f, cur.id);  // 0 for k <= j and padding
+            const uint32_t counted = cur.mk & cur.mj;  // columns in which the pair counts
             const char *Tb = reinterpret_cast<const char *>(T);
             // 16 table loads in flight, then the stores (the compiler must assume that the
             // ring stores alias the table and would otherwise serialise load -> store)
@@ -458,7 +461,7 @@ __global__ void __launch_bounds__(SIM2_THREADS, 2) k_similarity2(const Sim2Param
                 for (int u = 0; u < 16; u++) {
                     const int c = h * 16 + u;
                     dst[c * SIM2_CS] = __fmul_rn(w, t[u]);                              // numerator term
-                    dst[c * SIM2_CS + SIM2_KB] = (cur.mask & (1u << c)) ? w : 0.0f;     // denominator term
+                    dst[c * SIM2_CS + SIM2_KB] = (counted & (1u << c)) ? w : 0.0f;     // denominator term
                 }
             }
             __syncwarp();
