@@ -157,29 +157,33 @@ __global__ void __launch_bounds__(256) k_sim_rows(const uint8_t *__restrict__ co
 //
 // The chains  num += w * d;  den += w  of a column must run in the reference's
 // order, one rounded fp32 add after the other, but the two chains are
-// independent of each other and their TERMS are independent.  The four SM
-// sub-partitions (warp id % 4) get different jobs:
+// independent of each other and their TERMS are independent.  The twelve warps of a CTA
+// get different jobs by SM sub-partition (warp id % 4):
 //   numerator warp,    lane = column.  Nothing but LDS.128 (four consecutive inner
 //   denominator warp   rows of the lane's column) and one FADD per inner row: the
-//                      dependent add (4 cycles) is the critical path.  Each is alone
-//                      on its sub-partition.  The denominator's terms are w where the
-//                      pair counts in the column and +0 elsewhere.
-//   6 producer warps   (the two other sub-partitions) lane = inner row k of a
-//                      32-k batch.  Per batch a lane loads its row's 32 codes
-//                      (32 contiguous bytes), id[j,k] (coalesced) and the two
-//                      non-gap masks, forms w = 1 - id once, and for each of the
-//                      32 columns looks up D[a_j][a_k] (one PRMT forms the table
-//                      offset; the table has an all-zero row/column for gaps),
-//                      multiplies by w and stores both terms to a ring slot in
-//                      shared memory ([column][k], so the consumers read vectors).
+//                      dependent add (4 cycles) is the critical path.  Both sit on
+//                      one sub-partition, which they share with nobody: each chain
+//                      leaves three of four issue slots free, so the two interleave.
+//                      The denominator's terms are w where the pair counts in the
+//                      column and +0 elsewhere.
+//   9 producer warps   (the three other sub-partitions; forming the terms is issue-bound,
+//                      ~370 instructions per batch) lane = inner row k of a 32-k batch.
+//                      Per batch a lane loads its row's 32 codes (32 contiguous
+//                      bytes), id[j,k] (coalesced) and the two non-gap masks, forms
+//                      w = 1 - id once, and for each of the 32 columns looks up
+//                      D[a_j][a_k] (one PRMT forms the table offset; the table has an
+//                      all-zero row/column for gaps), multiplies by w and stores both
+//                      terms to its ring slot in shared memory ([column][k], so the
+//                      consumers read vectors).  One slot per producer: batch g goes
+//                      to slot g % 9.
 // Terms of pairs the reference skips are exact +0.
 // A single warp can start one shared-memory load every ~4 cycles, which is what
 // limited the first version of this kernel (one warp, LDS.64 + two FADDs per row:
 // 10.6 cycles per row); hence the vector loads and one chain per warp.
 // Slots are handed over with mbarriers (full: one arrival; empty: two).
 // ---------------------------------------------------------------------------
-constexpr int SIM2_NPROD = 6;
-constexpr int SIM2_MAX_SLOTS = 12;
+constexpr int SIM2_NPROD = 9;
+constexpr int SIM2_MAX_SLOTS = 9;
 constexpr int SIM2_CS = 68;                          // floats per column of a slot: [column][num 32 | den 32 | pad 4],
                                                      // 8 lanes x LDS.128 cover the 32 banks (68 % 32 == 4)
 constexpr int SIM2_SLOT_WORDS = 32 * SIM2_CS;
@@ -334,8 +338,8 @@ __global__ void __launch_bounds__(SIM2_THREADS, 2) k_similarity2(const Sim2Param
 
     // When more groups than SMs are launched two CTAs share an SM: put their consumer
     // warps on different sub-partitions (warp id % 4).
-    const int cn = (2 * (blockIdx.x / max(p.num_sms, 1))) & 3;  // numerator's sub-partition
-    const int cd = cn + 1;                                      // denominator's
+    const int cn = (2 * (blockIdx.x / max(p.num_sms, 1))) & 3;  // the consumers' sub-partition:
+    const int cd = cn + 4;                                      // numerator warp cn, denominator warp cn + 4
     const int sp = warp & 3;
     const uint8_t *gc = p.codesT + (size_t)group * p.npad * 32;
 
@@ -349,13 +353,12 @@ __global__ void __launch_bounds__(SIM2_THREADS, 2) k_similarity2(const Sim2Param
         const float acc = sim2_consume(W, p.nbatches[group], lane, warp == cn ? 0 : SIM2_KB, p.zero);
         const int col = group * 32 + lane;
         if (col < p.ncol && !p.col_skip[col]) (warp == cn ? p.num_out : p.den_out)[col] = acc;
-    } else if (sp != cn && sp != cd) {
+    } else if (sp != cn) {
         // ------------------------------ producers -----------------------------
-        // producer index 0..5: the six warps of the two sub-partitions without a consumer
-        // (the other warps of the consumers' sub-partitions exit: a consumer shares its
-        // issue slots with nobody)
+        // producer index 0..8: the nine warps of the three sub-partitions without a consumer
+        // (the third warp of the consumers' sub-partition exits)
         int pi = 0;
-        for (int w = 0; w < warp; w++) pi += ((w & 3) != cn && (w & 3) != cd);
+        for (int w = 0; w < warp; w++) pi += (w & 3) != cn;
         constexpr int spp = SIM2_MAX_SLOTS / SIM2_NPROD;  // slots per producer (p.slots == SIM2_MAX_SLOTS)
         const int nwords = p.npad >> 5;
         const uint32_t *skipw = p.skipbits + (size_t)group * nwords;
@@ -513,7 +516,7 @@ cudaError_t launch_similarity(const uint8_t *codesT, int nseq, int npad, int nco
     p.group_begin = group_begin;
     p.num_sms = num_sms;
     const int ngroups = group_end - group_begin;
-    p.slots = SIM2_MAX_SLOTS;  // 110 KB: two CTAs fit an SM when there are more groups than SMs
+    p.slots = SIM2_MAX_SLOTS;  // 85 KB: two CTAs fit an SM when there are more groups than SMs
     const size_t smem = sim2_smem_bytes(p.slots);
     cudaError_t e = cudaFuncSetAttribute(k_similarity2, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
