@@ -159,6 +159,15 @@ int tcu_identity_row_blocks(int kept_rows);
 /* Work (pair-matrix tiles) in row-blocks < block: lets a driver cut bands of equal work. */
 long long tcu_identity_tiles_before(int kept_rows, int block);
 
+/* The order in which a launch over row-blocks [block_begin, block_end) visits its tiles
+ * (tile indices tcu_identity_tiles_before(begin) .. tiles_before(end) - 1): row-block and
+ * 64-row column block of one tile.  Groups of 8 row-blocks share a column block before the
+ * next one is touched (L2 reuse of the operand); exposed so that the order -- a bijection
+ * onto {(I, j) : begin <= I < end, 2 I <= j < ceil(kept_rows / 64)} -- can be checked on the
+ * host.  No reference counterpart (template.h:395-441 walks pairs row by row). */
+int tcu_identity_tile(int kept_rows, int block_begin, int block_end, long long tile,
+                      int *row_block, int *col_block64);
+
 /* Packed-array offset of the first pair whose first row is i (kept-index space). */
 size_t tcu_identity_row_offset(int kept_rows, int i);
 

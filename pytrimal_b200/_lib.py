@@ -74,6 +74,7 @@ PROTOTYPES = {
     "tcu_identity_band": (C.c_int, [_h, _i32p, _i32p, C.c_uint8, C.c_int, C.c_int, _f32p]),
     "tcu_identity_band_rows": (C.c_int, []),
     "tcu_identity_row_blocks": (C.c_int, [C.c_int]),
+    "tcu_identity_tile": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_longlong, _i32p, _i32p]),
     "tcu_identity_tiles_before": (C.c_longlong, [C.c_int, C.c_int]),
     "tcu_identity_row_offset": (C.c_size_t, [C.c_int, C.c_int]),
     "tcu_identity_prepare": (C.c_int, [_h, _i32p, _i32p, C.c_uint8, _i32p]),

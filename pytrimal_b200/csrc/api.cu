@@ -801,6 +801,18 @@ extern "C" long long tcu_identity_tiles_before(int kept_rows, int block)
     return tiles_before2(std::max(0, std::min(block, nsb)), nb);
 }
 
+extern "C" int tcu_identity_tile(int kept_rows, int block_begin, int block_end, long long tile,
+                                 int *row_block, int *col_block64)
+{
+    const int nb = (kept_rows + RB - 1) / RB, nsb = (kept_rows + IB - 1) / IB;
+    if (!row_block || !col_block64 || block_begin < 0 || block_end > nsb || block_begin >= block_end ||
+        tile < tiles_before2(block_begin, nb) || tile >= tiles_before2(block_end, nb))
+        return fail(TCU_ERR_INVALID, "tile %lld outside row-blocks [%d, %d) of %d kept rows", tile,
+                    block_begin, block_end, kept_rows);
+    tile_to_blocks2(tile, nb, block_begin, block_end, *row_block, *col_block64);
+    return TCU_OK;
+}
+
 extern "C" size_t tcu_identity_row_offset(int kept_rows, int i)
 {
     const size_t n = (size_t)std::max(kept_rows, 0);

@@ -203,6 +203,26 @@ def test_similarity(gpu, port, n, L, cut):
     np.testing.assert_allclose(mdk, omdk, rtol=1e-5, atol=0)   # BASELINE.json tolerance
 
 
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 6, 7, 8, 9, 33, 34, 66])
+def test_similarity_few_batches(gpu, port, n):
+    """One to a handful of 32-row batches per column group (the consumers' peeled last
+    batches, odd and even counts), with all-gap rows and an all-gap group in between."""
+    rng = np.random.default_rng(900 + n)
+    L = 100
+    m = random_msa(rng, n, L, gap=0.45)
+    m[:, 32:64] = ord("-")                       # a column group without any batch
+    m[n // 2, 64:96] = ord("-")                  # a row the third group skips
+    smx = gpu.SimilarityMatrix.aa()
+    oi = port.identity(m, X)
+    omdk, onum, oden = port.similarity(m, X, oi, None, L, smx.distances, smx.vhash)
+    with gpu.DeviceAlignment(m) as d:
+        d.identity(X, keep_on_device=True)
+        mdk, num, den = d.similarity(smx, gaps=None, indet=X)
+    assert (bits(num) == bits(onum)).all()
+    assert (bits(den) == bits(oden)).all()
+    assert (bits(mdk) == bits(omdk)).all()
+
+
 def test_similarity_gap_cut_uses_residue_count(gpu, port):
     """threshold = 0.8 * numberOfResidues (columns!), SURVEY F4."""
     rng = np.random.default_rng(3)

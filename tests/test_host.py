@@ -61,6 +61,36 @@ def test_row_offset_and_blocks_match_python(lib):
     assert lib.tcu_identity_band_rows() == sharding.ROW_BLOCK
 
 
+def test_identity_tile_order_is_a_bijection(lib):
+    """tcu_identity_tile: the grouped order in which a K1 launch over row-blocks [b0, b1) visits
+    the pair matrix covers every tile (I, j >= 2 I) of those row-blocks exactly once, and the
+    tiles that share a 64-row column block inside a group of 8 row-blocks are consecutive."""
+    import ctypes as C
+    bi, bj = C.c_int(), C.c_int()
+
+    def order(nk, b0, b1):
+        t0, t1 = lib.tcu_identity_tiles_before(nk, b0), lib.tcu_identity_tiles_before(nk, b1)
+        out = []
+        for t in range(t0, t1):
+            assert lib.tcu_identity_tile(nk, b0, b1, t, C.byref(bi), C.byref(bj)) == 0
+            out.append((bi.value, bj.value))
+        return out
+
+    for nk in [1, 64, 65, 128, 129, 700, 1100, 2500, 5000]:
+        nsb, nb = lib.tcu_identity_row_blocks(nk), (nk + 63) // 64
+        for b0, b1 in {(0, nsb), (0, max(1, nsb // 2)), (nsb // 2, nsb), (min(3, nsb - 1), nsb)}:
+            if b0 >= b1:
+                continue
+            got = order(nk, b0, b1)
+            want = {(I, j) for I in range(b0, b1) for j in range(2 * I, nb)}
+            assert len(got) == len(set(got)) and set(got) == want, (nk, b0, b1)
+            # inside a group, a column block is finished before the next one starts
+            for g0 in range(b0, b1, 8):
+                cols = [j for I, j in got if g0 <= I < min(g0 + 8, b1)]
+                assert cols == sorted(cols), (nk, b0, b1, g0)
+    assert lib.tcu_identity_tile(700, 0, 2, 10**9, C.byref(bi), C.byref(bj)) != 0   # out of range
+
+
 def test_band_partition_balanced_and_covering():
     from pytrimal_b200.sharding import band_partition, band_slice, row_blocks, tiles_before
     for n in [100, 4097, 50000, 100000]:

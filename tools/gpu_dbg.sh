@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 400 python -m pytest tests -m gpu -x -q -k "simil or smoke or golden or dropin or pytrimal" 2>&1 | tail -2
-timeout 300 python tools/bench_stats.py --only similarity --workloads C2,C3 --repeats 2 | tee gpurun_out/stats_sim_r01k12.log | cut -c1-330
+( time timeout 900 python -m pytest tests -m gpu -x -q --timeout=150 ) > gpurun_out/pytest_gpu_r01k.log 2>&1; tail -5 gpurun_out/pytest_gpu_r01k.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
