@@ -280,20 +280,29 @@ __device__ __forceinline__ float sim2_consume(Sim2Walk W, unsigned long long bto
     // invariant at the top of a batch: its terms are in registers (X), the barrier of the
     // next batch (if any) has been seen complete
     auto iter = [&](const Sim2NumBatch &X, Sim2NumBatch &Y) {   // batches b+1 and b+2 exist
-        const uint32_t ready2 = mbar_try_wait(&W.full[W.s2], W.p2);
+        uint64_t *const f2 = &W.full[W.s2], *const e0 = &W.empty[W.s0];
+        const uint32_t par2 = W.p2;
+        const uint32_t ready2 = mbar_try_wait(f2, par2);
         acc = sim2_num_add<0, 1>(acc, X);
         sim2_num_load(Y, W.ring, W.s1, lane, __float_as_uint(acc) & zero);
+        W.rotate();  // here, not after the arrive: integer work in the shadow of the chain
         acc = sim2_num_add<1, 32>(acc, X);
-        if (!ready2) mbar_wait(&W.full[W.s2], W.p2);
+        if (!ready2) mbar_wait(f2, par2);
         __syncwarp();
-        if (lane0) mbar_arrive(&W.empty[W.s0]);
-        W.rotate();
+        if (lane0) mbar_arrive(e0);
     };
-    unsigned long long remaining = btot;
-    while (remaining > 3) {
-        iter(A, B);
-        iter(B, A);
-        remaining -= 2;
+    // pairs of batches with two more behind them: floor((btot - 2) / 2); a 32-bit counter in
+    // the loop (a 64-bit compare chain per iteration is not hidden by anything)
+    unsigned long long pairs = btot > 3 ? (btot - 2) / 2 : 0;
+    unsigned long long remaining = btot - 2 * pairs;
+    while (pairs) {
+        const uint32_t chunk = (uint32_t)min(pairs, 1ull << 30);
+        pairs -= chunk;
+#pragma unroll 1
+        for (uint32_t i = 0; i < chunk; i++) {
+            iter(A, B);
+            iter(B, A);
+        }
     }
     auto tail = [&](const Sim2NumBatch &X, Sim2NumBatch &Y) {
         if (remaining > 1) sim2_num_load(Y, W.ring, W.s1, lane, 0);
