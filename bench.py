@@ -179,6 +179,38 @@ def cpu_baseline(workload, L, seed, n_full):
                       "Identity::calculateSeqIdentity (AVX2) + the greedy walk"}
 
 
+def similarity_line(pb, CONFIGS, synthetic_msa):
+    """The other half of BASELINE.json's metric (identity + similarity): one pass of
+    Similarity::calculateVectors over the C3 alignment (10 000 x 5 000, BASELINE configs[2])
+    through the host-buffer C ABI, identity matrix resident on the device.  Reported beside
+    the headline, not folded into `value`: the statistic is bound by the sequential fp32 add
+    chain the reference's order mandates, so no roofline fraction applies."""
+    import numpy as np
+    n, L, seed = CONFIGS["C3"]
+    m = synthetic_msa(n, L, seed)
+    X = ord("X")
+    smx = pb.SimilarityMatrix.aa()
+    P = n * (n - 1) // 2
+    with pb.DeviceAlignment(m) as d:
+        g, _, _ = d.gaps()
+        d.identity(X, keep_on_device=True)
+        best_k, best_w = 1e30, 1e30
+        for _ in range(2):
+            t0 = time.perf_counter()
+            d.similarity(smx, gaps=g, indet=X)
+            best_w = min(best_w, time.perf_counter() - t0)
+            best_k = min(best_k, d.timings["kernel_ms"])
+    return {"workload": f"C3: per-column similarity {n}x{L} (AutomaticTrimmer strict*), identity resident in HBM",
+            "value": P * L / (best_k * 1e-3), "unit": UNIT, "kernel": "tcu::k_similarity2",
+            "kernel_ms": best_k, "call_ms_host_buffers": best_w * 1e3,
+            "ns_per_chain_step": best_k * 1e6 / P,
+            "columns_cut_by_gap_rule": int((g.astype(np.float32) >= np.float32(0.8) * np.float32(L)).sum()),
+            "roofline": None,
+            "note": "latency-bound: one dependent fp32 add per pair and column in the reference's "
+                    "order (floor 4 cycles per step); bit-identical to the reference"}
+
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -189,6 +221,7 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="debug: use only the first ROWS rows")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-similarity", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -428,6 +461,11 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.workload, L, seed, n)
+        if world == 1 and not args.rows and not args.no_similarity and not args.no_cpu_baseline:
+            try:
+                line["similarity"] = similarity_line(pb, CONFIGS, synthetic_msa)
+            except Exception as exc:  # never lose the headline line over the secondary figure
+                line["similarity"] = {"error": repr(exc)}
         print(json.dumps(line), flush=True)
 
     dev.close()
