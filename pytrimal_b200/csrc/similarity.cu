@@ -31,10 +31,10 @@ namespace tcu {
 // Output layout: codesT[group][row][32] -- the 32 columns of one column group
 // are contiguous per row, rows padded to a multiple of 32 -- holding 4 * code
 // (the byte offset of the code's entry in a table row); the gap class, skipped
-// columns and all padding hold SIM2_GAP8 = 4 * 31.
+// columns and all padding hold SIM2_GAPCODE = 4 * 31.
 // ---------------------------------------------------------------------------
 constexpr uint32_t SIM2_GAPIDX = 31;
-constexpr uint32_t SIM2_GAP8 = 4 * SIM2_GAPIDX;
+constexpr uint32_t SIM2_GAPCODE = 4 * SIM2_GAPIDX;
 
 __global__ void __launch_bounds__(256) k_sim_codes(const uint8_t *__restrict__ raw, int nseq,
                                                    int ncol, size_t pitch, int npad,
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) k_sim_codes(const uint8_t *__restrict__ r
             for (int b = 0; b < 4; b++) {
                 const int col = g * 16 + q * 4 + b;
                 const uint32_t byte = (w[q] >> (8 * b)) & 0xFF;
-                uint32_t out = SIM2_GAP8;
+                uint32_t out = SIM2_GAPCODE;
                 if (col < ncol && !col_skip[col]) {
                     const uint32_t code = lut[byte];
                     if (code == SIM_INCORRECT || code == SIM_UNDEFINED) {
@@ -87,7 +87,7 @@ cudaError_t launch_sim_codes(const uint8_t *raw, int nseq, int ncol, size_t pitc
 {
     if (nseq == 0 || ncol == 0) return cudaSuccess;
     // padding rows (and nothing else survives the kernel below) are gaps
-    cudaError_t e = cudaMemsetAsync(codesT, (int)SIM2_GAP8, (size_t)(pitch >> 5) * npad * 32, stream);
+    cudaError_t e = cudaMemsetAsync(codesT, (int)SIM2_GAPCODE, (size_t)(pitch >> 5) * npad * 32, stream);
     if (e != cudaSuccess) return e;
     const long long total = (long long)nseq * (long long)(pitch >> 4);
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
