@@ -53,10 +53,28 @@ typedef enum tcu_status {
     TCU_ERR_NCCL = -8              /* NCCL missing or a collective failed (*_all calls) */
 } tcu_status;
 
-typedef struct tcu_msa tcu_msa; /* opaque: one alignment resident on one GPU */
+typedef struct tcu_msa tcu_msa; /* opaque: one alignment resident on one GPU (or replicated
+                                  over the devices of the configured set, see below) */
 
 /* Number of usable sm_100 devices (0 when there is no driver or no GPU). */
 int tcu_device_count(void);
+
+/*
+ * Devices used by handles created with device = TCU_DEVICE_AUTO.  The reference has one compute
+ * platform per process and no device notion (statistics::Manager::platform,
+ * include/Statistics/Manager.h:51-68); a single-process caller such as pytrimal's
+ * platform="cuda" reaches several GPUs by naming them here -- or in the environment variable
+ * TRIMAL_CUDA_DEVICES ("all" or e.g. "0,1,2,3"), read on first use.  count = 0 goes back to
+ * the environment / device 0.  With more than one device an AUTO handle is replicated: every
+ * device uploads 1/N of the rows over its own PCIe link and the shards are exchanged over
+ * NVLink; tcu_identity / tcu_representatives split the pair matrix into row-block bands,
+ * tcu_gaps / tcu_spurious split the rows; every other call runs on the first device.  Results
+ * are bit-identical to the single-device ones.  Alignments below 4 MB stay on one device.
+ */
+#define TCU_DEVICE_AUTO (-1)
+int tcu_set_devices(const int *devices, int count);
+int tcu_get_devices(int *devices, int max); /* returns the size of the set */
+int tcu_msa_device_count(const tcu_msa *msa); /* devices this handle is replicated on */
 
 /* Message of the last error raised on this thread ("" if none). */
 const char *tcu_last_error(void);
@@ -269,9 +287,12 @@ int tcu_cluster_order(const int *lengths, int nseq, int *order);
 
 /*
  * Cleaner::calculateRepresentativeSeq (Cleaner.cpp:1398-1466) in one call for an
- * alignment with every row kept: identity matrix over the kept columns (save_res;
- * left resident on the device), sequence lengths, visiting order, greedy clustering
- * at `threshold` (maximumIdent).  clusters: up to nseq ints (may be NULL).
+ * alignment with every row kept: sequence lengths, visiting order, and the greedy
+ * clustering at `threshold` (maximumIdent) over the identities of the kept columns
+ * (save_res).  The walk only compares identities with the threshold (:1435-1440), so the
+ * identity kernel emits one bit per pair instead of the ratios: no float matrix is left on
+ * the device (tcu_identity_resident() is 0 afterwards) and the call is not limited by the
+ * 4*P bytes of the packed array.  clusters: up to nseq ints (may be NULL).
  */
 int tcu_representatives(tcu_msa *msa, const int *save_res, uint8_t indet, float threshold,
                         int *clusters, int *n_clusters);

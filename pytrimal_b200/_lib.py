@@ -63,6 +63,9 @@ PROTOTYPES = {
     "tcu_msa_create_strided": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int,
                                          C.POINTER(_h)]),
     "tcu_msa_destroy": (None, [_h]),
+    "tcu_set_devices": (C.c_int, [_i32p, C.c_int]),
+    "tcu_get_devices": (C.c_int, [_i32p, C.c_int]),
+    "tcu_msa_device_count": (C.c_int, [_h]),
     "tcu_release_cached_memory": (None, []),
     "tcu_msa_nseq": (C.c_int, [_h]),
     "tcu_msa_ncol": (C.c_int, [_h]),

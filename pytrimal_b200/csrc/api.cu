@@ -56,6 +56,42 @@ static int cuda_fail(cudaError_t e, const char *what)
     } while (0)
 
 extern "C" const char *tcu_last_error(void) { return g_last_error.c_str(); }
+
+// NVTX ranges around the entry points (the reference's StartTiming scopes):
+// libnvToolsExt is looked up at run time, a profiler that wants the ranges preloads it;
+// without it the calls cost one branch.
+namespace {
+struct NvtxApi {
+    int (*push)(const char *) = nullptr;
+    int (*pop)() = nullptr;
+    NvtxApi()
+    {
+        if (getenv("TRIMAL_CUDA_NVTX") == nullptr) return;
+        void *h = dlopen("libnvToolsExt.so.1", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnvToolsExt.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return;
+        push = (int (*)(const char *))dlsym(h, "nvtxRangePushA");
+        pop = (int (*)())dlsym(h, "nvtxRangePop");
+        if (!push || !pop) push = nullptr, pop = nullptr;
+    }
+};
+const NvtxApi &nvtx_api()
+{
+    static NvtxApi api;
+    return api;
+}
+struct NvtxRange {
+    bool on;
+    explicit NvtxRange(const char *name) : on(nvtx_api().push != nullptr)
+    {
+        if (on) nvtx_api().push(name);
+    }
+    ~NvtxRange()
+    {
+        if (on) nvtx_api().pop();
+    }
+};
+}  // namespace
 extern "C" const char *tcu_version(void) { return "trimal_cuda 0.1 (sm_100a)"; }
 
 // ---------------------------------------------------------------------------
@@ -254,9 +290,17 @@ struct tcu_msa {
     size_t ident_cap = 0;
     bool ident_full = false;  // unmasked rows: usable by tcu_similarity
 
+    // threshold bit matrix (slab layout, tcu_internal.cuh) of the clustering calls
+    uint32_t *d_bits = nullptr;
+    size_t bits_cap = 0;
+
     // generic scratch
     void *d_scratch = nullptr;
     size_t scratch_cap = 0;
+
+    // several GPUs in one process (tcu_set_devices / TRIMAL_CUDA_DEVICES): the handle the
+    // caller holds lives on the first device; one replica per further device hangs off it
+    std::vector<tcu_msa *> peers;
 
     cudaStream_t copy_stream = nullptr;       // D2H of finished sub-bands, overlapping the kernel
     std::vector<cudaEvent_t> band_done;       // one per sub-band (no timing)
@@ -513,19 +557,21 @@ static bool is_pinned_host(const void *p)
 // Page-locked source: ONE linear DMA of the whole strided block into scratch (a 2-D copy
 // would issue a descriptor per 1000-byte row), then a device kernel lays the rows out at
 // the device pitch and zero-fills the padding.
-static int upload_strided_pinned(tcu_msa *m, const uint8_t *data, size_t stride)
+static int upload_strided_pinned(tcu_msa *m, const uint8_t *data, size_t stride, int r0, int r1)
 {
     CK(cudaSetDevice(m->device));
-    const size_t bytes = (size_t)(m->nseq - 1) * stride + (size_t)m->ncol;
+    m->timings = tcu_timings{};
+    if (r1 <= r0) return TCU_OK;
+    const size_t bytes = (size_t)(r1 - r0 - 1) * stride + (size_t)m->ncol;
     int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, bytes);
     if (rc != TCU_OK) return rc;
     CK(cudaEventRecord(m->ev[0], m->stream));
-    CK(cudaMemcpyAsync(m->d_scratch, data, bytes, cudaMemcpyHostToDevice, m->stream));
-    CK(launch_repitch_rows((const uint8_t *)m->d_scratch, stride, m->nseq, m->ncol, m->d_raw,
-                           m->pitch, m->stream));
+    CK(cudaMemcpyAsync(m->d_scratch, data + (size_t)r0 * stride, bytes, cudaMemcpyHostToDevice,
+                       m->stream));
+    CK(launch_repitch_rows((const uint8_t *)m->d_scratch, stride, r1 - r0, m->ncol,
+                           m->d_raw + (size_t)r0 * m->pitch, m->pitch, m->stream));
     CK(cudaEventRecord(m->ev[1], m->stream));
     CK(cudaStreamSynchronize(m->stream));
-    m->timings = tcu_timings{};
     m->timings.h2d_ms = ev_ms(m->ev[0], m->ev[1]);
     m->timings.kernel_launches = 1;
     return TCU_OK;
@@ -533,16 +579,18 @@ static int upload_strided_pinned(tcu_msa *m, const uint8_t *data, size_t stride)
 
 // rows -> pinned staging (row pitch = device pitch, padding zero) -> device
 template <typename RowPtr>
-static int upload_rows(tcu_msa *m, RowPtr row_of)
+static int upload_rows(tcu_msa *m, RowPtr row_of, int row_begin, int row_end)
 {
     CK(cudaSetDevice(m->device));
     CK(cudaEventRecord(m->ev[0], m->stream));
     const size_t pitch = m->pitch;
     const size_t rows_per_stage = std::max<size_t>(1, STAGE_BYTES / pitch);
-    if (pitch > STAGE_BYTES) {
+    if (row_end <= row_begin) {
+    } else if (pitch > STAGE_BYTES) {
         // very long rows: copy row by row straight from caller memory
-        CK(cudaMemsetAsync(m->d_raw, 0, (size_t)m->nseq * pitch, m->stream));
-        for (int r = 0; r < m->nseq; r++)
+        CK(cudaMemsetAsync(m->d_raw + (size_t)row_begin * pitch, 0,
+                           (size_t)(row_end - row_begin) * pitch, m->stream));
+        for (int r = row_begin; r < row_end; r++)
             CK(cudaMemcpyAsync(m->d_raw + (size_t)r * pitch, row_of(r), m->ncol,
                                cudaMemcpyHostToDevice, m->stream));
     } else {
@@ -556,8 +604,9 @@ static int upload_rows(tcu_msa *m, RowPtr row_of)
         }
         int which = 0;
         int rc = TCU_OK;
-        for (size_t r0 = 0; r0 < (size_t)m->nseq && rc == TCU_OK; r0 += rows_per_stage) {
-            const size_t nr = std::min(rows_per_stage, (size_t)m->nseq - r0);
+        for (size_t r0 = (size_t)row_begin; r0 < (size_t)row_end && rc == TCU_OK;
+             r0 += rows_per_stage) {
+            const size_t nr = std::min(rows_per_stage, (size_t)row_end - r0);
             uint8_t *s = (uint8_t *)stage[which];
             if (used[which] && cudaEventSynchronize(done[which]) != cudaSuccess) {
                 rc = cuda_fail(cudaGetLastError(), "staging wait");
@@ -607,21 +656,6 @@ static int upload_rows(tcu_msa *m, RowPtr row_of)
     return TCU_OK;
 }
 
-extern "C" int tcu_msa_create(const char *const *rows, int nseq, int ncol, int device, tcu_msa **out)
-{
-    if (nseq > 0 && !rows) return fail(TCU_ERR_INVALID, "rows is NULL");
-    tcu_msa *m = nullptr;
-    int rc = msa_alloc(nseq, ncol, device, &m);
-    if (rc != TCU_OK) return rc;
-    rc = upload_rows(m, [&](int r) { return (const void *)rows[r]; });
-    if (rc != TCU_OK) {
-        tcu_msa_destroy(m);
-        return rc;
-    }
-    *out = m;
-    return TCU_OK;
-}
-
 static double now_ms()
 {
     timespec ts;
@@ -629,39 +663,264 @@ static double now_ms()
     return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
+// ---------------------------------------------------------------------------
+// Device set.  The reference has one compute platform per process and no notion of a
+// device; a caller that wants several GPUs behind the same single-process API (pytrimal's
+// platform="cuda") names them once -- tcu_set_devices() or the environment variable
+// TRIMAL_CUDA_DEVICES ("all" or a comma separated list) -- and creates its handles with
+// device = TCU_DEVICE_AUTO.
+// ---------------------------------------------------------------------------
+namespace {
+std::mutex g_devset_mutex;
+std::vector<int> g_devset;
+bool g_devset_ready = false;
+
+std::vector<int> usable_devices()
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    std::vector<int> v;
+    for (int d = 0; d < n; d++)
+        if (device_usable(d, nullptr)) v.push_back(d);
+    return v;
+}
+
+std::vector<int> configured_devices()
+{
+    std::lock_guard<std::mutex> lk(g_devset_mutex);
+    if (!g_devset_ready) {
+        g_devset_ready = true;
+        g_devset.clear();
+        const char *e = getenv("TRIMAL_CUDA_DEVICES");
+        if (e && *e) {
+            if (!strcmp(e, "all")) {
+                g_devset = usable_devices();
+            } else {
+                for (const char *p = e; *p;) {
+                    char *end = nullptr;
+                    const long d = strtol(p, &end, 10);
+                    if (end == p) break;
+                    if (d >= 0 && device_usable((int)d, nullptr) &&
+                        std::find(g_devset.begin(), g_devset.end(), (int)d) == g_devset.end())
+                        g_devset.push_back((int)d);
+                    p = *end == ',' ? end + 1 : end;
+                    if (*end && *end != ',') break;
+                }
+            }
+        }
+        if (g_devset.empty()) g_devset.push_back(0);
+    }
+    return g_devset;
+}
+
+// alignments smaller than this stay on the first device of the set (threads and peer copies
+// cost more than they save); TRIMAL_CUDA_MULTI_MIN_BYTES overrides (tests)
+size_t multi_min_bytes()
+{
+    const char *e = getenv("TRIMAL_CUDA_MULTI_MIN_BYTES");
+    return e && *e ? (size_t)strtoull(e, nullptr, 10) : (size_t)(4u << 20);
+}
+}  // namespace
+
+extern "C" int tcu_set_devices(const int *devices, int count)
+{
+    if (count < 0 || (count > 0 && !devices)) return fail(TCU_ERR_INVALID, "bad device list");
+    std::vector<int> v;
+    for (int k = 0; k < count; k++) {
+        if (!device_usable(devices[k], nullptr))
+            return fail(TCU_ERR_NO_DEVICE, "device %d is not an sm_100 GPU", devices[k]);
+        if (std::find(v.begin(), v.end(), devices[k]) != v.end())
+            return fail(TCU_ERR_INVALID, "device %d listed twice", devices[k]);
+        v.push_back(devices[k]);
+    }
+    std::lock_guard<std::mutex> lk(g_devset_mutex);
+    if (count == 0) {
+        g_devset_ready = false;  // back to TRIMAL_CUDA_DEVICES / device 0
+    } else {
+        g_devset = v;
+        g_devset_ready = true;
+    }
+    return TCU_OK;
+}
+
+extern "C" int tcu_get_devices(int *devices, int max)
+{
+    const std::vector<int> v = configured_devices();
+    for (int k = 0; k < (int)v.size() && k < max; k++)
+        if (devices) devices[k] = v[k];
+    return (int)v.size();
+}
+
+extern "C" int tcu_msa_device_count(const tcu_msa *m) { return m ? 1 + (int)m->peers.size() : 0; }
+
+// every replica of a handle, the caller's own first
+static std::vector<tcu_msa *> replicas(tcu_msa *m)
+{
+    std::vector<tcu_msa *> v{m};
+    v.insert(v.end(), m->peers.begin(), m->peers.end());
+    return v;
+}
+
+// f(replica, index) on every replica at once, one host thread per further device (the calls
+// block on their streams); the first failure wins and its message is carried over from the
+// worker thread (error strings are thread-local).
+template <class F>
+static int for_each_replica(tcu_msa *m, F f)
+{
+    std::vector<tcu_msa *> hs = replicas(m);
+    if (hs.size() == 1) return f(hs[0], 0);
+    std::vector<int> rcs(hs.size(), TCU_OK);
+    std::vector<std::string> errs(hs.size());
+    auto run = [&](int k) {
+        rcs[k] = f(hs[k], k);
+        if (rcs[k] != TCU_OK) errs[k] = g_last_error;
+    };
+    std::vector<std::thread> pool;
+    size_t started = 1;
+    try {
+        for (; started < hs.size(); started++) pool.emplace_back(run, (int)started);
+    } catch (...) {  // no thread to be had: the rest runs here, nothing may escape the C ABI
+    }
+    run(0);
+    for (size_t k = started; k < hs.size(); k++) run((int)k);
+    for (auto &t : pool) t.join();
+    for (size_t k = 0; k < hs.size(); k++)
+        if (rcs[k] != TCU_OK) return fail(rcs[k], "%s", errs[k].c_str());
+    return TCU_OK;
+}
+
+// direct access between every pair of devices of a set (NVLink / NVSwitch); copies between
+// devices without it still work, staged by the driver
+static void enable_peer_access(const std::vector<int> &devs)
+{
+    for (int a : devs) {
+        if (cudaSetDevice(a) != cudaSuccess) continue;
+        for (int b : devs) {
+            if (a == b) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, a, b) == cudaSuccess && can) cudaDeviceEnablePeerAccess(b, 0);
+        }
+    }
+    cudaGetLastError();  // cudaErrorPeerAccessAlreadyEnabled
+}
+
+// the caller's rows: separate row pointers, or one strided block (page-locked or not)
+struct HostRows {
+    const char *const *rows = nullptr;
+    const uint8_t *data = nullptr;
+    size_t stride = 0;
+    bool pinned = false;
+};
+
+static int upload_range(tcu_msa *m, const HostRows &h, int r0, int r1)
+{
+    if (h.rows) return upload_rows(m, [&](int r) { return (const void *)h.rows[r]; }, r0, r1);
+    if (h.pinned) return upload_strided_pinned(m, h.data, h.stride, r0, r1);
+    return upload_rows(m, [&](int r) { return (const void *)(h.data + (size_t)r * h.stride); }, r0,
+                       r1);
+}
+
+extern "C" void tcu_msa_destroy(tcu_msa *m);
+
+static int msa_create_any(const HostRows &h, int nseq, int ncol, int device, tcu_msa **out)
+{
+    if (!out) return fail(TCU_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    std::vector<int> devs;
+    if (device == TCU_DEVICE_AUTO) {
+        devs = configured_devices();
+        if ((size_t)std::max(nseq, 0) * (size_t)std::max(ncol, 0) < multi_min_bytes()) devs.resize(1);
+    } else {
+        devs.push_back(device);
+    }
+    static const bool trace = getenv("TCU_TRACE") != nullptr;
+    const double t0 = trace ? now_ms() : 0;
+    tcu_msa *m = nullptr;
+    int rc = msa_alloc(nseq, ncol, devs[0], &m);
+    if (rc != TCU_OK) return rc;
+    for (size_t k = 1; k < devs.size() && rc == TCU_OK; k++) {
+        tcu_msa *p = nullptr;
+        rc = msa_alloc(nseq, ncol, devs[k], &p);
+        if (rc == TCU_OK) m->peers.push_back(p);
+    }
+    const double t1 = trace ? now_ms() : 0;
+    if (rc == TCU_OK && devs.size() == 1) {
+        rc = upload_range(m, h, 0, nseq);
+    } else if (rc == TCU_OK) {
+        // every device takes 1/N of the rows over its own PCIe link, at their place in its
+        // copy of the matrix; the shards are then exchanged device to device
+        enable_peer_access(devs);
+        const int world = (int)devs.size();
+        rc = for_each_replica(m, [&](tcu_msa *r, int k) {
+            int r0, r1;
+            tcu_shard_range(nseq, 1, k, world, &r0, &r1);
+            return upload_range(r, h, r0, r1);
+        });
+        if (rc == TCU_OK) {
+            std::vector<tcu_msa *> hs = replicas(m);
+            cudaError_t e = cudaSuccess;
+            for (int k = 0; k < world && e == cudaSuccess; k++) {
+                e = cudaSetDevice(hs[k]->device);
+                for (int o = 0; o < world && e == cudaSuccess; o++) {
+                    int r0, r1;
+                    tcu_shard_range(nseq, 1, o, world, &r0, &r1);
+                    if (o == k || r1 <= r0) continue;
+                    e = cudaMemcpyPeerAsync(hs[k]->d_raw + (size_t)r0 * m->pitch, hs[k]->device,
+                                            hs[o]->d_raw + (size_t)r0 * m->pitch, hs[o]->device,
+                                            (size_t)(r1 - r0) * m->pitch, hs[k]->stream);
+                }
+            }
+            for (int k = 0; k < world; k++) {
+                cudaSetDevice(hs[k]->device);
+                cudaError_t e2 = cudaStreamSynchronize(hs[k]->stream);
+                if (e == cudaSuccess) e = e2;
+            }
+            if (e != cudaSuccess) rc = cuda_fail(e, "row exchange between devices");
+        }
+    }
+    if (trace)
+        fprintf(stderr, "[tcu] create on %zu device(s): alloc %.2f ms, upload(%s) %.2f ms (h2d events %.2f)\n",
+                devs.size(), t1 - t0, h.rows ? "rows" : (h.pinned ? "pinned" : "staged"),
+                now_ms() - t1, rc == TCU_OK ? m->timings.h2d_ms : -1.f);
+    if (rc != TCU_OK) {
+        const std::string keep = g_last_error;
+        tcu_msa_destroy(m);
+        g_last_error = keep;
+        return rc;
+    }
+    cudaSetDevice(m->device);
+    *out = m;
+    return TCU_OK;
+}
+
+extern "C" int tcu_msa_create(const char *const *rows, int nseq, int ncol, int device, tcu_msa **out)
+{
+    if (nseq > 0 && !rows) return fail(TCU_ERR_INVALID, "rows is NULL");
+    HostRows h;
+    h.rows = rows;
+    return msa_create_any(h, nseq, ncol, device, out);
+}
+
 extern "C" int tcu_msa_create_strided(const uint8_t *data, int nseq, int ncol, size_t stride,
                                       int device, tcu_msa **out)
 {
     if (nseq > 0 && ncol > 0 && !data) return fail(TCU_ERR_INVALID, "data is NULL");
     if (stride < (size_t)ncol) return fail(TCU_ERR_INVALID, "stride smaller than ncol");
-    static const bool trace = getenv("TCU_TRACE") != nullptr;
-    const double t0 = trace ? now_ms() : 0;
-    tcu_msa *m = nullptr;
-    int rc = msa_alloc(nseq, ncol, device, &m);
-    if (rc != TCU_OK) return rc;
-    const double t1 = trace ? now_ms() : 0;
-    const bool pinned =
-        nseq > 0 && ncol > 0 && stride <= 2 * (size_t)ncol + 64 && is_pinned_host(data);
-    const double t2 = trace ? now_ms() : 0;
-    if (pinned)
-        rc = upload_strided_pinned(m, data, stride);
-    else
-        rc = upload_rows(m, [&](int r) { return (const void *)(data + (size_t)r * stride); });
-    if (trace)
-        fprintf(stderr, "[tcu] create: alloc %.2f ms, attr %.2f ms, upload(%s) %.2f ms (h2d events %.2f)\n",
-                t1 - t0, t2 - t1, pinned ? "pinned" : "staged", now_ms() - t2,
-                rc == TCU_OK ? m->timings.h2d_ms : -1.f);
-    if (rc != TCU_OK) {
-        tcu_msa_destroy(m);
-        return rc;
-    }
-    *out = m;
-    return TCU_OK;
+    HostRows h;
+    h.data = data;
+    h.stride = stride;
+    h.pinned = nseq > 0 && ncol > 0 && stride <= 2 * (size_t)ncol + 64 && is_pinned_host(data);
+    return msa_create_any(h, nseq, ncol, device, out);
 }
 
 extern "C" void tcu_msa_destroy(tcu_msa *m)
 {
     if (!m) return;
+    for (tcu_msa *p : m->peers) tcu_msa_destroy(p);
+    m->peers.clear();
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     if (m->copy_stream) cudaStreamSynchronize(m->copy_stream);
@@ -669,6 +928,7 @@ extern "C" void tcu_msa_destroy(tcu_msa *m)
     dev_cache_give(m->device, m->d_planes, m->planes_cap);
     dev_cache_give(m->device, m->d_gbytes, m->gbytes_cap);
     dev_cache_give(m->device, m->d_ident, m->ident_cap);
+    dev_cache_give(m->device, m->d_bits, m->bits_cap);
     dev_cache_give(m->device, m->d_scratch, m->scratch_cap);
     cudaFree(m->d_kept_rows);
     cudaFree(m->d_col_drop);
@@ -721,8 +981,10 @@ static int download(tcu_msa *m, void *dst, const void *d_src, size_t bytes)
 // ---------------------------------------------------------------------------
 // K3 gaps
 // ---------------------------------------------------------------------------
-static int gaps_impl(tcu_msa *m, tcu_comm *comm, const int *save_seq, int *gaps_in_column,
-                     int *num_cols_with_gaps, int *max_gaps)
+// comm: this rank's share of the rows, all-reduced on the device.  Without comm: the share
+// (srank of sworld) only, no reduction -- 0 of 1 is the whole statistic.
+static int gaps_impl(tcu_msa *m, tcu_comm *comm, int srank, int sworld, const int *save_seq,
+                     int *gaps_in_column, int *num_cols_with_gaps, int *max_gaps)
 {
     if (!m || !gaps_in_column) return fail(TCU_ERR_INVALID, "NULL argument");
     CK(cudaSetDevice(m->device));
@@ -750,9 +1012,10 @@ static int gaps_impl(tcu_msa *m, tcu_comm *comm, const int *save_seq, int *gaps_
     // summed across GPUs (exact in any order)
     int r0 = 0, r1 = n;
     if (comm) tcu_shard_range(n, 1, comm->rank, comm->world, &r0, &r1);
+    else tcu_shard_range(n, 1, srank, sworld, &r0, &r1);
     CK(launch_column_counts(m->d_raw + (size_t)r0 * m->pitch, r1 - r0, L, m->pitch,
-                            d_drop ? d_drop + r0 : nullptr, '-', '-', d_cnt, nullptr, m->num_sms,
-                            m->stream));
+                            d_drop ? d_drop + r0 : nullptr, '-', '-', d_cnt, nullptr, nullptr, nullptr,
+                            m->num_sms, m->stream));
     CK(cudaEventRecord(m->ev[2], m->stream));
     if (comm) {
         rc = comm_allreduce_i32(comm, d_cnt, (size_t)L, m->stream);
@@ -779,14 +1042,34 @@ static int gaps_impl(tcu_msa *m, tcu_comm *comm, const int *save_seq, int *gaps_
 extern "C" int tcu_gaps(tcu_msa *m, const int *save_seq, int *gaps_in_column,
                         int *num_cols_with_gaps, int *max_gaps)
 {
-    return gaps_impl(m, nullptr, save_seq, gaps_in_column, num_cols_with_gaps, max_gaps);
+    NvtxRange nvtx("tcu_gaps");
+    if (!m || !gaps_in_column) return fail(TCU_ERR_INVALID, "NULL argument");
+    if (m->peers.empty())
+        return gaps_impl(m, nullptr, 0, 1, save_seq, gaps_in_column, num_cols_with_gaps, max_gaps);
+    // several devices: each counts its share of the rows; the integer partial counts are
+    // summed on the host (exact in any order)
+    const int world = 1 + (int)m->peers.size(), L = m->ncol;
+    std::vector<std::vector<int>> part((size_t)world, std::vector<int>((size_t)std::max(L, 1), 0));
+    int rc = for_each_replica(m, [&](tcu_msa *r, int k) {
+        return gaps_impl(r, nullptr, k, world, save_seq, part[k].data(), nullptr, nullptr);
+    });
+    if (rc != TCU_OK) return rc;
+    for (int k = 0; k < L; k++) {
+        int c = 0;
+        for (int d = 0; d < world; d++) c += part[d][k];
+        gaps_in_column[k] = c;
+        if (num_cols_with_gaps) num_cols_with_gaps[c]++;
+        if (max_gaps && c > *max_gaps) *max_gaps = c;
+    }
+    for (tcu_msa *p : m->peers) m->timings.kernel_ms = std::max(m->timings.kernel_ms, p->timings.kernel_ms);
+    return TCU_OK;
 }
 
 extern "C" int tcu_gaps_all(tcu_msa *m, tcu_comm *comm, const int *save_seq, int *gaps_in_column,
                             int *num_cols_with_gaps, int *max_gaps)
 {
     if (!comm) return fail(TCU_ERR_INVALID, "comm is NULL");
-    return gaps_impl(m, comm, save_seq, gaps_in_column, num_cols_with_gaps, max_gaps);
+    return gaps_impl(m, comm, 0, 1, save_seq, gaps_in_column, num_cols_with_gaps, max_gaps);
 }
 
 // ---------------------------------------------------------------------------
@@ -902,7 +1185,7 @@ extern "C" int tcu_identity_prepare(tcu_msa *m, const int *save_seq, const int *
 
 // super-blocks [sb_begin, sb_end) of IB = 128 kept rows each
 static int identity_launch(tcu_msa *m, int sb_begin, int sb_end, float *d_out, int *d_hit,
-                           int *d_dst)
+                           int *d_dst, uint32_t *d_bits = nullptr, float thr = 0.f)
 {
     if (m->nchunks == 0 || sb_end <= sb_begin) return TCU_OK;
     Identity2Params p{};
@@ -911,6 +1194,8 @@ static int identity_launch(tcu_msa *m, int sb_begin, int sb_end, float *d_out, i
     p.out = d_out;
     p.hit_out = d_hit;
     p.dst_out = d_dst;
+    p.bits_out = d_bits;
+    p.thr = thr;
     p.nb = m->nb;
     p.nb2 = m->nb2;
     p.nchunks = m->nchunks;
@@ -1083,9 +1368,86 @@ static int identity_host(tcu_msa *m, const int *save_seq, const int *save_res, u
     return TCU_OK;
 }
 
+// The same on the replicas of a multi-device handle: the pair matrix is cut into row-block
+// bands of equal work (tcu_shard_blocks), every device computes its band and copies it
+// into its slice of the caller's array over its own PCIe link; with keep_on_device the bands
+// are also collected on the first device (device-to-device) for the consumers that follow.
+static int identity_multi(tcu_msa *m, const int *save_seq, const int *save_res, uint8_t indet,
+                          float *identities, int keep_on_device)
+{
+    if (!identities && !keep_on_device)
+        return fail(TCU_ERR_INVALID, "identities is NULL and keep_on_device is 0");
+    const int world = 1 + (int)m->peers.size();
+    std::vector<size_t> lo((size_t)world), hi((size_t)world);
+    int rc = for_each_replica(m, [&](tcu_msa *r, int k) -> int {
+        r->timings = tcu_timings{};
+        r->ident_full = false;
+        int e = tcu_identity_prepare(r, save_seq, save_res, indet, nullptr);
+        if (e != TCU_OK) return e;
+        int b0 = 0, b1 = 0;
+        tcu_shard_blocks(r->nk, k, world, &b0, &b1);
+        lo[k] = tcu_identity_row_offset(r->nk, std::min(b0 * IB, r->nk));
+        hi[k] = tcu_identity_row_offset(r->nk, std::min(b1 * IB, r->nk));
+        const size_t npairs = (size_t)r->nk * (size_t)std::max(r->nk - 1, 0) / 2;
+        if (npairs == 0) {
+            CK(cudaStreamSynchronize(r->stream));
+            return TCU_OK;
+        }
+        // the first device holds the whole array when the matrix is to stay resident
+        const bool whole = k == 0 && keep_on_device;
+        e = ensure_ident(r, std::max<size_t>(whole ? npairs : hi[k] - lo[k], 1) * sizeof(float));
+        if (e != TCU_OK) return e;
+        float *d_band = whole ? r->d_ident + lo[k] : r->d_ident;
+        if (hi[k] > lo[k]) {
+            e = identity_pipeline(r, b0, b1, d_band, identities ? identities + lo[k] : nullptr,
+                                  nullptr, nullptr);
+            if (e != TCU_OK) return e;
+        }
+        CK(cudaStreamSynchronize(r->stream));
+        r->timings.h2d_ms = ev_ms(r->ev[0], r->ev[1]);
+        r->timings.pack_ms = ev_ms(r->ev[1], r->ev[2]);
+        if (hi[k] > lo[k]) r->timings.kernel_ms = ev_ms(r->ev[2], r->ev[3]);
+        return TCU_OK;
+    });
+    if (rc != TCU_OK) return rc;
+    if (keep_on_device && m->nk >= 2) {
+        CK(cudaSetDevice(m->device));
+        CK(cudaEventRecord(m->ev[4], m->stream));
+        for (int k = 1; k < world; k++) {
+            tcu_msa *p = m->peers[(size_t)k - 1];
+            if (hi[k] > lo[k])
+                CK(cudaMemcpyPeerAsync(m->d_ident + lo[k], m->device, p->d_ident, p->device,
+                                       (hi[k] - lo[k]) * sizeof(float), m->stream));
+        }
+        CK(cudaEventRecord(m->ev[5], m->stream));
+        CK(cudaStreamSynchronize(m->stream));
+        m->timings.comm_ms = ev_ms(m->ev[4], m->ev[5]);
+        m->ident_full = (m->nk == m->nseq);
+    }
+    for (tcu_msa *p : m->peers) {
+        m->timings.kernel_ms = std::max(m->timings.kernel_ms, p->timings.kernel_ms);
+        m->timings.d2h_ms = std::max(m->timings.d2h_ms, p->timings.d2h_ms);
+        m->timings.kernel_launches += p->timings.kernel_launches;
+        // the bands of the further devices are not needed there any more
+        dev_cache_give(p->device, p->d_ident, p->ident_cap);
+        p->d_ident = nullptr;
+        p->ident_cap = 0;
+    }
+    if (!keep_on_device) {
+        dev_cache_give(m->device, m->d_ident, m->ident_cap);
+        m->d_ident = nullptr;
+        m->ident_cap = 0;
+        m->ident_full = false;
+    }
+    return TCU_OK;
+}
+
 extern "C" int tcu_identity(tcu_msa *m, const int *save_seq, const int *save_res, uint8_t indet,
                             float *identities, int *hit_out, int *dst_out, int keep_on_device)
 {
+    NvtxRange nvtx("tcu_identity");
+    if (m && !m->peers.empty() && !hit_out && !dst_out)
+        return identity_multi(m, save_seq, save_res, indet, identities, keep_on_device);
     return identity_host(m, save_seq, save_res, indet, identities, hit_out, dst_out,
                          keep_on_device, false);
 }
@@ -1216,14 +1578,30 @@ extern "C" int tcu_identity_row_stats(tcu_msa *m, int upper_only, float *row_max
     return TCU_OK;
 }
 
-// Threshold bit matrix from rows [row_begin, row_end) of the identity matrix whose packed
-// offset 0 would be at `id0` (a rank that holds only its band passes band - band offset),
-// OR-combined across the ranks of `comm` (every word is written by exactly one rank -- bands
-// are multiples of 32 rows -- so an integer sum over zero-initialised matrices is the OR),
-// then the greedy clustering in the given order.
-static int clusters_impl(tcu_msa *m, tcu_comm *comm, const float *id0, int row_begin, int row_end,
-                         const int *order, int count, float threshold, int *clusters,
-                         int *n_clusters)
+// bytes of the threshold bit matrix of n sequences (slab layout, tcu_internal.cuh)
+static size_t bits_bytes(int n) { return std::max<size_t>(bits_total_words(n), 4) * sizeof(uint32_t); }
+
+// All-gather of the slabs the ranks' bands own: band [b0, b1) of 128-row blocks = slabs
+// [b0, b1), contiguous in the slab layout.
+static int bits_allgather(tcu_msa *m, tcu_comm *comm)
+{
+    std::vector<size_t> off(comm->world), cnt(comm->world);
+    const size_t slab_b = bits_slab_words(m->nk) * sizeof(uint32_t);
+    for (int r = 0; r < comm->world; r++) {
+        int b0, b1;
+        tcu_shard_blocks(m->nk, r, comm->world, &b0, &b1);
+        off[r] = (size_t)b0 * slab_b;
+        cnt[r] = (size_t)(b1 - b0) * slab_b;
+    }
+    return comm_allgatherv(comm, m->d_bits, off.data(), cnt.data(), m->stream);
+}
+
+// Greedy clustering in the given order over the threshold bit matrix m->d_bits.  When `id0`
+// is given the matrix is first derived from the resident float identities (K5: rows
+// [0, nseq), both mirror images); otherwise the caller has filled it (K1's threshold
+// epilogue + mirror pass).
+static int clusters_impl(tcu_msa *m, const float *id0, const int *order, int count,
+                         float threshold, int *clusters, int *n_clusters)
 {
     int rc = TCU_OK;
     if (!n_clusters || (count > 0 && !order)) return fail(TCU_ERR_INVALID, "NULL argument");
@@ -1234,18 +1612,20 @@ static int clusters_impl(tcu_msa *m, tcu_comm *comm, const float *id0, int row_b
             return fail(TCU_ERR_INVALID, "order[%d] = %d outside [0,%d)", k, order[k], n);
     *n_clusters = 0;
     if (count == 0) return TCU_OK;
-    const int W = (n + 31) / 32;
+    const int nslab = (n + 127) / 128;
     auto up = [](size_t b) { return (b + 255) / 256 * 256; };
-    const size_t bits_b = up((size_t)n * W * 4), rep_b = up((size_t)W * 4 + 4);
+    const size_t rep_b = up((size_t)nslab * 16 + 4);
     const size_t ord_b = up((size_t)count * 4), alive_b = up((size_t)mis_block());
     const size_t adj_b = up((size_t)mis_block() * 32 * 4);
-    rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, bits_b + rep_b + 2 * ord_b + alive_b + adj_b);
+    if (id0) {
+        rc = ensure_dev(m->device, (void **)&m->d_bits, &m->bits_cap, bits_bytes(n));
+        if (rc != TCU_OK) return rc;
+    }
+    rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, rep_b + 2 * ord_b + alive_b + adj_b);
     if (rc != TCU_OK) return rc;
     uint8_t *p = (uint8_t *)m->d_scratch;
-    uint32_t *d_bits = (uint32_t *)p;
-    p += bits_b;
-    uint32_t *d_rep = (uint32_t *)p;  // W words, then the cluster counter
-    int *d_count = (int *)(d_rep + W);
+    uint32_t *d_rep = (uint32_t *)p;  // 4 * nslab words, then the cluster counter
+    int *d_count = (int *)(d_rep + 4 * nslab);
     p += rep_b;
     int *d_order = (int *)p;
     p += ord_b;
@@ -1257,17 +1637,11 @@ static int clusters_impl(tcu_msa *m, tcu_comm *comm, const float *id0, int row_b
     CK(cudaEventRecord(m->ev[0], m->stream));
     CK(cudaMemcpyAsync(d_order, order, (size_t)count * 4, cudaMemcpyHostToDevice, m->stream));
     CK(cudaMemsetAsync(d_rep, 0, rep_b, m->stream));
-    if (comm) CK(cudaMemsetAsync(d_bits, 0, (size_t)n * W * 4, m->stream));
     CK(cudaEventRecord(m->ev[1], m->stream));
-    CK(launch_identity_bits(id0, n, W, threshold, d_bits, row_begin, row_end, m->stream));
-    CK(cudaEventRecord(m->ev[5], m->stream));
-    if (comm) {
-        rc = comm_allreduce_i32(comm, (int *)d_bits, (size_t)n * W, m->stream);
-        if (rc != TCU_OK) return rc;
-    }
+    if (id0) CK(launch_identity_bits(id0, n, threshold, m->d_bits, 0, n, m->stream));
     CK(cudaEventRecord(m->ev[2], m->stream));
-    CK(launch_greedy_clusters(d_bits, W, d_order, count, d_rep, d_alive, d_adj, d_clusters, d_count,
-                              m->stream));
+    CK(launch_greedy_clusters(m->d_bits, n, d_order, count, d_rep, d_alive, d_adj, d_clusters,
+                              d_count, m->stream));
     CK(cudaEventRecord(m->ev[3], m->stream));
     int found = 0;
     CK(cudaMemcpyAsync(&found, d_count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
@@ -1279,11 +1653,10 @@ static int clusters_impl(tcu_msa *m, tcu_comm *comm, const float *id0, int row_b
     CK(cudaStreamSynchronize(m->stream));
     *n_clusters = found;
     m->timings.h2d_ms = ev_ms(m->ev[0], m->ev[1]);
-    m->timings.pack_ms = ev_ms(m->ev[1], m->ev[5]);    // threshold -> bit matrix
-    m->timings.comm_ms = ev_ms(m->ev[5], m->ev[2]);    // OR across ranks
+    m->timings.pack_ms = ev_ms(m->ev[1], m->ev[2]);    // threshold -> bit matrix (K5)
     m->timings.kernel_ms = ev_ms(m->ev[2], m->ev[3]);  // greedy clustering
     m->timings.d2h_ms = ev_ms(m->ev[3], m->ev[4]);
-    m->timings.kernel_launches = 1 + 2 * ((count + mis_block() - 1) / mis_block());
+    m->timings.kernel_launches = (id0 ? 1 : 0) + 2 * ((count + mis_block() - 1) / mis_block());
     return TCU_OK;
 }
 
@@ -1292,8 +1665,7 @@ extern "C" int tcu_identity_clusters(tcu_msa *m, const int *order, int count, fl
 {
     int rc = need_resident(m);
     if (rc != TCU_OK) return rc;
-    return clusters_impl(m, nullptr, m->d_ident, 0, m->nseq, order, count, threshold, clusters,
-                         n_clusters);
+    return clusters_impl(m, m->d_ident, order, count, threshold, clusters, n_clusters);
 }
 
 extern "C" int tcu_byte_histogram(tcu_msa *m, unsigned long long *hist256)
@@ -1383,15 +1755,24 @@ extern "C" int tcu_cluster_order(const int *lengths, int nseq, int *order)
     return TCU_OK;
 }
 
-// Cleaner::calculateRepresentativeSeq in one call: identity matrix (left on the device),
-// sequence lengths, visiting order, greedy clustering.  With a communicator every rank
-// computes its row band of the matrix and thresholds it; the bit matrices (n^2/8 bytes, 32x
-// smaller than the floats) are OR-ed across the ranks with one NCCL all-reduce and every
-// rank runs the (sequential, cheap) clustering and returns the full result.
+// Cleaner::calculateRepresentativeSeq in one call.  The walk only ever asks "identity >
+// threshold" (Cleaner.cpp:1435-1440), so the float matrix is never materialised: K1 compares
+// each ratio with the threshold in its epilogue and emits one bit per pair (n^2/16 bytes
+// instead of 4*P: 156 MB instead of 5 GB at 50 000 sequences, and no capacity ceiling from
+// the packed array), a mirror pass completes the symmetric matrix, and the greedy
+// clustering runs on it.  The sequence lengths go first (one tiny kernel) so that the
+// host-side replay of the reference's sort runs on another thread under the identity kernel.
+// With a communicator every rank computes the bits of its row band (a contiguous run of
+// slabs), the bands are all-gathered over NVLink and every rank finishes alone.
 static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res, uint8_t indet,
                                 float threshold, int *clusters, int *n_clusters)
 {
     if (!m || !n_clusters) return fail(TCU_ERR_INVALID, "NULL argument");
+    int rc = comm_check(m, comm);
+    if (rc != TCU_OK) return rc;
+    const int n = m->nseq;
+    *n_clusters = 0;
+    if (n == 0) return TCU_OK;
     tcu_timings total{};
     auto add = [&](const tcu_timings &t) {
         total.h2d_ms += t.h2d_ms;
@@ -1401,16 +1782,14 @@ static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res,
         total.comm_ms += t.comm_ms;
         total.kernel_launches += t.kernel_launches;
     };
-    // lengths first (one tiny kernel), so that the host-side sort of the visiting order
-    // runs on another thread while the GPU computes the identity matrix
-    std::vector<int> lengths((size_t)m->nseq), order((size_t)m->nseq);
-    int rc = tcu_sequence_lengths(m, lengths.data());
+    std::vector<int> lengths((size_t)n), order((size_t)n);
+    rc = tcu_sequence_lengths(m, lengths.data());
     if (rc != TCU_OK) return rc;
     add(m->timings);
     int sort_rc = TCU_OK;
     std::string sort_err;
     auto sort = [&]() {
-        sort_rc = tcu_cluster_order(lengths.data(), m->nseq, order.data());
+        sort_rc = tcu_cluster_order(lengths.data(), n, order.data());
         if (sort_rc != TCU_OK) sort_err = g_last_error;  // thread-local: carry it over
     };
     std::thread sorter;
@@ -1419,46 +1798,101 @@ static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res,
     } catch (...) {  // no thread to be had: sort here, nothing may escape the C ABI
         sort();
     }
-    const float *id0 = nullptr;
-    int row_begin = 0, row_end = m->nseq;
-    if (comm) {
-        // this rank's band only (no float all-gather: the ranks exchange the 32x smaller
-        // bit matrix instead); the band sits at the start of d_ident
-        rc = comm_check(m, comm);
-        if (rc == TCU_OK) {
-            m->timings = tcu_timings{};
-            m->ident_full = false;
-            rc = tcu_identity_prepare(m, nullptr, save_res, indet, nullptr);
-        }
-        if (rc == TCU_OK) {
-            int b0 = 0, b1 = 0;
-            tcu_shard_blocks(m->nk, comm->rank, comm->world, &b0, &b1);
-            row_begin = std::min(b0 * IB, m->nk);
-            row_end = std::min(b1 * IB, m->nk);
-            const size_t lo = tcu_identity_row_offset(m->nk, row_begin);
-            const size_t hi = tcu_identity_row_offset(m->nk, row_end);
-            rc = ensure_ident(m, std::max<size_t>(hi - lo, 1) * sizeof(float));
-            if (rc == TCU_OK) rc = identity_launch(m, b0, b1, m->d_ident, nullptr, nullptr);
-            if (rc == TCU_OK) {
-                id0 = m->d_ident - lo;
-                cudaError_t e = cudaEventRecord(m->ev[3], m->stream);
-                if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
-                if (e != cudaSuccess) rc = cuda_fail(e, "identity band");
-                m->timings.h2d_ms = ev_ms(m->ev[0], m->ev[1]);
-                m->timings.pack_ms = ev_ms(m->ev[1], m->ev[2]);
-                m->timings.kernel_ms = ev_ms(m->ev[2], m->ev[3]);
+    auto device_part = [&]() -> int {
+        m->timings = tcu_timings{};
+        m->ident_full = false;
+        int r = tcu_identity_prepare(m, nullptr, save_res, indet, nullptr);
+        if (r != TCU_OK) return r;
+        r = ensure_dev(m->device, (void **)&m->d_bits, &m->bits_cap, bits_bytes(n));
+        if (r != TCU_OK) return r;
+        if (m->nchunks == 0) {
+            // no columns: every identity is 0 (template.h:427-434)
+            CK(cudaMemsetAsync(m->d_bits, threshold < 0.f ? 0xFF : 0, bits_bytes(n), m->stream));
+            CK(cudaEventRecord(m->ev[3], m->stream));
+        } else {
+            int b0 = 0, b1 = m->nsb;
+            if (comm) tcu_shard_blocks(m->nk, comm->rank, comm->world, &b0, &b1);
+            r = identity_launch(m, b0, b1, nullptr, nullptr, nullptr, m->d_bits, threshold);
+            if (r != TCU_OK) return r;
+            CK(cudaEventRecord(m->ev[3], m->stream));
+            if (comm) {
+                r = bits_allgather(m, comm);
+                if (r != TCU_OK) return r;
             }
+            CK(cudaEventRecord(m->ev[4], m->stream));
+            CK(launch_bits_symmetrize(m->d_bits, n, m->stream));
+            m->timings.kernel_launches++;
         }
-    } else {
-        rc = tcu_identity(m, nullptr, save_res, indet, nullptr, nullptr, nullptr, 1);
-        id0 = m->d_ident;
-    }
+        CK(cudaEventRecord(m->ev[5], m->stream));
+        CK(cudaStreamSynchronize(m->stream));
+        m->timings.h2d_ms = ev_ms(m->ev[0], m->ev[1]);
+        m->timings.pack_ms = ev_ms(m->ev[1], m->ev[2]);
+        m->timings.kernel_ms = ev_ms(m->ev[2], m->ev[3]);
+        if (m->nchunks) {
+            m->timings.comm_ms = ev_ms(m->ev[3], m->ev[4]);
+            m->timings.pack_ms += ev_ms(m->ev[4], m->ev[5]);  // mirror pass
+        }
+        return TCU_OK;
+    };
+    // The replicas of a multi-device handle (one process, several GPUs): every device
+    // thresholds its band into its own run of slabs; the first device then pulls the other
+    // bands over NVLink (one contiguous peer copy each), mirrors and clusters.
+    auto device_part_multi = [&]() -> int {
+        const int world = 1 + (int)m->peers.size();
+        const size_t slab_w = bits_slab_words(n);
+        std::vector<int> bb((size_t)world + 1, 0);
+        int r = for_each_replica(m, [&](tcu_msa *d, int k) -> int {
+            d->timings = tcu_timings{};
+            d->ident_full = false;
+            int e = tcu_identity_prepare(d, nullptr, save_res, indet, nullptr);
+            if (e != TCU_OK) return e;
+            int b0 = 0, b1 = 0;
+            tcu_shard_blocks(d->nk, k, world, &b0, &b1);
+            bb[k] = b0;
+            bb[k + 1] = b1;
+            const size_t need = k == 0 ? bits_bytes(n)
+                                       : std::max<size_t>((size_t)(b1 - b0) * slab_w, 4) * sizeof(uint32_t);
+            e = ensure_dev(d->device, (void **)&d->d_bits, &d->bits_cap, need);
+            if (e != TCU_OK) return e;
+            // K1 indexes slabs absolutely: a device that holds only its band passes the address
+            // slab 0 would have
+            uint32_t *base = k == 0 ? d->d_bits : d->d_bits - (size_t)b0 * slab_w;
+            e = identity_launch(d, b0, b1, nullptr, nullptr, nullptr, base, threshold);
+            if (e != TCU_OK) return e;
+            CK(cudaEventRecord(d->ev[3], d->stream));
+            CK(cudaStreamSynchronize(d->stream));
+            d->timings.h2d_ms = ev_ms(d->ev[0], d->ev[1]);
+            d->timings.pack_ms = ev_ms(d->ev[1], d->ev[2]);
+            d->timings.kernel_ms = ev_ms(d->ev[2], d->ev[3]);
+            return TCU_OK;
+        });
+        if (r != TCU_OK) return r;
+        CK(cudaSetDevice(m->device));
+        CK(cudaEventRecord(m->ev[3], m->stream));
+        for (int k = 1; k < world; k++) {
+            tcu_msa *p = m->peers[(size_t)k - 1];
+            if (bb[k + 1] > bb[k])
+                CK(cudaMemcpyPeerAsync(m->d_bits + (size_t)bb[k] * slab_w, m->device, p->d_bits,
+                                       p->device, (size_t)(bb[k + 1] - bb[k]) * slab_w * sizeof(uint32_t),
+                                       m->stream));
+            m->timings.kernel_ms = std::max(m->timings.kernel_ms, p->timings.kernel_ms);
+            m->timings.kernel_launches += p->timings.kernel_launches;
+        }
+        CK(cudaEventRecord(m->ev[4], m->stream));
+        CK(launch_bits_symmetrize(m->d_bits, n, m->stream));
+        m->timings.kernel_launches++;
+        CK(cudaEventRecord(m->ev[5], m->stream));
+        CK(cudaStreamSynchronize(m->stream));
+        m->timings.comm_ms = ev_ms(m->ev[3], m->ev[4]);
+        m->timings.pack_ms += ev_ms(m->ev[4], m->ev[5]);  // mirror pass
+        return TCU_OK;
+    };
+    rc = (!comm && !m->peers.empty() && m->ncol > 0) ? device_part_multi() : device_part();
     if (sorter.joinable()) sorter.join();
     if (rc != TCU_OK) return rc;
     add(m->timings);
     if (sort_rc != TCU_OK) return fail(sort_rc, "%s", sort_err.c_str());
-    rc = clusters_impl(m, comm, id0, row_begin, row_end, order.data(), m->nseq, threshold, clusters,
-                       n_clusters);
+    rc = clusters_impl(m, nullptr, order.data(), n, threshold, clusters, n_clusters);
     if (rc != TCU_OK) return rc;
     add(m->timings);
     m->timings = total;
@@ -1468,6 +1902,7 @@ static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res,
 extern "C" int tcu_representatives(tcu_msa *m, const int *save_res, uint8_t indet, float threshold,
                                    int *clusters, int *n_clusters)
 {
+    NvtxRange nvtx("tcu_representatives");
     return representatives_impl(m, nullptr, save_res, indet, threshold, clusters, n_clusters);
 }
 
@@ -1482,47 +1917,80 @@ extern "C" int tcu_representatives_all(tcu_msa *m, tcu_comm *comm, const int *sa
 // ---------------------------------------------------------------------------
 // K2 spurious
 // ---------------------------------------------------------------------------
-static int spurious_impl(tcu_msa *m, tcu_comm *comm, uint8_t indet, uint32_t ovrlap,
-                         float *spurious)
+// How one device takes part in the statistic when the rows are spread over the replicas of a
+// multi-device handle: phase 1 = partial column counts of the share (rank of world) to
+// host_counts (2 * ncol ints: '-' then indet); phase 2 = total counts from host_counts, then
+// the share's rows of the vector straight into the caller's array.  Phase 0 = all of it.
+struct SpuriousShare {
+    int rank = 0, world = 1, phase = 0;
+    int *host_counts = nullptr;
+};
+
+static int spurious_impl(tcu_msa *m, tcu_comm *comm, const SpuriousShare &sh, uint8_t indet,
+                         uint32_t ovrlap, float *spurious)
 {
     if (!m || !spurious) return fail(TCU_ERR_INVALID, "NULL argument");
     CK(cudaSetDevice(m->device));
     int rc0 = comm_check(m, comm);
     if (rc0 != TCU_OK) return rc0;
-    m->timings = tcu_timings{};
+    if (sh.phase != 2) m->timings = tcu_timings{};
     const int n = m->nseq, L = m->ncol;
     if (n == 0) return TCU_OK;
     if (L == 0) {
         // 0/0 in the reference's final division (template.h:309)
-        for (int i = 0; i < n; i++) spurious[i] = NAN;
+        if (sh.phase != 1 && sh.rank == 0)
+            for (int i = 0; i < n; i++) spurious[i] = NAN;
         return TCU_OK;
     }
     const size_t cnt_bytes = ((size_t)L * sizeof(int) + 255) / 256 * 256;
     const size_t out_bytes = ((size_t)n * sizeof(float) + 255) / 256 * 256;
-    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, 2 * cnt_bytes + out_bytes + m->pitch);
+    const size_t flag_bytes = (3 * (m->pitch >> 5) * sizeof(uint32_t) + 255) / 256 * 256;
+    const size_t plane_bytes = (size_t)n * (m->pitch >> 3);  // one bit per cell, pitch % 128 == 0
+    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap,
+                        2 * cnt_bytes + out_bytes + flag_bytes + 2 * plane_bytes);
     if (rc != TCU_OK) return rc;
     int *d_cg = (int *)m->d_scratch;
     int *d_cx = (int *)((uint8_t *)m->d_scratch + cnt_bytes);
     float *d_out = (float *)((uint8_t *)m->d_scratch + 2 * cnt_bytes);
-    uint8_t *d_flags = (uint8_t *)m->d_scratch + 2 * cnt_bytes + out_bytes;
-    CK(cudaMemsetAsync(d_cg, 0, 2 * cnt_bytes, m->stream));
-    CK(cudaMemsetAsync(d_flags, 0, m->pitch, m->stream));
-    CK(cudaEventRecord(m->ev[1], m->stream));
+    uint32_t *d_flags = (uint32_t *)((uint8_t *)m->d_scratch + 2 * cnt_bytes + out_bytes);
+    uint8_t *d_pg = (uint8_t *)d_flags + flag_bytes, *d_px = d_pg + plane_bytes;
     // several ranks: partial column counts over this rank's rows, summed across GPUs
     // (d_cg and d_cx are adjacent: one all-reduce), then this rank's rows of the
     // vector, all-gathered
     int r0 = 0, r1 = n;
     if (comm) tcu_shard_range(n, 1, comm->rank, comm->world, &r0, &r1);
-    CK(launch_column_counts(m->d_raw + (size_t)r0 * m->pitch, r1 - r0, L, m->pitch, nullptr, '-',
-                            indet, d_cg, d_cx, m->num_sms, m->stream));
-    CK(cudaEventRecord(m->ev[4], m->stream));
-    if (comm) {
-        rc = comm_allreduce_i32(comm, d_cg, 2 * cnt_bytes / sizeof(int), m->stream);
-        if (rc != TCU_OK) return rc;
+    else tcu_shard_range(n, 1, sh.rank, sh.world, &r0, &r1);
+    const size_t prow = m->pitch >> 3;  // bytes per plane row
+    if (sh.phase != 2) {
+        CK(cudaMemsetAsync(d_cg, 0, 2 * cnt_bytes, m->stream));
+        CK(cudaEventRecord(m->ev[1], m->stream));
+        CK(launch_column_counts(m->d_raw + (size_t)r0 * m->pitch, r1 - r0, L, m->pitch, nullptr,
+                                '-', indet, d_cg, d_cx, (uint16_t *)(d_pg + (size_t)r0 * prow),
+                                (uint16_t *)(d_px + (size_t)r0 * prow), m->num_sms, m->stream));
+        CK(cudaEventRecord(m->ev[4], m->stream));
+        if (comm) {
+            rc = comm_allreduce_i32(comm, d_cg, 2 * cnt_bytes / sizeof(int), m->stream);
+            if (rc != TCU_OK) return rc;
+        }
+        if (sh.phase == 1) {
+            CK(cudaMemcpyAsync(sh.host_counts, d_cg, (size_t)L * sizeof(int), cudaMemcpyDeviceToHost,
+                               m->stream));
+            CK(cudaMemcpyAsync(sh.host_counts + L, d_cx, (size_t)L * sizeof(int),
+                               cudaMemcpyDeviceToHost, m->stream));
+            CK(cudaStreamSynchronize(m->stream));
+            m->timings.kernel_ms = ev_ms(m->ev[1], m->ev[4]);
+            m->timings.kernel_launches = 1;
+            return TCU_OK;
+        }
+    } else {
+        CK(cudaMemcpyAsync(d_cg, sh.host_counts, (size_t)L * sizeof(int), cudaMemcpyHostToDevice,
+                           m->stream));
+        CK(cudaMemcpyAsync(d_cx, sh.host_counts + L, (size_t)L * sizeof(int), cudaMemcpyHostToDevice,
+                           m->stream));
     }
     CK(cudaEventRecord(m->ev[5], m->stream));
-    CK(launch_spurious_rows(m->d_raw, n, r0, r1, L, m->pitch, indet, d_cg, d_cx, ovrlap, d_flags,
-                            d_out, m->stream));
+    CK(launch_spurious_rows((const uint32_t *)d_pg, (const uint32_t *)d_px, n, r0, r1, L, m->pitch,
+                            d_cg, d_cx, ovrlap, d_flags, d_out, m->num_sms, m->stream));
     CK(cudaEventRecord(m->ev[2], m->stream));
     if (comm) {
         std::vector<size_t> off(comm->world), cnt(comm->world);
@@ -1536,27 +2004,60 @@ static int spurious_impl(tcu_msa *m, tcu_comm *comm, uint8_t indet, uint32_t ovr
         if (rc != TCU_OK) return rc;
     }
     CK(cudaEventRecord(m->ev[0], m->stream));
-    CK(cudaMemcpyAsync(spurious, d_out, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost,
-                       m->stream));
+    if (sh.phase == 2) {
+        if (r1 > r0)
+            CK(cudaMemcpyAsync(spurious + r0, d_out + r0, (size_t)(r1 - r0) * sizeof(float),
+                               cudaMemcpyDeviceToHost, m->stream));
+    } else {
+        CK(cudaMemcpyAsync(spurious, d_out, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost,
+                           m->stream));
+    }
     CK(cudaEventRecord(m->ev[3], m->stream));
     CK(cudaStreamSynchronize(m->stream));
-    m->timings.kernel_ms = ev_ms(m->ev[1], m->ev[4]) + ev_ms(m->ev[5], m->ev[2]);
-    m->timings.comm_ms = ev_ms(m->ev[4], m->ev[5]) + ev_ms(m->ev[2], m->ev[0]);
+    if (sh.phase == 2) {
+        m->timings.kernel_ms += ev_ms(m->ev[5], m->ev[2]);
+        m->timings.kernel_launches += 2;
+    } else {
+        m->timings.kernel_ms = ev_ms(m->ev[1], m->ev[4]) + ev_ms(m->ev[5], m->ev[2]);
+        m->timings.comm_ms = ev_ms(m->ev[4], m->ev[5]) + ev_ms(m->ev[2], m->ev[0]);
+        m->timings.kernel_launches = 3;
+    }
     m->timings.d2h_ms = ev_ms(m->ev[0], m->ev[3]);
-    m->timings.kernel_launches = 3;
     return TCU_OK;
 }
 
 extern "C" int tcu_spurious(tcu_msa *m, uint8_t indet, uint32_t ovrlap, float *spurious)
 {
-    return spurious_impl(m, nullptr, indet, ovrlap, spurious);
+    NvtxRange nvtx("tcu_spurious");
+    if (!m || !spurious) return fail(TCU_ERR_INVALID, "NULL argument");
+    if (m->peers.empty()) return spurious_impl(m, nullptr, SpuriousShare{}, indet, ovrlap, spurious);
+    // several devices: partial column counts per share of the rows, summed on the host
+    // (integers), then every device finishes its own rows of the vector
+    const int world = 1 + (int)m->peers.size(), L = m->ncol;
+    std::vector<std::vector<int>> part((size_t)world, std::vector<int>((size_t)std::max(2 * L, 1), 0));
+    int rc = for_each_replica(m, [&](tcu_msa *r, int k) {
+        SpuriousShare sh;
+        sh.rank = k, sh.world = world, sh.phase = 1, sh.host_counts = part[k].data();
+        return spurious_impl(r, nullptr, sh, indet, ovrlap, spurious);
+    });
+    if (rc != TCU_OK) return rc;
+    for (int d = 1; d < world; d++)
+        for (int k = 0; k < 2 * L; k++) part[0][k] += part[d][k];
+    rc = for_each_replica(m, [&](tcu_msa *r, int k) {
+        SpuriousShare sh;
+        sh.rank = k, sh.world = world, sh.phase = 2, sh.host_counts = part[0].data();
+        return spurious_impl(r, nullptr, sh, indet, ovrlap, spurious);
+    });
+    if (rc != TCU_OK) return rc;
+    for (tcu_msa *p : m->peers) m->timings.kernel_ms = std::max(m->timings.kernel_ms, p->timings.kernel_ms);
+    return TCU_OK;
 }
 
 extern "C" int tcu_spurious_all(tcu_msa *m, tcu_comm *comm, uint8_t indet, uint32_t ovrlap,
                                 float *spurious)
 {
     if (!comm) return fail(TCU_ERR_INVALID, "comm is NULL");
-    return spurious_impl(m, comm, indet, ovrlap, spurious);
+    return spurious_impl(m, comm, SpuriousShare{}, indet, ovrlap, spurious);
 }
 
 // ---------------------------------------------------------------------------
@@ -1711,6 +2212,7 @@ extern "C" int tcu_similarity(tcu_msa *m, uint8_t indet, const float *dist, int 
                               const float *identities, float *num, float *den, float *mdk,
                               int *err_col, int *err_row, int *err_byte)
 {
+    NvtxRange nvtx("tcu_similarity");
     return similarity_impl(m, nullptr, indet, dist, npos, vhash, gaps, gap_threshold, identities,
                            num, den, mdk, err_col, err_row, err_byte);
 }

@@ -11,7 +11,9 @@
 // Here they run where the matrix already is:
 //
 //   K5 k_identity_bits   one streaming pass (HBM-bound, 4*P bytes read): identity > threshold
-//                        as a full symmetric nseq x nseq BIT matrix (nseq^2/8 bytes)
+//                        as a full symmetric nseq x nseq BIT matrix (nseq^2/8 bytes); only for
+//                        a matrix that is already resident as floats -- tcu_representatives gets
+//                        the bits from K1's epilogue + k_bits_symmetrize
 //   K6 k_row_stats       per-row statistics; each lane owns one row and replays the
 //                        reference's fp32 additions in the reference's order (j ascending)
 //   K7 k_mis_scan  +  K8 k_mis_resolve
@@ -23,7 +25,8 @@
 //                        sequence of the block against all representatives of earlier
 //                        blocks (one AND over two bit rows per sequence, whole GPU) and
 //                        gathers the 1024 x 1024 adjacency inside the block; K8 resolves
-//                        the block sequentially in one warp (one vote per live sequence).
+//                        the block in one CTA (fixed point of the greedy rule, all 1024
+//                        sequences at once).
 //                        Result and order of the cluster list are exactly the reference's.
 #include "tcu_internal.cuh"
 
@@ -37,10 +40,11 @@ __device__ __forceinline__ long long pair_row_base(long long i, long long n)
 }
 
 // ---------------------------------------------------------------------------
-// K5: threshold -> symmetric bit matrix.  One warp per 32 x 32 block of the upper
-// triangle: 32 coalesced row reads (issued in batches of 16 before any is used, so
-// that a warp keeps 2 KB in flight); the ballots are the row words, the per-lane
-// accumulated bits the words of the transposed block.
+// K5: threshold -> symmetric bit matrix in the slab layout (tcu_internal.cuh), from a
+// resident float matrix.  One warp per 32 x 32 block of the upper triangle: 32 coalesced row
+// reads (issued in batches of 16 before any is used, so that a warp keeps 2 KB in
+// flight); the ballots are the row words, the per-lane accumulated bits the words of the
+// transposed block.  (tcu_representatives does not come here: K1 thresholds in its epilogue.)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_identity_bits(const float *__restrict__ id, int n, int W,
                                                        float thr, uint32_t *__restrict__ bits,
@@ -73,23 +77,81 @@ __global__ void __launch_bounds__(256) k_identity_bits(const float *__restrict__
     }
     if (jw == rb) {
         // diagonal block: bits j > i come from the row word, bits j < i from the column word
-        if (i0 + lane < n) bits[(size_t)(i0 + lane) * W + jw] = mine | colword;
+        if (i0 + lane < n) bits[bits_word_index(n, i0 + lane, jw)] = mine | colword;
     } else {
-        if (i0 + lane < n) bits[(size_t)(i0 + lane) * W + jw] = mine;
-        if (j < n) bits[(size_t)j * W + rb] = colword;
+        if (i0 + lane < n) bits[bits_word_index(n, i0 + lane, jw)] = mine;
+        if (j < n) bits[bits_word_index(n, j, rb)] = colword;
     }
 }
 
 // Rows [row_begin, row_end) of the matrix (multiples of 32, or n): `id` is the address
 // packed offset 0 WOULD have, so a rank that holds only its band passes band - band_offset.
-// Every word of `bits` that belongs to these rows' pairs is written; a caller that covers
-// only part of the rows must zero `bits` first.
-cudaError_t launch_identity_bits(const float *id, int n, int W, float thr, uint32_t *bits,
-                                 int row_begin, int row_end, cudaStream_t stream)
+// Every word of `bits` that belongs to these rows' pairs is written (both mirror images).
+cudaError_t launch_identity_bits(const float *id, int n, float thr, uint32_t *bits, int row_begin,
+                                 int row_end, cudaStream_t stream)
 {
     if (n <= 0 || row_end <= row_begin) return cudaSuccess;
+    const int W = (n + 31) / 32;
     dim3 grid((W + 7) / 8, (row_end - row_begin + 31) / 32);
     k_identity_bits<<<grid, 256, 0, stream>>>(id, n, W, thr, bits, row_begin / 32);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Mirror pass over a bit matrix of which K1's threshold epilogue wrote the "column words"
+// (row j against earlier sequences i < j; zeros where j <= i): every 128 x 128 block (BI, BJ),
+// BI < BJ, is transposed into its mirror image and a diagonal block becomes U | U^T.  One CTA
+// of 128 threads per block: thread = row, one 16-byte load, four 32 x 32 butterfly transposes,
+// the mirrored rows leave as 16-byte stores through shared memory.  HBM-bound: reads and
+// writes n^2 / 16 bytes each.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_bits_symmetrize(uint32_t *__restrict__ bits, int n)
+{
+    // block (BI, BJ), BJ >= BI: rows of super-block BJ against the sequences of super-block BI
+    const int BI = blockIdx.x, BJ = blockIdx.y;
+    if (BJ < BI) return;
+    __shared__ uint4 s_out[128];  // [sequence of BI] = its words against the rows of BJ
+    const int lane = threadIdx.x & 31, u = threadIdx.x >> 5;
+    const int r = BJ * 128 + threadIdx.x;  // this thread's row of BJ (warp u = its 32-row group)
+    uint4 *slabs = reinterpret_cast<uint4 *>(bits);
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    const uint4 own = r < n ? slabs[(size_t)BI * n + r] : zero;  // bits (r, i) for i < r
+    const uint32_t w4[4] = {own.x, own.y, own.z, own.w};
+    uint32_t *s_words = reinterpret_cast<uint32_t *>(s_out);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        // 32 x 32 bit transpose across the warp (lane = row): five butterfly stages, each
+        // swapping the off-diagonal j x j blocks with the lane j away; afterwards lane k
+        // holds sequence 128 BI + 32 q + k against rows 128 BJ + 32 u ..
+        uint32_t x = w4[q];
+        uint32_t low = 0x0000FFFFu;  // columns c with (c & j) == 0
+#pragma unroll
+        for (int j = 16; j >= 1; j >>= 1) {
+            const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+            x = (lane & j) ? ((x & ~low) | ((y & ~low) >> j)) : ((x & low) | ((y & low) << j));
+            low ^= low << (j >> 1);  // 0x0000FFFF -> 0x00FF00FF -> 0x0F0F0F0F -> 0x33333333 -> 0x55555555
+        }
+        s_words[(32 * q + lane) * 4 + u] = x;
+    }
+    __syncthreads();
+    const int c = BI * 128 + threadIdx.x;  // sequence of BI whose mirrored words this thread stores
+    if (c >= n) return;
+    uint4 t4 = s_out[threadIdx.x];
+    if (BI == BJ) {
+        t4.x |= own.x;
+        t4.y |= own.y;
+        t4.z |= own.z;
+        t4.w |= own.w;
+    }
+    slabs[(size_t)BJ * n + c] = t4;
+}
+
+cudaError_t launch_bits_symmetrize(uint32_t *bits, int n, cudaStream_t stream)
+{
+    if (n <= 0) return cudaSuccess;
+    const int nsb = (n + 127) / 128;
+    dim3 grid(nsb, nsb);
+    k_bits_symmetrize<<<grid, 128, 0, stream>>>(bits, n);
     return cudaGetLastError();
 }
 
@@ -202,10 +264,12 @@ cudaError_t launch_row_stats(const float *id, int n, bool upper_only, float *row
 //   adj[l][t]  = adjacency bits to the block's sequences 32*l .. 32*l+31 that precede t
 //                (word-major, so that K8 reads one word of 32 consecutive sequences
 //                without bank conflicts); zero for a sequence that is not alive
+// A sequence's bits are one 16-byte entry per slab (tcu_internal.cuh); `rep` is padded to
+// whole slabs (4 * nslab words, zero beyond n).
 // ---------------------------------------------------------------------------
 constexpr int MIS_NB = 1024;
 
-__global__ void __launch_bounds__(256) k_mis_scan(const uint32_t *__restrict__ bits, int W,
+__global__ void __launch_bounds__(256) k_mis_scan(const uint32_t *__restrict__ bits, int n,
                                                   const int *__restrict__ order, int base, int cnt,
                                                   const uint32_t *__restrict__ rep,
                                                   uint8_t *__restrict__ alive8,
@@ -217,14 +281,26 @@ __global__ void __launch_bounds__(256) k_mis_scan(const uint32_t *__restrict__ b
     const int lane = threadIdx.x & 31;
     const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (t >= cnt) return;
-    const uint32_t *row = bits + (size_t)s_ord[t] * W;
+    const int s = s_ord[t];
+    const int nslab = (n + 127) >> 7;
+    const uint4 *slabs = reinterpret_cast<const uint4 *>(bits) + s;
+    const uint4 *rep4 = reinterpret_cast<const uint4 *>(rep);
     uint32_t acc = 0;
-    int w = lane;
-    for (; w + 96 < W; w += 128) {  // four independent load pairs per step
-        const uint32_t a0 = row[w], a1 = row[w + 32], a2 = row[w + 64], a3 = row[w + 96];
-        acc |= (a0 & rep[w]) | (a1 & rep[w + 32]) | (a2 & rep[w + 64]) | (a3 & rep[w + 96]);
+    int S = lane;
+    for (; S + 96 < nslab; S += 128) {  // four independent load pairs per step
+        const uint4 a0 = slabs[(size_t)S * n], a1 = slabs[(size_t)(S + 32) * n];
+        const uint4 a2 = slabs[(size_t)(S + 64) * n], a3 = slabs[(size_t)(S + 96) * n];
+        const uint4 r0 = rep4[S], r1 = rep4[S + 32], r2 = rep4[S + 64], r3 = rep4[S + 96];
+        acc |= (a0.x & r0.x) | (a0.y & r0.y) | (a0.z & r0.z) | (a0.w & r0.w);
+        acc |= (a1.x & r1.x) | (a1.y & r1.y) | (a1.z & r1.z) | (a1.w & r1.w);
+        acc |= (a2.x & r2.x) | (a2.y & r2.y) | (a2.z & r2.z) | (a2.w & r2.w);
+        acc |= (a3.x & r3.x) | (a3.y & r3.y) | (a3.z & r3.z) | (a3.w & r3.w);
     }
-    for (; w < W; w += 32) acc |= row[w] & rep[w];
+    for (; S < nslab; S += 32) {
+        const uint4 a0 = slabs[(size_t)S * n];
+        const uint4 r0 = rep4[S];
+        acc |= (a0.x & r0.x) | (a0.y & r0.y) | (a0.z & r0.z) | (a0.w & r0.w);
+    }
     const bool dead = __any_sync(0xffffffffu, acc != 0);
     if (lane == 0) alive8[t] = dead ? 0 : 1;
     uint32_t word = 0;
@@ -234,31 +310,27 @@ __global__ void __launch_bounds__(256) k_mis_scan(const uint32_t *__restrict__ b
         if (amax == 32) {
             uint32_t g[32];
 #pragma unroll
-            for (int a = 0; a < 32; a++) g[a] = row[s_ord[a0 + a] >> 5];
+            for (int a = 0; a < 32; a++) g[a] = bits[bits_word_index(n, s, s_ord[a0 + a] >> 5)];
 #pragma unroll
             for (int a = 0; a < 32; a++) word |= ((g[a] >> (s_ord[a0 + a] & 31)) & 1u) << a;
         } else {
             for (int a = 0; a < amax; a++) {
                 const int u = s_ord[a0 + a];
-                word |= ((row[u >> 5] >> (u & 31)) & 1u) << a;
+                word |= ((bits[bits_word_index(n, s, u >> 5)] >> (u & 31)) & 1u) << a;
             }
         }
     }
     adj[lane * MIS_NB + t] = word;
 }
 
-// K8: one CTA copies the block's adjacency into shared memory; warp 0 then resolves the
-// block 32 sequences at a time, lane l owning sequence 32*g + l of group g:
-//   1. killed by a representative of an earlier group of this block?  One AND per
-//      earlier group, lanes in parallel (the representatives of group w live in lane w).
-//   2. inside the group the greedy rule is iterated to its fixed point with ballots: a
-//      sequence with an adjacent representative is out; one whose earlier neighbours
-//      are all decided and none of them a representative becomes one.  The lowest
-//      undecided lane always decides, so this ends after at most 32 rounds (2-3 in practice)
-//      and gives exactly the sequential answer.
-//   3. the new representatives are appended in visiting order (prefix popcount).
-constexpr int MIS_SMEM = MIS_NB * 32 * 4 + MIS_NB * 4 + MIS_NB;
-
+// K8: one CTA of 1024 threads resolves the block; thread t owns sequence t of the block and
+// keeps its adjacency words to the earlier sequences of the block in registers.  The greedy
+// rule is iterated to its fixed point for the whole block at once:
+//   a sequence with an adjacent representative is out;
+//   one none of whose earlier neighbours is undecided or a representative becomes one.
+// The earliest undecided sequence always decides, so the loop ends (after as many rounds as
+// the longest chain of dependent decisions: a handful on real alignments) with exactly the
+// sequential answer.  The new representatives are appended in visiting order.
 __global__ void __launch_bounds__(1024) k_mis_resolve(const uint32_t *__restrict__ adj,
                                                       const uint8_t *__restrict__ alive8,
                                                       const int *__restrict__ order, int base,
@@ -266,70 +338,73 @@ __global__ void __launch_bounds__(1024) k_mis_resolve(const uint32_t *__restrict
                                                       int *__restrict__ clusters,
                                                       int *__restrict__ count)
 {
-    extern __shared__ uint32_t sm[];
-    uint32_t *s_adj = sm;                    // [32][MIS_NB]
-    int *s_ord = (int *)(sm + MIS_NB * 32);  // [MIS_NB]
-    uint8_t *s_alive = (uint8_t *)(s_ord + MIS_NB);  // [MIS_NB]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ngroups = (cnt + 31) >> 5;
-    // word w of sequence t only matters for w <= t/32: copy the lower triangle of groups
-    for (int w = warp; w < ngroups; w += 32)
-        for (int t = w * 32 + lane; t < cnt; t += 32) s_adj[w * MIS_NB + t] = adj[w * MIS_NB + t];
-    if (tid < cnt) {
-        s_ord[tid] = order[base + tid];
-        s_alive[tid] = alive8[tid];
+    __shared__ uint32_t s_in[32], s_und[32], s_pre[32];
+    const int t = threadIdx.x, lane = t & 31, g = t >> 5;
+    uint32_t a[32];
+#pragma unroll
+    for (int w = 0; w < 32; w++) a[w] = (w <= g && t < cnt) ? adj[w * MIS_NB + t] : 0u;
+    bool undec = t < cnt && alive8[t] != 0;
+    {
+        const uint32_t b = __ballot_sync(0xffffffffu, undec);
+        if (lane == 0) {
+            s_und[g] = b;
+            s_in[g] = 0;
+        }
     }
     __syncthreads();
-    if (warp != 0) return;
-    int c = *count;
-    uint32_t repw = 0;  // lane w: representatives of group w
-    for (int g = 0; g < ngroups; g++) {
-        const int t = g * 32 + lane;
-        bool undec = t < cnt && s_alive[t] != 0;
-        uint32_t killed = 0;
-        for (int w = 0; w < g; w++)
-            killed |= s_adj[w * MIS_NB + min(t, cnt - 1)] & __shfl_sync(0xffffffffu, repw, w);
-        undec = undec && killed == 0;
-        const uint32_t a = t < cnt ? s_adj[g * MIS_NB + t] : 0;  // bits of earlier lanes only
-        uint32_t reps = 0, und = __ballot_sync(0xffffffffu, undec);
-        while (und) {
-            const bool out = undec && (a & reps) != 0;
-            const bool in = undec && !out && (a & und) == 0;
-            const uint32_t nin = __ballot_sync(0xffffffffu, in);
-            const uint32_t nout = __ballot_sync(0xffffffffu, out);
-            reps |= nin;
-            und &= ~(nin | nout);
-            undec = undec && !in && !out;
+    for (;;) {
+        uint32_t hit = 0, wait = 0;
+#pragma unroll
+        for (int w = 0; w < 32; w++) {
+            hit |= a[w] & s_in[w];
+            wait |= a[w] & s_und[w];
         }
-        if ((reps >> lane) & 1u) {
-            const int v = s_ord[t];
-            if (clusters) clusters[c + __popc(reps & ((1u << lane) - 1u))] = v;
-            atomicOr(&rep[v >> 5], 1u << (v & 31));
+        const bool out = undec && hit != 0;
+        const bool in = undec && hit == 0 && wait == 0;
+        const uint32_t bi = __ballot_sync(0xffffffffu, in), bo = __ballot_sync(0xffffffffu, out);
+        undec = undec && !in && !out;
+        __syncthreads();  // every thread has read the masks of this round
+        if (lane == 0) {
+            s_in[g] |= bi;
+            s_und[g] &= ~(bi | bo);
         }
-        c += __popc(reps);
-        repw = lane == g ? reps : repw;
+        if (!__syncthreads_or(undec)) break;
     }
-    if (lane == 0) *count = c;
+    if (g == 0) {  // exclusive prefix of the representatives per group
+        const uint32_t c = __popc(s_in[lane]);
+        uint32_t x = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        s_pre[lane] = x - c;
+    }
+    __syncthreads();
+    const int c0 = *count;
+    const uint32_t mine = s_in[g];
+    if ((mine >> lane) & 1u) {
+        const int v = order[base + t];
+        if (clusters) clusters[c0 + s_pre[g] + __popc(mine & ((1u << lane) - 1u))] = v;
+        atomicOr(&rep[v >> 5], 1u << (v & 31));
+    }
+    __syncthreads();  // every thread has read *count
+    if (t == 0) *count = c0 + (int)(s_pre[31] + __popc(s_in[31]));
 }
 
 int mis_block() { return MIS_NB; }
 
-// Greedy clustering over the bit matrix in the given order; rep (W words), alive8
-// (MIS_NB bytes), adj (MIS_NB*32 words) and count (1 int) are scratch; rep and count must
-// be zero on entry.
-cudaError_t launch_greedy_clusters(const uint32_t *bits, int W, const int *order, int total,
+// Greedy clustering over the bit matrix (slab layout, n sequences) in the given order; rep
+// (4 * ceil(n / 128) words), alive8 (MIS_NB bytes), adj (MIS_NB * 32 words) and count (1 int)
+// are scratch; rep and count must be zero on entry.
+cudaError_t launch_greedy_clusters(const uint32_t *bits, int n, const int *order, int total,
                                    uint32_t *rep, uint8_t *alive8, uint32_t *adj, int *clusters,
                                    int *count, cudaStream_t stream)
 {
-    // per device, cheap: set on every call rather than tracking which devices have it
-    cudaError_t e = cudaFuncSetAttribute(k_mis_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         MIS_SMEM);
-    if (e != cudaSuccess) return e;
     for (int base = 0; base < total; base += MIS_NB) {
         const int cnt = min(MIS_NB, total - base);
-        k_mis_scan<<<(cnt + 7) / 8, 256, 0, stream>>>(bits, W, order, base, cnt, rep, alive8, adj);
-        k_mis_resolve<<<1, 1024, MIS_SMEM, stream>>>(adj, alive8, order, base, cnt, rep, clusters,
-                                                     count);
+        k_mis_scan<<<(cnt + 7) / 8, 256, 0, stream>>>(bits, n, order, base, cnt, rep, alive8, adj);
+        k_mis_resolve<<<1, 1024, 0, stream>>>(adj, alive8, order, base, cnt, rep, clusters, count);
     }
     return cudaGetLastError();
 }

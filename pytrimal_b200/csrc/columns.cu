@@ -6,11 +6,11 @@
 //
 // Both are one streaming pass over the n x L byte matrix -> HBM-bound.  The
 // column-count kernel reads 16 columns per thread per row (one 128-bit load,
-// 512 contiguous bytes per warp), compares the four 32-bit words byte-wise
-// and keeps 8-bit partial sums packed in registers that are widened every
-// 255 rows -- the same idea as the reference's u8 accumulators
-// (template.h:452-487) but flushed on the number of rows actually counted,
-// so masked rows cannot make a lane wrap.
+// 512 contiguous bytes per warp, eight rows in flight per thread), compares the
+// four 32-bit words byte-wise and keeps 8-bit partial sums packed in registers
+// that are widened before they can reach 255 -- the same idea as the reference's
+// u8 accumulators (template.h:452-487) but flushed on the number of rows actually
+// counted, so masked rows cannot make a lane wrap.
 #include "tcu_internal.cuh"
 
 namespace tcu {
@@ -21,19 +21,25 @@ __device__ __forceinline__ uint32_t byte_eq_ones(uint32_t x, uint32_t pat)
     return __vcmpeq4(x, pat) & 0x01010101u;
 }
 
-// grid.x covers column groups of 16 (blockDim.x threads each), grid.y strides
-// over rows.  TWO selects whether a second symbol is counted in the same pass.
+// One CTA = 32 column groups of 16 columns (512 columns, one warp-wide 512-byte row segment)
+// x CC_LANES row lanes; grid.x tiles the columns, grid.y cuts the rows into slices.  Each
+// thread streams its rows CC_UNROLL at a time (that many independent 16-byte loads in
+// flight), the row lanes are summed through shared memory and every CTA issues ONE atomic
+// per column.  TWO selects whether a second symbol is counted in the same pass.
+constexpr int CC_LANES = 8;
+constexpr int CC_UNROLL = 8;
+
 template <bool TWO>
-__global__ void __launch_bounds__(128) k_column_counts(const uint8_t *__restrict__ raw, int nseq,
-                                                       int ncol, size_t pitch,
-                                                       const uint8_t *__restrict__ row_drop,
-                                                       uint32_t pat_a, uint32_t pat_b,
-                                                       int *__restrict__ count_a,
-                                                       int *__restrict__ count_b)
+__global__ void __launch_bounds__(32 * CC_LANES) k_column_counts(
+    const uint8_t *__restrict__ raw, int nseq, int ncol, size_t pitch,
+    const uint8_t *__restrict__ row_drop, uint32_t pat_a, uint32_t pat_b, int rows_per_slice,
+    int *__restrict__ count_a, int *__restrict__ count_b, uint16_t *__restrict__ plane_a,
+    uint16_t *__restrict__ plane_b)
 {
-    const int group = blockIdx.x * blockDim.x + threadIdx.x;  // 16 columns
-    const int col0 = group * 16;
-    if (col0 >= ncol) return;
+    __shared__ int s_sum[TWO ? 2 : 1][CC_LANES][32 * 16 + 16];
+    const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int col0 = (blockIdx.x * 32 + lane) * 16;
+    const bool live = col0 < ncol;  // pitch is a multiple of 128: a live group is readable
 
     uint32_t acc_a[4] = {0, 0, 0, 0}, acc_b[4] = {0, 0, 0, 0};  // packed u8 partial sums
     int tot_a[16], tot_b[16];
@@ -55,47 +61,97 @@ __global__ void __launch_bounds__(128) k_column_counts(const uint8_t *__restrict
         pending = 0;
     };
 
-    for (int r = blockIdx.y; r < nseq; r += gridDim.y) {
-        if (row_drop && row_drop[r]) continue;  // warp-uniform
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(raw + (size_t)r * pitch + col0));
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    const int r_begin = blockIdx.y * rows_per_slice;
+    const int r_end = min(nseq, r_begin + rows_per_slice);
+    if (live) {
+        const uint8_t *base = raw + col0;
+        for (int r = r_begin + rl; r < r_end; r += CC_LANES * CC_UNROLL) {
+            uint4 v[CC_UNROLL];
+            bool use[CC_UNROLL];
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            acc_a[q] += byte_eq_ones(w[q], pat_a);
-            if (TWO) acc_b[q] += byte_eq_ones(w[q], pat_b);
+            for (int u = 0; u < CC_UNROLL; u++) {
+                const int rr = r + u * CC_LANES;
+                use[u] = rr < r_end && !(row_drop && row_drop[rr]);  // warp-uniform
+                v[u] = use[u] ? __ldg(reinterpret_cast<const uint4 *>(base + (size_t)rr * pitch))
+                              : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < CC_UNROLL; u++) {
+                if (!use[u]) continue;
+                const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                uint32_t bits_a = 0, bits_b = 0;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t ea = byte_eq_ones(w[q], pat_a);
+                    acc_a[q] += ea;
+                    // the four 0/1 bytes -> one nibble (bit k = column 4q + k): the product
+                    // lines byte k up at bit 24 + k
+                    if (TWO) bits_a |= ((ea * 0x01020408u) >> 24 & 0xFu) << (4 * q);
+                    if (TWO) {
+                        const uint32_t eb = byte_eq_ones(w[q], pat_b);
+                        acc_b[q] += eb;
+                        bits_b |= ((eb * 0x01020408u) >> 24 & 0xFu) << (4 * q);
+                    }
+                }
+                if (TWO && plane_a) {
+                    // one 16-column word per thread: 64 contiguous bytes per warp and plane
+                    const size_t o = (size_t)(r + u * CC_LANES) * (pitch >> 4) + (col0 >> 4);
+                    plane_a[o] = (uint16_t)bits_a;
+                    plane_b[o] = (uint16_t)bits_b;
+                }
+                pending++;
+            }
+            if (pending > 255 - CC_UNROLL) flush();
         }
-        if (++pending == 255) flush();
     }
     flush();
-
 #pragma unroll
     for (int i = 0; i < 16; i++) {
-        if (col0 + i < ncol) {
-            if (tot_a[i]) atomicAdd(&count_a[col0 + i], tot_a[i]);
-            if (TWO && tot_b[i]) atomicAdd(&count_b[col0 + i], tot_b[i]);
+        s_sum[0][rl][lane * 16 + i + (lane >> 1)] = tot_a[i];  // skewed: no 16-way bank conflict
+        if (TWO) s_sum[TWO ? 1 : 0][rl][lane * 16 + i + (lane >> 1)] = tot_b[i];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 512; c += 32 * CC_LANES) {
+        const int col = blockIdx.x * 512 + c;
+        if (col >= ncol) break;
+        const int idx = c + (c >> 5);  // (c / 16) >> 1 == c >> 5
+        int a = 0, b = 0;
+#pragma unroll
+        for (int l = 0; l < CC_LANES; l++) {
+            a += s_sum[0][l][idx];
+            if (TWO) b += s_sum[TWO ? 1 : 0][l][idx];
         }
+        if (a) atomicAdd(&count_a[col], a);
+        if (TWO && b) atomicAdd(&count_b[col], b);
     }
 }
 
-// count_a / count_b must be zeroed by the caller.  sym_b == sym_a -> single count.
+// count_a / count_b must be zeroed by the caller.  count_b == nullptr -> single count.
+// plane_a / plane_b (optional, with count_b): one bit per cell "byte == sym", rows of pitch / 8
+// bytes, bit k of a row = column k -- what the second pass of the spurious vector reads
+// instead of the bytes.
 cudaError_t launch_column_counts(const uint8_t *raw, int nseq, int ncol, size_t pitch,
                                  const uint8_t *row_drop, uint8_t sym_a, uint8_t sym_b,
-                                 int *count_a, int *count_b, int num_sms, cudaStream_t stream)
+                                 int *count_a, int *count_b, uint16_t *plane_a, uint16_t *plane_b,
+                                 int num_sms, cudaStream_t stream)
 {
     if (nseq == 0 || ncol == 0) return cudaSuccess;
-    const int groups = (ncol + 15) / 16;
-    const int gx = (groups + 127) / 128;
-    // enough row slices to fill the machine (8 CTAs of 128 threads per SM)
-    int gy = max(1, min(nseq, (num_sms * 8 + gx - 1) / gx));
-    gy = min(gy, 65535);
+    const int gx = (ncol + 511) / 512;
+    // about 4 CTAs (1024 threads) per SM; a slice is at least one unrolled pass of the lanes
+    int gy = max(1, (num_sms * 4 + gx - 1) / gx);
+    int rows_per_slice = max(CC_LANES * CC_UNROLL, (nseq + gy - 1) / gy);
+    gy = min(65535, (nseq + rows_per_slice - 1) / rows_per_slice);
+    rows_per_slice = (nseq + gy - 1) / gy;
     const uint32_t pa = 0x01010101u * sym_a, pb = 0x01010101u * sym_b;
     dim3 grid(gx, gy);
     if (count_b)
-        k_column_counts<true><<<grid, 128, 0, stream>>>(raw, nseq, ncol, pitch, row_drop, pa, pb,
-                                                        count_a, count_b);
+        k_column_counts<true><<<grid, 32 * CC_LANES, 0, stream>>>(
+            raw, nseq, ncol, pitch, row_drop, pa, pb, rows_per_slice, count_a, count_b, plane_a,
+            plane_b);
     else
-        k_column_counts<false><<<grid, 128, 0, stream>>>(raw, nseq, ncol, pitch, row_drop, pa, pb,
-                                                         count_a, count_b);
+        k_column_counts<false><<<grid, 32 * CC_LANES, 0, stream>>>(
+            raw, nseq, ncol, pitch, row_drop, pa, pb, rows_per_slice, count_a, count_b, nullptr,
+            nullptr);
     return cudaGetLastError();
 }
 
@@ -109,73 +165,98 @@ cudaError_t launch_column_counts(const uint8_t *raw, int nseq, int ncol, size_t 
 //               = cg - 1   if byte_i == '-'
 //               = cx - 1   if byte_i == indet
 // an integer identity, so the O(n^2 L) loop collapses to two streaming passes:
-// column counts (kernel above) then one pass per row testing
+// column counts (kernel above, which also leaves the '-' / indet bit planes of
+// the rows behind) then one pass per row over those planes testing
 // hits >= ovrlap (template.h:301-305) and the final ratio (:309).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_spurious_flags(int nseq, int ncol,
+// One warp per 32 columns: which classes reach `ovrlap` there, as three bit words
+// (residue / '-' / indet).  flag_words: 3 arrays of pitch / 32 words, fully written.
+__global__ void __launch_bounds__(256) k_spurious_flags(int nseq, int ncol, int nwords,
                                                         const int *__restrict__ cnt_gap,
                                                         const int *__restrict__ cnt_indet,
                                                         uint32_t ovrlap,
-                                                        uint8_t *__restrict__ col_flags)
+                                                        uint32_t *__restrict__ flag_words)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= ncol) return;
-    const int cg = cnt_gap[k], cx = cnt_indet[k];
-    const int ng = nseq - cg - cx;
-    uint8_t f = 0;
-    // a class with zero members is never looked up; guard the unsigned compare
-    if (ng >= 1 && (uint32_t)(ng - 1) >= ovrlap) f |= 1;
-    if (cg >= 1 && (uint32_t)(cg - 1) >= ovrlap) f |= 2;
-    if (cx >= 1 && (uint32_t)(cx - 1) >= ovrlap) f |= 4;
-    col_flags[k] = f;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= nwords) return;
+    const int k = w * 32 + lane;
+    bool fr = false, fg = false, fx = false;
+    if (k < ncol) {
+        const int cg = cnt_gap[k], cx = cnt_indet[k];
+        const int ng = nseq - cg - cx;
+        // a class with zero members is never looked up; guard the unsigned compare
+        fr = ng >= 1 && (uint32_t)(ng - 1) >= ovrlap;
+        fg = cg >= 1 && (uint32_t)(cg - 1) >= ovrlap;
+        fx = cx >= 1 && (uint32_t)(cx - 1) >= ovrlap;
+    }
+    const uint32_t br = __ballot_sync(0xffffffffu, fr), bg = __ballot_sync(0xffffffffu, fg);
+    const uint32_t bx = __ballot_sync(0xffffffffu, fx);
+    if (lane == 0) {
+        flag_words[w] = br;
+        flag_words[nwords + w] = bg;
+        flag_words[2 * nwords + w] = bx;
+    }
 }
 
-// one warp per row of [row_begin, row_end)
-__global__ void __launch_bounds__(256) k_spurious_rows(const uint8_t *__restrict__ raw,
+// Second pass, from the two bit planes the column-count pass left behind (1/4 of the bytes):
+// one warp per row of [row_begin, row_end), grid-stride; per 32 columns
+//     popc(~G & ~X & F_residue) + popc(G & F_gap) + popc(X & F_indet)
+// columns pass (template.h:301-305), then the ratio (:309).  Padding columns have G = X = 0
+// and F_residue = 0.
+constexpr int SP_SMEM_WORDS = 1024;  // flag words kept in shared memory (32 768 columns)
+
+template <bool SMEM>
+__global__ void __launch_bounds__(256) k_spurious_rows(const uint32_t *__restrict__ plane_gap,
+                                                       const uint32_t *__restrict__ plane_indet,
                                                        int row_begin, int row_end, int ncol,
-                                                       size_t pitch, uint8_t indet,
-                                                       const uint8_t *__restrict__ col_flags,
+                                                       int nwords,
+                                                       const uint32_t *__restrict__ flag_words,
                                                        float *__restrict__ out)
 {
-    const int warp = row_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31;
-    if (warp >= row_end) return;
-    const uint8_t *row = raw + (size_t)warp * pitch;
-    uint32_t good = 0;
-    // 4 columns per lane per step: 128 contiguous bytes per warp
-    for (int k = lane * 4; k < ncol; k += 128) {
-        const uint32_t v = *reinterpret_cast<const uint32_t *>(row + k);
-        const uint32_t f = *reinterpret_cast<const uint32_t *>(col_flags + k);
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-            if (k + b < ncol) {
-                const uint32_t c = (v >> (8 * b)) & 0xFF;
-                const uint32_t fl = (f >> (8 * b)) & 0xFF;
-                const uint32_t bit = c == '-' ? 2u : (c == indet ? 4u : 1u);
-                good += (fl & bit) != 0;
-            }
-        }
+    __shared__ uint32_t s_flags[SMEM ? 3 * SP_SMEM_WORDS : 1];
+    if (SMEM) {
+        for (int k = threadIdx.x; k < 3 * nwords; k += 256) s_flags[k] = flag_words[k];
+        __syncthreads();
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) good += __shfl_xor_sync(0xffffffffu, good, o);
-    if (lane == 0) out[warp] = __fdiv_rn((float)good, (float)ncol);
+    const uint32_t *fl = SMEM ? s_flags : flag_words;
+    const int lane = threadIdx.x & 31;
+    const int warps = gridDim.x * 8;
+    for (int row = row_begin + blockIdx.x * 8 + (threadIdx.x >> 5); row < row_end; row += warps) {
+        const uint32_t *g = plane_gap + (size_t)row * nwords;
+        const uint32_t *x = plane_indet + (size_t)row * nwords;
+        uint32_t good = 0;
+        for (int k = lane; k < nwords; k += 32) {
+            const uint32_t G = __ldg(g + k), X = __ldg(x + k);
+            good += __popc(~G & ~X & fl[k]) + __popc(G & fl[nwords + k]) +
+                    __popc(X & fl[2 * nwords + k]);
+        }
+        good = __reduce_add_sync(0xffffffffu, good);
+        if (lane == 0) out[row] = __fdiv_rn((float)good, (float)ncol);
+    }
 }
 
-// col_flags: scratch of at least roundup(ncol, 4) bytes.  The column counts cover all
-// nseq rows; out[row_begin .. row_end) is written (a rank's share of the rows).
-cudaError_t launch_spurious_rows(const uint8_t *raw, int nseq, int row_begin, int row_end,
-                                 int ncol, size_t pitch, uint8_t indet, const int *cnt_gap,
-                                 const int *cnt_indet, uint32_t ovrlap, uint8_t *col_flags,
-                                 float *out, cudaStream_t stream)
+// flag_words: scratch of 3 * pitch / 32 words.  The column counts cover all nseq rows; the
+// planes and out[row_begin .. row_end) cover a rank's share of the rows (plane row r is at
+// (r - 0) * pitch / 8 bytes: the planes are indexed by absolute row).
+cudaError_t launch_spurious_rows(const uint32_t *plane_gap, const uint32_t *plane_indet, int nseq,
+                                 int row_begin, int row_end, int ncol, size_t pitch,
+                                 const int *cnt_gap, const int *cnt_indet, uint32_t ovrlap,
+                                 uint32_t *flag_words, float *out, int num_sms, cudaStream_t stream)
 {
     if (nseq == 0 || ncol == 0) return cudaSuccess;
-    k_spurious_flags<<<(ncol + 255) / 256, 256, 0, stream>>>(nseq, ncol, cnt_gap, cnt_indet,
-                                                             ovrlap, col_flags);
+    const int nwords = (int)(pitch >> 5);
+    k_spurious_flags<<<(nwords * 32 + 255) / 256, 256, 0, stream>>>(nseq, ncol, nwords, cnt_gap,
+                                                                    cnt_indet, ovrlap, flag_words);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || row_end <= row_begin) return e;
-    const long long threads = (long long)(row_end - row_begin) * 32;
-    k_spurious_rows<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
-        raw, row_begin, row_end, ncol, pitch, indet, col_flags, out);
+    const int rows = row_end - row_begin;
+    const int grid = min((rows + 7) / 8, num_sms * 8);
+    if (nwords <= SP_SMEM_WORDS)
+        k_spurious_rows<true><<<grid, 256, 0, stream>>>(plane_gap, plane_indet, row_begin, row_end,
+                                                        ncol, nwords, flag_words, out);
+    else
+        k_spurious_rows<false><<<grid, 256, 0, stream>>>(plane_gap, plane_indet, row_begin, row_end,
+                                                         ncol, nwords, flag_words, out);
     return cudaGetLastError();
 }
 

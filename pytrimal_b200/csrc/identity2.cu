@@ -402,6 +402,41 @@ __global__ void __launch_bounds__(ID2_THREADS, NP <= 5 ? 2 : 1) k_identity2(cons
             }
             __syncwarp();
 
+            if (p.bits_out != nullptr) {
+                // threshold mode (Cleaner.cpp:1435-1440: a pair joins two sequences iff
+                // identity > threshold): the same division, but only its comparison with the
+                // threshold leaves the SM.  ballot(a, b) holds bit (i = li + 4a, j = lj + 8b)
+                // of the patch at lane position li + 4 lj; lane c assembles the word of patch
+                // column c (sequence j0 + c against the 32 sequences i0 ..): nibble c % 8 of
+                // the ballots with b = c / 8, one nibble per a.  Patches below the diagonal
+                // hold no pair j > i and store zeros (the mirror pass fills them).
+                const int i0 = BI * IB + 32 * wi, j0 = bj * RB + 32 * wj;
+                uint32_t colword = 0;
+                if (j0 + 31 > i0) {
+#pragma unroll
+                    for (int a = 0; a < 8; a++) {
+                        const int i = i0 + li + 4 * a;
+                        uint32_t mine = 0;
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            const int j = j0 + lj + 8 * b;
+                            const int h = !PACKED ? (int)hit[a][b]
+                                                  : (b < 2 ? (int)(hit[a][b] & 0xFFFFu)
+                                                           : (int)(hit[a][b - 2] >> 16));
+                            const int d = p.total_bits - (int)patch[(li + 4 * a) * ID2_XS + lj + 8 * b];
+                            const float v = d == 0 ? 0.0f : __fdiv_rn((float)h, (float)d);
+                            const bool bit = i < p.nk && j < p.nk && j > i && v > p.thr;
+                            const uint32_t w = __ballot_sync(0xffffffffu, bit);
+                            if ((lane >> 3) == b) mine = w;
+                        }
+                        colword |= ((mine >> (4 * (lane & 7))) & 0xFu) << (4 * a);
+                    }
+                }
+                const int j = j0 + lane;
+                if (j < p.nk) p.bits_out[bits_word_index(p.nk, j, 4 * BI + wi)] = colword;
+                __syncwarp();  // the patch is rewritten by the next tile
+                continue;
+            }
 #pragma unroll
             for (int a = 0; a < 8; a++) {
                 const int il = 64 * half + rowA0 + 4 * a;  // row inside the super-block

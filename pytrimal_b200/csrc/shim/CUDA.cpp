@@ -3,6 +3,7 @@
 // C ABI of libtrimal_cuda.  Error convention: never throw; report
 // through debug.report(...) and return false / leave zero-filled outputs.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -49,32 +50,54 @@ int cudaPlatformDeviceCount() { return tcu_device_count(); }
 
 CUDAContext::~CUDAContext()
 {
-  std::lock_guard<std::mutex> lk(g_ctx_mutex);
-  auto it = g_contexts.find(rows_key);
-  if (it != g_contexts.end() && it->second.expired()) g_contexts.erase(it);
-  tcu_msa_destroy(handle);
+  {
+    std::lock_guard<std::mutex> lk(g_ctx_mutex);
+    auto it = g_contexts.find(rows_key);
+    if (it != g_contexts.end() && it->second.expired()) g_contexts.erase(it);
+  }
+  tcu_msa_destroy(handle);  // waits for the device: outside the table's lock
+}
+
+IdentityShare::IdentityShare() : id([] {
+  static std::atomic<uint64_t> next{1};
+  return next.fetch_add(1);
+}())
+{
 }
 
 std::shared_ptr<CUDAContext> CUDAContext::acquire(Alignment *alig)
 {
   const void *key = alig->sequences;
+  // this alignment's manager already owns the upload of these rows
+  if (alig->Statistics->cudaContext) {
+    auto sp = std::static_pointer_cast<CUDAContext>(alig->Statistics->cudaContext);
+    if (sp->rows_key == key) return sp;
+    alig->Statistics->cudaContext.reset();
+  }
   {
+    // an alignment sharing the same rows (the source of a copy, or a copy) does
     std::lock_guard<std::mutex> lk(g_ctx_mutex);
     auto it = g_contexts.find(key);
     if (it != g_contexts.end())
-      if (auto sp = it->second.lock()) return sp;
+      if (auto sp = it->second.lock()) {
+        alig->Statistics->cudaContext = sp;
+        return sp;
+      }
   }
   const int n = alig->originalNumberOfSequences, L = alig->originalNumberOfResidues;
   std::vector<const char *> rows((size_t)n);
   for (int i = 0; i < n; i++) rows[i] = alig->sequences[i].data();
   tcu_msa *h = nullptr;
-  if (tcu_msa_create(rows.data(), n, L, /*device=*/0, &h) != TCU_OK) {
+  // TCU_DEVICE_AUTO: the device set of tcu_set_devices / TRIMAL_CUDA_DEVICES (device 0 by
+  // default; several GPUs of the box when the user names them)
+  if (tcu_msa_create(rows.data(), n, L, TCU_DEVICE_AUTO, &h) != TCU_OK) {
     report_failure("CUDA platform: alignment upload failed");
     return nullptr;
   }
   auto sp = std::make_shared<CUDAContext>();
   sp->handle = h;
   sp->rows_key = key;
+  alig->Statistics->cudaContext = sp;
   std::lock_guard<std::mutex> lk(g_ctx_mutex);
   g_contexts[key] = sp;
   return sp;
@@ -159,7 +182,7 @@ void CUDAGaps::CalculateVectors()
   const int L = alig->originalNumberOfResidues;
   // valid output even on failure: Cleaner keeps running after a void override
   memset(gapsInColumn, 0, sizeof(int) * L);
-  if (!ctx) ctx = CUDAContext::acquire(alig);
+  std::shared_ptr<CUDAContext> ctx = CUDAContext::acquire(alig);
   if (!ctx) return;
   std::lock_guard<std::recursive_mutex> lk(ctx->mutex);
   if (tcu_gaps(ctx->handle, alig->saveSequences, gapsInColumn, numColumnsWithGaps, &maxGaps) !=
@@ -208,7 +231,6 @@ CUDAIdentity::CUDAIdentity(Alignment *parent, Identity *parentIdentity)
 {
   if (auto *mold = dynamic_cast<CUDAIdentity *>(parentIdentity)) {
     share = mold->share;
-    ctx = mold->ctx;
   } else {
     share = std::make_shared<IdentityShare>();
     share->host = identities;
@@ -246,7 +268,7 @@ void CUDAIdentity::computeToHost()
   const int n = alig->originalNumberOfSequences;
   const size_t size = ((float)n * n + n) / 2;
   if (!allocateHost()) return;
-  if (!ctx) ctx = CUDAContext::acquire(alig);
+  std::shared_ptr<CUDAContext> ctx = CUDAContext::acquire(alig);
   int kept = 0;
   for (int i = 0; i < n; i++) kept += alig->saveSequences[i] != -1;
   const int keep_on_device = kept == n;
@@ -257,11 +279,11 @@ void CUDAIdentity::computeToHost()
                            identities, nullptr, nullptr, keep_on_device) != TCU_OK) {
     if (ctx) {
       report_failure("CUDA platform: identity statistic failed");
-      ctx->ident_owner = nullptr;
+      ctx->ident_owner = 0;
     }
     memset(identities, 0, sizeof(float) * size);
   } else {
-    ctx->ident_owner = keep_on_device ? share.get() : nullptr;
+    ctx->ident_owner = keep_on_device ? share->id : 0;
   }
   std::lock_guard<std::mutex> sl(share->mutex);
   share->host = identities;
@@ -278,11 +300,11 @@ void CUDAIdentity::calculateSeqIdentity()
 bool CUDAIdentity::computeOnDevice()
 {
   if (!all_rows_kept(alig)) return false;
-  if (!ctx) ctx = CUDAContext::acquire(alig);
+  std::shared_ptr<CUDAContext> ctx = CUDAContext::acquire(alig);
   if (!ctx) return false;
   const char indet = indet_of(alig);  // before the lock: type detection may use the handle
   std::lock_guard<std::recursive_mutex> lk(ctx->mutex);
-  if (ctx->ident_owner == share.get() && tcu_identity_resident(ctx->handle)) return true;
+  if (ctx->ident_owner == share->id && tcu_identity_resident(ctx->handle)) return true;
   {
     // a host copy without a device copy: let the reference code walk the host array
     std::lock_guard<std::mutex> sl(share->mutex);
@@ -291,10 +313,10 @@ bool CUDAIdentity::computeOnDevice()
   if (tcu_identity(ctx->handle, alig->saveSequences, alig->saveResidues, indet, nullptr,
                    nullptr, nullptr, /*keep_on_device=*/1) != TCU_OK) {
     report_failure("CUDA platform: identity statistic failed");
-    ctx->ident_owner = nullptr;
+    ctx->ident_owner = 0;
     return false;
   }
-  ctx->ident_owner = share.get();
+  ctx->ident_owner = share->id;
   return true;
 }
 
@@ -308,9 +330,9 @@ void CUDAIdentity::materialize()
       return;
     }
   }
-  if (ctx) {
+  if (std::shared_ptr<CUDAContext> ctx = CUDAContext::acquire(alig)) {
     std::unique_lock<std::recursive_mutex> lk(ctx->mutex);
-    if (ctx->ident_owner == share.get() && tcu_identity_resident(ctx->handle)) {
+    if (ctx->ident_owner == share->id && tcu_identity_resident(ctx->handle)) {
       if (!allocateHost()) return;
       if (tcu_identity_download(ctx->handle, identities) == TCU_OK) {
         std::lock_guard<std::mutex> sl(share->mutex);
@@ -336,8 +358,9 @@ void cudaMaterializeIdentity(Identity *identity)
 // ---------------------------------------------------------------------------
 namespace {
 
-// the CUDAIdentity of `alig` with its matrix resident on the device, or nullptr
-CUDAIdentity *device_identity(Alignment *alig)
+// the CUDAIdentity of `alig` with its matrix resident on the device (and the upload it is
+// resident on), or nullptr
+CUDAIdentity *device_identity(Alignment *alig, std::shared_ptr<CUDAContext> &ctx)
 {
   if (!all_rows_kept(alig)) return nullptr;
   {
@@ -346,7 +369,8 @@ CUDAIdentity *device_identity(Alignment *alig)
   }
   auto *ci = dynamic_cast<CUDAIdentity *>(alig->Statistics->identity);
   if (ci == nullptr || !ci->computeOnDevice()) return nullptr;
-  return ci;
+  ctx = CUDAContext::acquire(alig);
+  return ctx ? ci : nullptr;
 }
 
 // visiting order of the clustering walks (Cleaner.cpp:1413-1426 / 1078-1089)
@@ -364,13 +388,14 @@ bool cluster_order(CUDAContext &ctx, int n, std::vector<int> &order)
 bool cudaSelectMethod(Alignment *alig, int *method)
 {
   StartTiming("bool cudaSelectMethod(Alignment *, int *) ");
-  CUDAIdentity *ci = device_identity(alig);
+  std::shared_ptr<CUDAContext> ctx;
+  CUDAIdentity *ci = device_identity(alig, ctx);
   if (ci == nullptr) return false;
   const int n = alig->numberOfSequences;
   std::vector<float> rowMax((size_t)n), rowSum((size_t)n);
   {
-    std::lock_guard<std::recursive_mutex> lk(ci->ctx->mutex);
-    if (tcu_identity_row_stats(ci->ctx->handle, /*upper_only=*/0, rowMax.data(), nullptr,
+    std::lock_guard<std::recursive_mutex> lk(ctx->mutex);
+    if (tcu_identity_row_stats(ctx->handle, /*upper_only=*/0, rowMax.data(), nullptr,
                                rowSum.data()) != TCU_OK) {
       report_failure("CUDA platform: identity row statistics failed");
       return false;
@@ -394,13 +419,14 @@ bool cudaSelectMethod(Alignment *alig, int *method)
 bool cudaCutPointClusters(Alignment *alig, int clusterNumber, float *cut)
 {
   StartTiming("bool cudaCutPointClusters(Alignment *, int, float *) ");
-  CUDAIdentity *ci = device_identity(alig);
+  std::shared_ptr<CUDAContext> ctx;
+  CUDAIdentity *ci = device_identity(alig, ctx);
   if (ci == nullptr) return false;
   const int n = alig->numberOfSequences;
   std::vector<float> rowMax((size_t)n), rowMin((size_t)n), rowSum((size_t)n);
   {
-    std::lock_guard<std::recursive_mutex> lk(ci->ctx->mutex);
-    if (tcu_identity_row_stats(ci->ctx->handle, /*upper_only=*/1, rowMax.data(), rowMin.data(),
+    std::lock_guard<std::recursive_mutex> lk(ctx->mutex);
+    if (tcu_identity_row_stats(ctx->handle, /*upper_only=*/1, rowMax.data(), rowMin.data(),
                                rowSum.data()) != TCU_OK) {
       report_failure("CUDA platform: identity row statistics failed");
       return false;
@@ -420,7 +446,7 @@ bool cudaCutPointClusters(Alignment *alig, int clusterNumber, float *cut)
   if (pairs > 0) startingPoint /= pairs;
 
   std::vector<int> order;
-  if (!cluster_order(*ci->ctx, n, order)) {
+  if (!cluster_order(*ctx, n, order)) {
     report_failure("CUDA platform: clustering order failed");
     return false;
   }
@@ -429,8 +455,8 @@ bool cudaCutPointClusters(Alignment *alig, int clusterNumber, float *cut)
   for (;;) {
     int clusterNum = 0;
     {
-      std::lock_guard<std::recursive_mutex> lk(ci->ctx->mutex);
-      if (tcu_identity_clusters(ci->ctx->handle, order.data(), n, startingPoint, nullptr,
+      std::lock_guard<std::recursive_mutex> lk(ctx->mutex);
+      if (tcu_identity_clusters(ctx->handle, order.data(), n, startingPoint, nullptr,
                                 &clusterNum) != TCU_OK) {
         report_failure("CUDA platform: clustering failed");
         return false;
@@ -457,36 +483,33 @@ int *cudaRepresentativeSeq(Alignment *alig, float maximumIdent)
   const int n = alig->originalNumberOfSequences;
   std::shared_ptr<CUDAContext> ctx = CUDAContext::acquire(alig);
   if (!ctx) return nullptr;
-  // lengths first (one small kernel); the host-side sort of the visiting order then runs
-  // on another thread while the device computes the identity matrix
-  std::vector<int> lengths((size_t)n), order((size_t)n);
-  {
-    std::lock_guard<std::recursive_mutex> lk(ctx->mutex);
-    if (tcu_sequence_lengths(ctx->handle, lengths.data()) != TCU_OK) {
-      report_failure("CUDA platform: sequence lengths failed");
-      return nullptr;
-    }
-  }
-  int sort_rc = TCU_OK;
-  std::thread sorter;
-  try {
-    sorter = std::thread([&]() { sort_rc = tcu_cluster_order(lengths.data(), n, order.data()); });
-  } catch (...) {
-    sort_rc = tcu_cluster_order(lengths.data(), n, order.data());
-  }
-  CUDAIdentity *ci = device_identity(alig);
-  if (sorter.joinable()) sorter.join();
-  if (ci == nullptr || sort_rc != TCU_OK) return nullptr;
   // Cleaner.cpp:1435-1440: a hit needs identity > maximumIdent AND > max (0 at first)
   const float threshold = maximumIdent < 0 ? 0 : maximumIdent;
+  const char indet = indet_of(alig);  // before the lock: type detection may use the handle
   std::vector<int> reps((size_t)n);
   int count = 0;
   {
-    std::lock_guard<std::recursive_mutex> lk(ci->ctx->mutex);
-    if (tcu_identity_clusters(ci->ctx->handle, order.data(), n, threshold, reps.data(), &count) !=
-        TCU_OK) {
-      report_failure("CUDA platform: clustering failed");
-      return nullptr;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mutex);
+    auto *cid = dynamic_cast<CUDAIdentity *>(alig->Statistics->identity);
+    if (cid != nullptr && ctx->ident_owner == cid->share->id && tcu_identity_resident(ctx->handle)) {
+      // this alignment's matrix is already on the device (an earlier statistic or walk left
+      // it there): threshold and walk it
+      std::vector<int> order;
+      if (!cluster_order(*ctx, n, order) ||
+          tcu_identity_clusters(ctx->handle, order.data(), n, threshold, reps.data(), &count) != TCU_OK) {
+        report_failure("CUDA platform: clustering failed");
+        return nullptr;
+      }
+    } else {
+      // the walk only compares identities with the threshold: one call, the identity kernel
+      // emits one bit per pair and no float matrix exists anywhere (and none is left behind:
+      // the operand is repacked, whatever was resident is gone)
+      ctx->ident_owner = 0;
+      if (tcu_representatives(ctx->handle, alig->saveResidues, (uint8_t)indet, threshold, reps.data(),
+                              &count) != TCU_OK) {
+        report_failure("CUDA platform: clustering failed");
+        return nullptr;
+      }
     }
   }
   int *repres = new (std::nothrow) int[count + 1];  // freed by the caller (Cleaner.cpp:1201)
@@ -502,7 +525,7 @@ bool CUDAOverlap::calculateSpuriousVector(float overlap, float *spuriousVector)
   if (spuriousVector == nullptr) return false;  // template.h:210-211
   const uint32_t ovrlap =
       uint32_t(ceil(overlap * float(alig->originalNumberOfSequences - 1)));  // template.h:217-218
-  if (!ctx) ctx = CUDAContext::acquire(alig);
+  std::shared_ptr<CUDAContext> ctx = CUDAContext::acquire(alig);
   if (!ctx) return false;
   const char indet = indet_of(alig);  // before the lock: type detection may use the handle
   std::lock_guard<std::recursive_mutex> lk(ctx->mutex);
@@ -555,14 +578,14 @@ bool CUDASimilarity::calculateVectors(bool cutByGap)
   const int L = alig->originalNumberOfResidues;
   std::vector<float> num((size_t)L), den((size_t)L);
   int err_col = -1, err_row = -1, err_byte = 0;
-  if (!ctx) ctx = CUDAContext::acquire(alig);
+  std::shared_ptr<CUDAContext> ctx = CUDAContext::acquire(alig);
   if (!ctx) return false;
   const char indet = indet_of(alig);  // before the lock: type detection may use the handle
   std::unique_lock<std::recursive_mutex> lk(ctx->mutex);
   // a CUDAIdentity leaves its result on the device; identities computed by any
   // other platform (or whose device copy was replaced) are uploaded from the host
   auto *cid = dynamic_cast<CUDAIdentity *>(alig->Statistics->identity);
-  const bool on_device = cid != nullptr && ctx->ident_owner == cid->share.get() &&
+  const bool on_device = cid != nullptr && ctx->ident_owner == cid->share->id &&
                          tcu_identity_resident(ctx->handle);
   const float *identities = nullptr;
   if (!on_device) {
@@ -575,7 +598,7 @@ bool CUDASimilarity::calculateVectors(bool cutByGap)
                           gapThreshold, on_device ? nullptr : identities, num.data(), den.data(),
                           MDK, &err_col, &err_row, &err_byte);
   // an uploaded matrix replaces whatever was resident
-  if (!on_device) ctx->ident_owner = cid != nullptr ? cid->share.get() : nullptr;
+  if (!on_device) ctx->ident_owner = cid != nullptr ? cid->share->id : 0;
   if (rc == TCU_ERR_INCORRECT_SYMBOL) {  // template.h:135-138
     debug.report(ErrorCode::IncorrectSymbol, new std::string[1]{std::string(1, (char)err_byte)});
     return false;

@@ -7,6 +7,7 @@
 #ifndef TRIMAL_PLATFORM_CUDA_H
 #define TRIMAL_PLATFORM_CUDA_H
 
+#include <cstdint>
 #include <memory>
 #include <mutex>
 
@@ -19,9 +20,12 @@ struct tcu_msa;
 
 namespace statistics {
 
-// One uploaded alignment, shared by the four statistics of an Alignment and by
-// the copies the mold constructors make (rows are shared read-only between
-// copies through Alignment::SeqRef, so the device copy can be too).
+// One uploaded alignment.  It is owned by the statistics::Manager of every Alignment that
+// used it (Manager::cudaContext, patches/Manager.h.patch) and found by the others that share
+// the same rows (Alignment copies share `sequences` read-only through SeqRef) through a
+// table of weak references -- so the device memory lives exactly as long as an alignment
+// that computed on it, and the copies a trim() returns (fresh mold copies that never
+// compute) pin nothing.
 class CUDAContext {
 public:
   // Returns the handle for `alig`'s rows, uploading on first use; nullptr
@@ -33,15 +37,18 @@ public:
   // a tcu_msa handle serves one thread at a time; recursive because a statistic may ask for
   // the alignment type (another user of the handle) while it holds the lock
   std::recursive_mutex mutex;
-  // Which group of CUDAIdentity objects (IdentityShare*) the identity matrix resident on
-  // the device belongs to; nullptr = none.  Alignment copies share the upload but may
-  // carry different identity objects (different column masks).
-  const void *ident_owner = nullptr;
+  // Which group of CUDAIdentity objects (IdentityShare::id) the identity matrix resident on
+  // the device belongs to; 0 = none.  Alignment copies share the upload but may carry
+  // different identity objects (different column masks).  Ids are never reused, so a group
+  // that died cannot be mistaken for a new one at the same address.
+  uint64_t ident_owner = 0;
 };
 
 // State shared by a CUDAIdentity and the copies the mold constructor makes of it (the
 // base class shares `identities` and `refCounter` the same way, Identity.cpp:50-58).
 struct IdentityShare {
+  IdentityShare();
+  const uint64_t id;  // process-wide unique, never 0
   std::mutex mutex;
   float *host = nullptr;  // the packed matrix on the host once something asked for it
 };
@@ -52,7 +59,6 @@ public:
   CUDASimilarity(Alignment *parentAlignment, Similarity *parentSimilarity)
       : Similarity(parentAlignment, parentSimilarity) {}
   bool calculateVectors(bool cutByGap) override;
-  std::shared_ptr<CUDAContext> ctx;  // keeps the upload alive between calls
 };
 
 class CUDAGaps : public Gaps {
@@ -60,7 +66,6 @@ public:
   CUDAGaps(Alignment *parentAlignment) : Gaps(parentAlignment) {}
   CUDAGaps(Alignment *parentAlignment, Gaps *parentGaps) : Gaps(parentAlignment, parentGaps) {}
   void CalculateVectors() override;
-  std::shared_ptr<CUDAContext> ctx;
 };
 
 class CUDAOverlap : public Overlap {
@@ -68,7 +73,6 @@ public:
   CUDAOverlap(Alignment *parent) : Overlap(parent) {}
   CUDAOverlap(Alignment *parent, Overlap *parentOverlap) : Overlap(parent, parentOverlap) {}
   bool calculateSpuriousVector(float overlap, float *spuriousVector) override;
-  std::shared_ptr<CUDAContext> ctx;
 };
 
 // The identity matrix may live on the device only: Cleaner's three walks over it
@@ -89,7 +93,6 @@ public:
   bool computeOnDevice();
   // Make `identities` a valid host array (download, or compute as a last resort).
   void materialize();
-  std::shared_ptr<CUDAContext> ctx;
   std::shared_ptr<IdentityShare> share;
 
 private:

@@ -78,7 +78,30 @@ struct Identity2Params {
     int nchunks;             // 128-column chunks
     int nk;                  // kept rows
     int total_bits;          // nchunks * 128
+    // threshold mode (bits_out != nullptr): instead of the ratios, identity > thr as one bit per
+    // pair in the slab layout below; out / hit_out / dst_out are not touched
+    uint32_t *bits_out;
+    float thr;
 };
+
+// ---------------------------------------------------------------------------
+// Threshold bit matrix ("is identity(i, j) > thr"), symmetric, nk x nk bits, stored in slabs
+// of 128 columns:  word (row r, 32-column word w)  at  ((w / 4) * nk + r) * 4 + (w % 4),
+// i.e. slab s = [nk rows][4 words] holds every sequence's bits against the sequences
+// 128 s .. 128 s + 127.  A row-block band of the pair matrix (what one GPU owns) is a
+// contiguous run of slabs, so the bands of several GPUs concatenate without a strided
+// copy.  K1 writes, for the pairs i < j it owns, the bits of row j against the earlier
+// sequences i ("column words"); k_bits_symmetrize then mirrors every 128 x 128 block.
+// ---------------------------------------------------------------------------
+__host__ __device__ inline size_t bits_slab_words(int nk) { return (size_t)nk * 4; }
+__host__ __device__ inline size_t bits_word_index(int nk, int row, int w)
+{
+    return ((size_t)(w >> 2) * (size_t)nk + (size_t)row) * 4 + (size_t)(w & 3);
+}
+__host__ __device__ inline size_t bits_total_words(int nk)
+{
+    return (size_t)((nk + 127) / 128) * bits_slab_words(nk);
+}
 
 // tiles in super-block rows < sb: each super-block BI pairs with J blocks 2*BI .. nb-1
 __host__ __device__ inline long long tiles_before2(long long sb, long long nb)
@@ -146,11 +169,12 @@ cudaError_t launch_identity_bytes(const uint8_t *raw, size_t pitch, int ncol, co
                                   int *hit_out, int *dst_out, cudaStream_t stream);
 cudaError_t launch_column_counts(const uint8_t *raw, int nseq, int ncol, size_t pitch,
                                  const uint8_t *row_drop, uint8_t sym_a, uint8_t sym_b,
-                                 int *count_a, int *count_b, int num_sms, cudaStream_t stream);
-cudaError_t launch_spurious_rows(const uint8_t *raw, int nseq, int row_begin, int row_end,
-                                 int ncol, size_t pitch, uint8_t indet, const int *cnt_gap,
-                                 const int *cnt_indet, uint32_t ovrlap, uint8_t *col_flags,
-                                 float *out, cudaStream_t stream);
+                                 int *count_a, int *count_b, uint16_t *plane_a, uint16_t *plane_b,
+                                 int num_sms, cudaStream_t stream);
+cudaError_t launch_spurious_rows(const uint32_t *plane_gap, const uint32_t *plane_indet, int nseq,
+                                 int row_begin, int row_end, int ncol, size_t pitch,
+                                 const int *cnt_gap, const int *cnt_indet, uint32_t ovrlap,
+                                 uint32_t *flag_words, float *out, int num_sms, cudaStream_t stream);
 cudaError_t launch_sim_codes(const uint8_t *raw, int nseq, int ncol, size_t pitch, int npad,
                              const uint8_t *lut256, const uint8_t *col_skip, uint8_t *codesT,
                              unsigned long long *first_error, cudaStream_t stream);
@@ -168,12 +192,13 @@ cudaError_t launch_row_lengths(const uint8_t *raw, int nseq, int ncol, size_t pi
                                cudaStream_t stream);
 
 // consumers of the device-resident identity matrix (clusters.cu)
-cudaError_t launch_identity_bits(const float *id, int n, int W, float thr, uint32_t *bits,
-                                 int row_begin, int row_end, cudaStream_t stream);
+cudaError_t launch_identity_bits(const float *id, int n, float thr, uint32_t *bits, int row_begin,
+                                 int row_end, cudaStream_t stream);
+cudaError_t launch_bits_symmetrize(uint32_t *bits, int n, cudaStream_t stream);
 cudaError_t launch_row_stats(const float *id, int n, bool upper_only, float *row_max,
                              float *row_min, float *row_sum, cudaStream_t stream);
 int mis_block();
-cudaError_t launch_greedy_clusters(const uint32_t *bits, int W, const int *order, int total,
+cudaError_t launch_greedy_clusters(const uint32_t *bits, int n, const int *order, int total,
                                    uint32_t *rep, uint8_t *alive8, uint32_t *adj, int *clusters,
                                    int *count, cudaStream_t stream);
 

@@ -102,14 +102,39 @@ def shard_blocks(kept_rows, rank, world):
     return a.value, b.value
 
 
+DEVICE_AUTO = -1
+
+
+def set_devices(devices=None):
+    """``tcu_set_devices``: the GPUs that ``DeviceAlignment(..., device="auto")`` handles are
+    replicated on (one process driving several GPUs); ``None`` goes back to the environment
+    variable ``TRIMAL_CUDA_DEVICES`` / device 0."""
+    lib = _lib.load()
+    if not devices:
+        _lib.check(lib.tcu_set_devices(None, 0))
+        return
+    arr = (C.c_int * len(devices))(*devices)
+    _lib.check(lib.tcu_set_devices(arr, len(devices)))
+
+
+def get_devices():
+    lib = _lib.load()
+    arr = (C.c_int * 64)()
+    k = lib.tcu_get_devices(arr, 64)
+    return list(arr[:k])
+
+
 class DeviceAlignment:
-    """One alignment uploaded to one GPU (wraps a ``tcu_msa`` handle).
+    """One alignment uploaded to one GPU -- or, with ``device="auto"``, replicated over the
+    configured device set (wraps a ``tcu_msa`` handle).
 
     Every statistic takes ``comm=``: with a :class:`Communicator` the ``tcu_*_all``
     entry point is used (each rank computes its share, NCCL exchanges the shares,
     every rank returns the complete result)."""
 
     def __init__(self, alignment, device=0):
+        if device == "auto":
+            device = DEVICE_AUTO
         if not isinstance(alignment, Alignment):
             alignment = Alignment.from_matrix(np.asarray(alignment, np.uint8))
         self.alignment = alignment
@@ -121,6 +146,7 @@ class DeviceAlignment:
             m.strides[0] if m.shape[0] else max(m.shape[1], 1), device, C.byref(self._h)))
         self.nseq, self.ncol = m.shape
         self.device = device
+        self.device_count = self.lib.tcu_msa_device_count(self._h)
 
     def close(self):
         if getattr(self, "_h", None):

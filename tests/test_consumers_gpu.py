@@ -88,6 +88,10 @@ def test_select_method_cutpoint_and_representatives(gpu, port, n, L, seed):
         for thr in (0.3, 0.8, 0.95):
             assert d.representatives(thr, indet=X).tolist() == \
                 port.greedy_clusters(oi, n, order, thr).tolist()
+        assert not d.identity_resident      # the one-call form thresholds inside K1: no floats
+        d.identity_on_device(X)
+        for thr in (0.3, 0.8, 0.95):        # same walk over the resident float matrix (K5)
+            assert d.clusters(order, thr).tolist() == port.greedy_clusters(oi, n, order, thr).tolist()
         name, avg_seq, max_seq = d.select_method()
         code, oavg, omax = port.select_method(oi, n)
         assert bits(avg_seq) == bits(oavg) and bits(max_seq) == bits(omax)
@@ -96,6 +100,50 @@ def test_select_method_cutpoint_and_representatives(gpu, port, n, L, seed):
             got, runs = d.cutpoint_clusters(k)
             want, oruns = port.cutpoint_clusters(oi, n, order, k)
             assert bits(got) == bits(want) and runs == oruns, k
+
+
+@pytest.mark.parametrize("n,L", [(1, 7), (2, 5), (3, 40), (31, 64), (33, 100), (63, 33), (64, 65),
+                                 (65, 300), (127, 130), (128, 128), (129, 127), (257, 129),
+                                 (383, 700), (1000, 200), (1025, 64), (2100, 96), (2700, 33)])
+def test_representatives_threshold_epilogue(gpu, port, n, L):
+    """tcu_representatives = K1 in threshold mode (one bit per pair, slab layout) + the mirror
+    pass + K7/K8: every tile-edge shape, thresholds at exact identity values (the > must not
+    become >=), negative and >= 1 thresholds, masked columns."""
+    rng = np.random.default_rng(n * 131 + L)
+    m = family_msa(n, L, n + L) if n >= 64 else random_msa(rng, n, L)
+    oi = port.identity(m, X)
+    order = port.cluster_order(port.sequence_lengths(m))
+    qs = np.quantile(oi, [0.0, 0.25, 0.5, 0.9, 1.0]).tolist() if len(oi) else []
+    exact = [float(v) for v in rng.choice(oi, min(3, len(oi)), replace=False)] if len(oi) else []
+    with gpu.DeviceAlignment(m) as d:
+        for thr in [-1.0, 0.0, 0.8, 1.0, 2.0] + qs + exact:
+            got = d.representatives(thr, indet=X)
+            assert got.tolist() == port.greedy_clusters(oi, n, order, np.float32(thr)).tolist(), thr
+        sr = np.arange(L, dtype=np.int32)
+        sr[rng.random(L) < 0.5] = -1
+        om = port.identity(m, X, None, sr)
+        assert d.representatives(0.5, indet=X, save_res=sr).tolist() == \
+            port.greedy_clusters(om, n, order, 0.5).tolist()
+
+
+def test_representatives_dense_graph_long_chains(gpu, port):
+    """Worst case for the fixed-point resolve: a path-like threshold graph in visiting order
+    (each sequence within the threshold of its successor only), and a complete graph."""
+    n, L = 1500, 256
+    rng = np.random.default_rng(5)
+    m = np.empty((n, L), np.uint8)
+    base = np.frombuffer(b"ARNDCQEGHILKMFPSTWYV", np.uint8)[rng.integers(0, 20, L)]
+    m[0] = base
+    for r in range(1, n):                      # drift: row r differs from row r-1 in 8 columns
+        m[r] = m[r - 1]
+        cols = rng.choice(L, 8, replace=False)
+        m[r, cols] = np.frombuffer(b"ARNDCQEGHILKMFPSTWYV", np.uint8)[rng.integers(0, 20, 8)]
+    oi = port.identity(m, X)
+    order = port.cluster_order(port.sequence_lengths(m))
+    with gpu.DeviceAlignment(m) as d:
+        for thr in (0.96, 0.9, 0.5, 0.0):
+            assert d.representatives(thr, indet=X).tolist() == \
+                port.greedy_clusters(oi, n, order, thr).tolist(), thr
 
 
 def test_representatives_with_column_mask(gpu, port):
@@ -120,6 +168,7 @@ def test_consumers_match_reference_fixture(gpu, path):
     with gpu.DeviceAlignment(a) as d:
         for thr in (0.5, 0.75, 0.9):
             assert d.representatives(thr).tolist() == g[f"repr_{int(thr * 100)}"].tolist()
+        d.identity_on_device()
         assert d.select_method()[0] == {1: "gappyout", 2: "strict"}[int(g["select_method"])]
         for k, want in zip(g["cutpoint_k"], g["cutpoint_thr"]):
             assert bits(d.cutpoint_clusters(int(k))[0]) == bits(want)
@@ -135,6 +184,7 @@ def test_representatives_full_size_properties(gpu):
     thr = 0.8
     with gpu.DeviceAlignment(m) as d:
         reps = d.representatives(thr, indet=X)
+        d.identity_on_device(X)
         ident = d.identity_download()
         lengths = d.sequence_lengths()
         order = gpu.cluster_order(lengths)
