@@ -278,6 +278,24 @@ int tcu_byte_histogram(tcu_msa *msa, unsigned long long *hist256);
 int tcu_sequence_lengths(tcu_msa *msa, int *lengths);
 
 /*
+ * Per row, the number of bytes other than '-' over the kept columns (save_res; NULL = all
+ * columns = tcu_sequence_lengths).  Together with tcu_gaps(save_seq) -- a column holds only
+ * gaps iff its count equals the number of kept rows -- this is everything
+ * Cleaner::removeAllGapsSeqsAndCols (source/Cleaner.cpp:1331-1396) scans the alignment for.
+ * residues: nseq ints (rows removed by the caller's row mask are simply ignored by it).
+ */
+int tcu_row_residues(tcu_msa *msa, const int *save_res, int *residues);
+
+/*
+ * Two 64-bit hashes of every row over all columns: hashes[2 i], hashes[2 i + 1] (2 * nseq
+ * values).  Equal rows have equal hashes; Cleaner::removeDuplicates
+ * (source/Cleaner.cpp:1489-1509: O(nseq^2) string compares) then only has to compare rows
+ * inside groups of equal hashes.  The hashes select candidates, the caller's byte compare
+ * decides.
+ */
+int tcu_row_hashes(tcu_msa *msa, unsigned long long *hashes);
+
+/*
  * Host only (no device needed).  The order in which both clustering walks visit the
  * sequences: (length, index) records sorted with the reference's own non-stable
  * quicksort (utils.cpp:246-273) and walked from the end (Cleaner.cpp:1413-1426 /
@@ -324,6 +342,12 @@ int tcu_comm_create(const void *id, int rank, int world, int device, tcu_comm **
 void tcu_comm_destroy(tcu_comm *comm);
 int tcu_comm_rank(const tcu_comm *comm);
 int tcu_comm_world(const tcu_comm *comm);
+
+/* tcu_msa_create_strided for a group of ranks that all hold the same alignment on the host:
+ * each rank uploads its share of the rows (tcu_shard_range) to the communicator's device and
+ * the shares are all-gathered over NVLink.  The handle is an ordinary single-device one. */
+int tcu_msa_create_all(tcu_comm *comm, const uint8_t *data, int nseq, int ncol, size_t stride,
+                       tcu_msa **out);
 
 /* Host-only partition helpers (no device needed). */
 int tcu_shard_range(int total, int granule, int rank, int world, int *begin, int *end);

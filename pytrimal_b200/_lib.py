@@ -63,6 +63,7 @@ PROTOTYPES = {
     "tcu_msa_create_strided": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int,
                                          C.POINTER(_h)]),
     "tcu_msa_destroy": (None, [_h]),
+    "tcu_msa_create_all": (C.c_int, [_h, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.POINTER(_h)]),
     "tcu_set_devices": (C.c_int, [_i32p, C.c_int]),
     "tcu_get_devices": (C.c_int, [_i32p, C.c_int]),
     "tcu_msa_device_count": (C.c_int, [_h]),
@@ -104,6 +105,8 @@ PROTOTYPES = {
     "tcu_identity_clusters": (C.c_int, [_h, _i32p, C.c_int, C.c_float, _i32p, _i32p]),
     "tcu_byte_histogram": (C.c_int, [_h, C.POINTER(C.c_ulonglong)]),
     "tcu_sequence_lengths": (C.c_int, [_h, _i32p]),
+    "tcu_row_residues": (C.c_int, [_h, _i32p, _i32p]),
+    "tcu_row_hashes": (C.c_int, [_h, C.POINTER(C.c_ulonglong)]),
     "tcu_cluster_order": (C.c_int, [_i32p, C.c_int, _i32p]),
     "tcu_representatives": (C.c_int, [_h, _i32p, C.c_uint8, C.c_float, _i32p, _i32p]),
     "tcu_representatives_all": (C.c_int, [_h, _h, _i32p, C.c_uint8, C.c_float, _i32p, _i32p]),

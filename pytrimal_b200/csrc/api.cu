@@ -465,20 +465,26 @@ extern "C" int tcu_comm_rank(const tcu_comm *c) { return c ? c->rank : -1; }
 extern "C" int tcu_comm_world(const tcu_comm *c) { return c ? c->world : 0; }
 
 // In-place all-gather of unequal contiguous byte ranges of `buf` (rank r owns
-// [off[r], off[r]+cnt[r])): one broadcast per owner, fused into a single NCCL group so
-// that they progress concurrently over NVLink.
+// [off[r], off[r]+cnt[r])): every rank sends its range to every other rank and receives
+// theirs, all point-to-point transfers fused into one NCCL group so that they run
+// concurrently over NVLink / NVSwitch (a group of broadcasts, the first version, moved
+// 78 MB in 0.67 ms; NVSwitch gives every pair its own full-bandwidth path).
 static int comm_allgatherv(tcu_comm *c, void *buf, const size_t *off, const size_t *cnt,
                            cudaStream_t stream)
 {
     const NcclApi &api = nccl_api();
+    const int me = c->rank;
     NK(api.GroupStart());
-    for (int r = 0; r < c->world; r++) {
-        if (cnt[r] == 0) continue;
-        uint8_t *p = (uint8_t *)buf + off[r];
-        int rc = api.Broadcast(p, p, cnt[r], NCCL_UINT8, r, c->comm, stream);
+    for (int d = 1; d < c->world; d++) {
+        // staggered partners: at step d everybody sends to rank + d and receives from rank - d
+        const int to = (me + d) % c->world, from = (me - d + c->world) % c->world;
+        int rc = NCCL_SUCCESS;
+        if (cnt[me]) rc = api.Send((const uint8_t *)buf + off[me], cnt[me], NCCL_UINT8, to, c->comm, stream);
+        if (rc == NCCL_SUCCESS && cnt[from])
+            rc = api.Recv((uint8_t *)buf + off[from], cnt[from], NCCL_UINT8, from, c->comm, stream);
         if (rc != NCCL_SUCCESS) {
             api.GroupEnd();
-            return nccl_fail(rc, "ncclBroadcast");
+            return nccl_fail(rc, "ncclSend/ncclRecv");
         }
     }
     NK(api.GroupEnd());
@@ -914,6 +920,52 @@ extern "C" int tcu_msa_create_strided(const uint8_t *data, int nseq, int ncol, s
     h.stride = stride;
     h.pinned = nseq > 0 && ncol > 0 && stride <= 2 * (size_t)ncol + 64 && is_pinned_host(data);
     return msa_create_any(h, nseq, ncol, device, out);
+}
+
+// One process per GPU: every rank holds the same alignment on the host; each uploads only
+// its share of the rows and the shares are all-gathered over NVLink, instead of N copies of
+// the whole alignment crossing the host's PCIe complex at once.
+extern "C" int tcu_msa_create_all(tcu_comm *comm, const uint8_t *data, int nseq, int ncol,
+                                  size_t stride, tcu_msa **out)
+{
+    NvtxRange nvtx("tcu_msa_create_all");
+    if (!comm || !out) return fail(TCU_ERR_INVALID, "NULL argument");
+    if (nseq > 0 && ncol > 0 && !data) return fail(TCU_ERR_INVALID, "data is NULL");
+    if (stride < (size_t)ncol) return fail(TCU_ERR_INVALID, "stride smaller than ncol");
+    *out = nullptr;
+    HostRows h;
+    h.data = data;
+    h.stride = stride;
+    h.pinned = nseq > 0 && ncol > 0 && stride <= 2 * (size_t)ncol + 64 && is_pinned_host(data);
+    tcu_msa *m = nullptr;
+    int rc = msa_alloc(nseq, ncol, comm->device, &m);
+    if (rc != TCU_OK) return rc;
+    int r0 = 0, r1 = 0;
+    tcu_shard_range(nseq, 1, comm->rank, comm->world, &r0, &r1);
+    rc = upload_range(m, h, r0, r1);
+    if (rc == TCU_OK && nseq > 0) {
+        std::vector<size_t> off(comm->world), cnt(comm->world);
+        for (int r = 0; r < comm->world; r++) {
+            int a, b;
+            tcu_shard_range(nseq, 1, r, comm->world, &a, &b);
+            off[r] = (size_t)a * m->pitch;
+            cnt[r] = (size_t)(b - a) * m->pitch;
+        }
+        cudaEventRecord(m->ev[4], m->stream);
+        rc = comm_allgatherv(comm, m->d_raw, off.data(), cnt.data(), m->stream);
+        cudaEventRecord(m->ev[5], m->stream);
+        if (rc == TCU_OK && cudaStreamSynchronize(m->stream) != cudaSuccess)
+            rc = cuda_fail(cudaGetLastError(), "row exchange between ranks");
+        if (rc == TCU_OK) m->timings.comm_ms = ev_ms(m->ev[4], m->ev[5]);
+    }
+    if (rc != TCU_OK) {
+        const std::string keep = g_last_error;
+        tcu_msa_destroy(m);
+        g_last_error = keep;
+        return rc;
+    }
+    *out = m;
+    return TCU_OK;
 }
 
 extern "C" void tcu_msa_destroy(tcu_msa *m)
@@ -1582,8 +1634,11 @@ extern "C" int tcu_identity_row_stats(tcu_msa *m, int upper_only, float *row_max
 static size_t bits_bytes(int n) { return std::max<size_t>(bits_total_words(n), 4) * sizeof(uint32_t); }
 
 // All-gather of the slabs the ranks' bands own: band [b0, b1) of 128-row blocks = slabs
-// [b0, b1), contiguous in the slab layout.
-static int bits_allgather(tcu_msa *m, tcu_comm *comm)
+// [b0, b1), contiguous in the slab layout.  (Splitting the band so that one half crosses
+// NVLink while the other is computed was considered and dropped: the NCCL transfer kernels
+// would take SM slots from the persistent identity kernel, whose static tile schedule turns
+// every delayed CTA into tail latency.)
+static int bits_allgather(tcu_msa *m, tcu_comm *comm, cudaStream_t stream)
 {
     std::vector<size_t> off(comm->world), cnt(comm->world);
     const size_t slab_b = bits_slab_words(m->nk) * sizeof(uint32_t);
@@ -1593,7 +1648,7 @@ static int bits_allgather(tcu_msa *m, tcu_comm *comm)
         off[r] = (size_t)b0 * slab_b;
         cnt[r] = (size_t)(b1 - b0) * slab_b;
     }
-    return comm_allgatherv(comm, m->d_bits, off.data(), cnt.data(), m->stream);
+    return comm_allgatherv(comm, m->d_bits, off.data(), cnt.data(), stream);
 }
 
 // Greedy clustering in the given order over the threshold bit matrix m->d_bits.  When `id0`
@@ -1713,6 +1768,65 @@ extern "C" int tcu_sequence_lengths(tcu_msa *m, int *lengths)
     return TCU_OK;
 }
 
+// Per row, the number of non-gap bytes over the kept columns (save_res; NULL = all columns,
+// i.e. tcu_sequence_lengths).  With tcu_gaps(save_seq) for the columns this is everything
+// Cleaner::removeAllGapsSeqsAndCols (Cleaner.cpp:1331-1396) scans the alignment for.
+extern "C" int tcu_row_residues(tcu_msa *m, const int *save_res, int *residues)
+{
+    NvtxRange nvtx("tcu_row_residues");
+    if (!m || !residues) return fail(TCU_ERR_INVALID, "NULL argument");
+    if (!save_res) return tcu_sequence_lengths(m, residues);
+    CK(cudaSetDevice(m->device));
+    m->timings = tcu_timings{};
+    const int n = m->nseq, L = m->ncol;
+    if (n == 0) return TCU_OK;
+    const size_t out_b = ((size_t)n * sizeof(int) + 255) / 256 * 256;
+    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, out_b + m->pitch);
+    if (rc != TCU_OK) return rc;
+    std::vector<uint8_t> keep(m->pitch, 0);
+    for (int k = 0; k < L; k++) keep[k] = save_res[k] != -1;
+    uint8_t *d_keep = (uint8_t *)m->d_scratch + out_b;
+    CK(cudaEventRecord(m->ev[0], m->stream));
+    CK(cudaMemcpyAsync(d_keep, keep.data(), m->pitch, cudaMemcpyHostToDevice, m->stream));
+    CK(cudaEventRecord(m->ev[1], m->stream));
+    CK(launch_row_residues(m->d_raw, n, m->pitch, d_keep, (int *)m->d_scratch, m->stream));
+    CK(cudaEventRecord(m->ev[2], m->stream));
+    CK(cudaMemcpyAsync(residues, m->d_scratch, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost,
+                       m->stream));
+    CK(cudaEventRecord(m->ev[3], m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    m->timings.h2d_ms = ev_ms(m->ev[0], m->ev[1]);
+    m->timings.kernel_ms = ev_ms(m->ev[1], m->ev[2]);
+    m->timings.d2h_ms = ev_ms(m->ev[2], m->ev[3]);
+    m->timings.kernel_launches = 1;
+    return TCU_OK;
+}
+
+// Two 64-bit hashes per row (hashes[2 i], hashes[2 i + 1]); equal rows have equal hashes.
+// Candidates for Cleaner::removeDuplicates (Cleaner.cpp:1489-1509), which the caller then
+// confirms byte for byte.
+extern "C" int tcu_row_hashes(tcu_msa *m, unsigned long long *hashes)
+{
+    NvtxRange nvtx("tcu_row_hashes");
+    if (!m || !hashes) return fail(TCU_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(m->device));
+    m->timings = tcu_timings{};
+    const int n = m->nseq;
+    if (n == 0) return TCU_OK;
+    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, (size_t)n * 16);
+    if (rc != TCU_OK) return rc;
+    CK(cudaEventRecord(m->ev[1], m->stream));
+    CK(launch_row_hashes(m->d_raw, n, m->pitch, (unsigned long long *)m->d_scratch, m->stream));
+    CK(cudaEventRecord(m->ev[2], m->stream));
+    CK(cudaMemcpyAsync(hashes, m->d_scratch, (size_t)n * 16, cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaEventRecord(m->ev[3], m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    m->timings.kernel_ms = ev_ms(m->ev[1], m->ev[2]);
+    m->timings.d2h_ms = ev_ms(m->ev[2], m->ev[3]);
+    m->timings.kernel_launches = 1;
+    return TCU_OK;
+}
+
 // Host only.  The visiting order of the two clustering walks: records (length, index)
 // sorted ascending by the reference's own quicksort -- pivot = last element, compared as a
 // float, Hoare-style scans that stop on equal keys, not stable -- and then walked from the
@@ -1720,16 +1834,22 @@ extern "C" int tcu_sequence_lengths(tcu_msa *m, int *lengths)
 // among equal lengths decides which sequence represents a cluster, so the partition steps
 // are replayed exactly; recursion is replaced by an explicit stack (sorted inputs make the
 // reference recurse n deep).
-extern "C" int tcu_cluster_order(const int *lengths, int nseq, int *order)
+namespace {
+struct LenRec {
+    int key, idx;
+};
+
+// The reference's partition scheme on v[ini..fin] with an explicit stack (sorted inputs make
+// the reference recurse n deep).  The two halves a partition leaves are independent of
+// each other, so a large left half may be handed to another thread (`spawn` = how many more
+// threads this call may start): same swaps, same result, a fraction of the wall time -- the
+// sort sits on the critical path of tcu_representatives once the identity kernel is
+// spread over several GPUs.
+void replay_quicksort(LenRec *v, int ini0, int fin0, int spawn)
 {
-    if (nseq < 0 || (nseq > 0 && (!lengths || !order))) return fail(TCU_ERR_INVALID, "bad argument");
-    struct Rec {
-        int key, idx;
-    };
-    std::vector<Rec> v((size_t)nseq);
-    for (int i = 0; i < nseq; i++) v[i] = Rec{lengths[i], i};
     std::vector<std::pair<int, int>> todo;
-    todo.emplace_back(0, nseq - 1);
+    std::vector<std::thread> helpers;
+    todo.emplace_back(ini0, fin0);
     while (!todo.empty()) {
         const int ini = todo.back().first, fin = todo.back().second;
         todo.pop_back();
@@ -1747,9 +1867,36 @@ extern "C" int tcu_cluster_order(const int *lengths, int nseq, int *order)
                 break;
         }
         std::swap(v[i], v[fin]);
-        // the two halves are independent; order of processing does not change the result
+        bool handed = false;
+        if (spawn > 0 && i - 1 - ini >= 8192 && fin - (i + 1) >= 8192) {
+            try {
+                helpers.emplace_back(replay_quicksort, v, ini, i - 1, spawn / 2);
+                spawn /= 2;
+                handed = true;
+            } catch (...) {  // no thread to be had: do it here
+            }
+        }
         todo.emplace_back(i + 1, fin);
-        todo.emplace_back(ini, i - 1);
+        if (!handed) todo.emplace_back(ini, i - 1);
+    }
+    for (auto &t : helpers) t.join();
+}
+}  // namespace
+
+extern "C" int tcu_cluster_order(const int *lengths, int nseq, int *order)
+{
+    if (nseq < 0 || (nseq > 0 && (!lengths || !order))) return fail(TCU_ERR_INVALID, "bad argument");
+    std::vector<LenRec> v;
+    try {
+        v.resize((size_t)nseq);
+    } catch (...) {
+        return fail(TCU_ERR_OOM, "host allocation failed");
+    }
+    for (int i = 0; i < nseq; i++) v[i] = LenRec{lengths[i], i};
+    try {
+        replay_quicksort(v.data(), 0, nseq - 1, /*spawn=*/4);
+    } catch (...) {
+        return fail(TCU_ERR_OOM, "host allocation failed");
     }
     for (int i = 0; i < nseq; i++) order[i] = v[nseq - 1 - i].idx;
     return TCU_OK;
@@ -1816,7 +1963,7 @@ static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res,
             if (r != TCU_OK) return r;
             CK(cudaEventRecord(m->ev[3], m->stream));
             if (comm) {
-                r = bits_allgather(m, comm);
+                r = bits_allgather(m, comm, m->stream);
                 if (r != TCU_OK) return r;
             }
             CK(cudaEventRecord(m->ev[4], m->stream));

@@ -259,7 +259,7 @@ cudaError_t launch_row_stats(const float *id, int n, bool upper_only, float *row
 }
 
 // ---------------------------------------------------------------------------
-// K7: one warp per sequence t of the current block (order[base .. base+cnt)).
+// K7: four warps per sequence t of the current block (order[base .. base+cnt)).
 //   alive8[t]  = no representative found so far (bitset `rep`) is adjacent to it
 //   adj[l][t]  = adjacency bits to the block's sequences 32*l .. 32*l+31 that precede t
 //                (word-major, so that K8 reads one word of 32 consecutive sequences
@@ -275,52 +275,53 @@ __global__ void __launch_bounds__(256) k_mis_scan(const uint32_t *__restrict__ b
                                                   uint8_t *__restrict__ alive8,
                                                   uint32_t *__restrict__ adj)
 {
+    // four warps per sequence, two sequences per CTA: the scan of a block is a chain of
+    // dependent memory latencies, so it is spread over many warps with few loads each
+    // (2 048 warps per block of 1 024 sequences)
     __shared__ int s_ord[MIS_NB];
+    __shared__ uint32_t s_hit[2][4];
     for (int k = threadIdx.x; k < cnt; k += 256) s_ord[k] = order[base + k];
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (t >= cnt) return;
-    const int s = s_ord[t];
+    const int lane = threadIdx.x & 31, part = (threadIdx.x >> 5) & 3, sub = threadIdx.x >> 7;
+    const int t = blockIdx.x * 2 + sub;
+    const bool live = t < cnt;
+    const int s = live ? s_ord[t] : 0;
     const int nslab = (n + 127) >> 7;
     const uint4 *slabs = reinterpret_cast<const uint4 *>(bits) + s;
     const uint4 *rep4 = reinterpret_cast<const uint4 *>(rep);
     uint32_t acc = 0;
-    int S = lane;
-    for (; S + 96 < nslab; S += 128) {  // four independent load pairs per step
-        const uint4 a0 = slabs[(size_t)S * n], a1 = slabs[(size_t)(S + 32) * n];
-        const uint4 a2 = slabs[(size_t)(S + 64) * n], a3 = slabs[(size_t)(S + 96) * n];
-        const uint4 r0 = rep4[S], r1 = rep4[S + 32], r2 = rep4[S + 64], r3 = rep4[S + 96];
-        acc |= (a0.x & r0.x) | (a0.y & r0.y) | (a0.z & r0.z) | (a0.w & r0.w);
-        acc |= (a1.x & r1.x) | (a1.y & r1.y) | (a1.z & r1.z) | (a1.w & r1.w);
-        acc |= (a2.x & r2.x) | (a2.y & r2.y) | (a2.z & r2.z) | (a2.w & r2.w);
-        acc |= (a3.x & r3.x) | (a3.y & r3.y) | (a3.z & r3.z) | (a3.w & r3.w);
-    }
-    for (; S < nslab; S += 32) {
-        const uint4 a0 = slabs[(size_t)S * n];
-        const uint4 r0 = rep4[S];
-        acc |= (a0.x & r0.x) | (a0.y & r0.y) | (a0.z & r0.z) | (a0.w & r0.w);
-    }
-    const bool dead = __any_sync(0xffffffffu, acc != 0);
-    if (lane == 0) alive8[t] = dead ? 0 : 1;
-    uint32_t word = 0;
-    const int a0 = lane * 32;
-    if (!dead && a0 < t) {
-        const int amax = min(32, t - a0);
-        if (amax == 32) {
-            uint32_t g[32];
-#pragma unroll
-            for (int a = 0; a < 32; a++) g[a] = bits[bits_word_index(n, s, s_ord[a0 + a] >> 5)];
-#pragma unroll
-            for (int a = 0; a < 32; a++) word |= ((g[a] >> (s_ord[a0 + a] & 31)) & 1u) << a;
-        } else {
-            for (int a = 0; a < amax; a++) {
-                const int u = s_ord[a0 + a];
-                word |= ((bits[bits_word_index(n, s, u >> 5)] >> (u & 31)) & 1u) << a;
-            }
+    if (live) {
+        for (int S = lane + 32 * part; S < nslab; S += 128) {
+            const uint4 a = slabs[(size_t)S * n];
+            const uint4 r = rep4[S];
+            acc |= (a.x & r.x) | (a.y & r.y) | (a.z & r.z) | (a.w & r.w);
         }
     }
-    adj[lane * MIS_NB + t] = word;
+    const uint32_t any = __any_sync(0xffffffffu, acc != 0) ? 1u : 0u;
+    if (lane == 0) s_hit[sub][part] = any;
+    __syncthreads();
+    if (!live) return;
+    const bool dead = (s_hit[sub][0] | s_hit[sub][1] | s_hit[sub][2] | s_hit[sub][3]) != 0;
+    if (part == 0 && lane == 0) alive8[t] = dead ? 0 : 1;
+    // adjacency to the earlier sequences of the block: word w = 8 part + lane / 4 holds the
+    // block's sequences 32 w ..; four lanes gather 8 bits each
+    const int w = 8 * part + (lane >> 2);
+    const int a0 = w * 32 + (lane & 3) * 8;
+    uint32_t word = 0;
+    if (!dead && a0 < t) {
+        const int amax = min(8, t - a0);
+        uint32_t g[8];
+#pragma unroll
+        for (int a = 0; a < 8; a++) {
+            const int u = s_ord[min(a0 + a, cnt - 1)];
+            g[a] = a < amax ? (bits[bits_word_index(n, s, u >> 5)] >> (u & 31)) & 1u : 0u;
+        }
+#pragma unroll
+        for (int a = 0; a < 8; a++) word |= g[a] << ((lane & 3) * 8 + a);
+    }
+    word |= __shfl_xor_sync(0xffffffffu, word, 1);
+    word |= __shfl_xor_sync(0xffffffffu, word, 2);
+    if ((lane & 3) == 0) adj[w * MIS_NB + t] = word;
 }
 
 // K8: one CTA of 1024 threads resolves the block; thread t owns sequence t of the block and
@@ -403,7 +404,7 @@ cudaError_t launch_greedy_clusters(const uint32_t *bits, int n, const int *order
 {
     for (int base = 0; base < total; base += MIS_NB) {
         const int cnt = min(MIS_NB, total - base);
-        k_mis_scan<<<(cnt + 7) / 8, 256, 0, stream>>>(bits, n, order, base, cnt, rep, alive8, adj);
+        k_mis_scan<<<(cnt + 1) / 2, 256, 0, stream>>>(bits, n, order, base, cnt, rep, alive8, adj);
         k_mis_resolve<<<1, 1024, 0, stream>>>(adj, alive8, order, base, cnt, rep, clusters, count);
     }
     return cudaGetLastError();

@@ -72,7 +72,9 @@ __global__ void __launch_bounds__(32 * CC_LANES) k_column_counts(
             for (int u = 0; u < CC_UNROLL; u++) {
                 const int rr = r + u * CC_LANES;
                 use[u] = rr < r_end && !(row_drop && row_drop[rr]);  // warp-uniform
-                v[u] = use[u] ? __ldg(reinterpret_cast<const uint4 *>(base + (size_t)rr * pitch))
+                // read once: streaming hint, so that the bit planes written below (and read
+                // back by the row pass) stay in L2 instead of the bytes
+                v[u] = use[u] ? __ldcs(reinterpret_cast<const uint4 *>(base + (size_t)rr * pitch))
                               : make_uint4(0u, 0u, 0u, 0u);
             }
 #pragma unroll
@@ -282,6 +284,97 @@ __global__ void __launch_bounds__(256) k_row_lengths(const uint8_t *__restrict__
     }
     c = __reduce_add_sync(0xffffffffu, c);
     if (lane == 0) lengths[row] = ncol - c;
+}
+
+// The same count restricted to the kept columns (keep01: one byte per column up to `pitch`,
+// 1 = kept, 0 = removed or padding): what Cleaner::removeAllGapsSeqsAndCols
+// (source/Cleaner.cpp:1338-1370) needs to know about a row -- "all gaps" is count == 0.
+__global__ void __launch_bounds__(256) k_row_residues(const uint8_t *__restrict__ raw, int nseq,
+                                                      size_t pitch,
+                                                      const uint8_t *__restrict__ keep01,
+                                                      int *__restrict__ residues)
+{
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= nseq) return;
+    const uint4 *p = reinterpret_cast<const uint4 *>(raw + (size_t)row * pitch);
+    const uint4 *k4 = reinterpret_cast<const uint4 *>(keep01);
+    const uint32_t dash = 0x2d2d2d2du;
+    int c = 0;
+    for (int k = lane; k < (int)(pitch / 16); k += 32) {
+        const uint4 v = __ldg(p + k), m = __ldg(k4 + k);
+        c += __popc(~byte_eq_ones(v.x, dash) & m.x) + __popc(~byte_eq_ones(v.y, dash) & m.y) +
+             __popc(~byte_eq_ones(v.z, dash) & m.z) + __popc(~byte_eq_ones(v.w, dash) & m.w);
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0) residues[row] = c;
+}
+
+cudaError_t launch_row_residues(const uint8_t *raw, int nseq, size_t pitch, const uint8_t *keep01,
+                                int *residues, cudaStream_t stream)
+{
+    if (nseq == 0) return cudaSuccess;
+    const long long threads = (long long)nseq * 32;
+    k_row_residues<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(raw, nseq, pitch, keep01,
+                                                                          residues);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Two independent 64-bit hashes of every row (all `pitch` bytes: the padding is zero in
+// every row).  Cleaner::removeDuplicates (source/Cleaner.cpp:1489-1509) compares every pair
+// of rows with std::string::operator== -- O(n^2) memcmp; equal rows have equal hashes, so
+// the host only has to compare rows inside groups of equal hashes (and does compare them:
+// the hashes select candidates, they do not decide).  One warp per row; every lane folds
+// its 16-byte words in order, the lanes are combined with lane-dependent keys.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x)
+{
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ull;
+    x ^= x >> 33;
+    return x;
+}
+
+__global__ void __launch_bounds__(256) k_row_hashes(const uint8_t *__restrict__ raw, int nseq,
+                                                    size_t pitch,
+                                                    unsigned long long *__restrict__ hashes)
+{
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= nseq) return;
+    const uint4 *p = reinterpret_cast<const uint4 *>(raw + (size_t)row * pitch);
+    unsigned long long a = 0x9e3779b97f4a7c15ull * (lane + 1), b = 0xd6e8feb86659fd93ull * (lane + 1);
+    for (int k = lane; k < (int)(pitch / 16); k += 32) {
+        const uint4 v = __ldg(p + k);
+        const unsigned long long lo = ((unsigned long long)v.y << 32) | v.x;
+        const unsigned long long hi = ((unsigned long long)v.w << 32) | v.z;
+        a = mix64(a ^ lo) + hi;
+        b = mix64(b + hi) ^ (lo * 0x9fb21c651e98df25ull);
+    }
+    a = mix64(a);
+    b = mix64(b);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b ^= __shfl_xor_sync(0xffffffffu, b, o) * 0x2545f4914f6cdd1dull + 1;
+    }
+    // the xor-shuffle reduction of b is not symmetric in its operands: take lane 0's value
+    if (lane == 0) {
+        hashes[2 * (size_t)row] = a;
+        hashes[2 * (size_t)row + 1] = b;
+    }
+}
+
+cudaError_t launch_row_hashes(const uint8_t *raw, int nseq, size_t pitch, unsigned long long *hashes,
+                              cudaStream_t stream)
+{
+    if (nseq == 0) return cudaSuccess;
+    const long long threads = (long long)nseq * 32;
+    k_row_hashes<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(raw, nseq, pitch, hashes);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_row_lengths(const uint8_t *raw, int nseq, int ncol, size_t pitch, int *lengths,

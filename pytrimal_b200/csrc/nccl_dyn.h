@@ -31,6 +31,8 @@ struct NcclApi {
     int (*GroupEnd)() = nullptr;
     int (*Broadcast)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*Send)(const void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
     int (*GetVersion)(int *) = nullptr;
     bool ok = false;
     const char *why = "";
@@ -61,6 +63,8 @@ inline const NcclApi &nccl_api()
         api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
         api.Broadcast = (decltype(api.Broadcast))sym("ncclBroadcast");
         api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+        api.Send = (decltype(api.Send))sym("ncclSend");
+        api.Recv = (decltype(api.Recv))sym("ncclRecv");
         api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
         api.ok = all;
         if (!all) api.why = "libnccl.so.2 lacks a required symbol";

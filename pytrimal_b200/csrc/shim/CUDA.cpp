@@ -4,7 +4,9 @@
 // through debug.report(...) and return false / leave zero-filled outputs.
 #include <algorithm>
 #include <atomic>
+#include <cctype>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -84,7 +86,11 @@ std::shared_ptr<CUDAContext> CUDAContext::acquire(Alignment *alig)
         return sp;
       }
   }
-  const int n = alig->originalNumberOfSequences, L = alig->originalNumberOfResidues;
+  // (inside Alignment::fillMatrices the original* counters are not set yet)
+  const int n = alig->originalNumberOfSequences > 0 ? alig->originalNumberOfSequences
+                                                    : alig->numberOfSequences;
+  const int L = alig->originalNumberOfResidues > 0 ? alig->originalNumberOfResidues
+                                                   : alig->numberOfResidues;
   std::vector<const char *> rows((size_t)n);
   for (int i = 0; i < n; i++) rows[i] = alig->sequences[i].data();
   tcu_msa *h = nullptr;
@@ -517,6 +523,157 @@ int *cudaRepresentativeSeq(Alignment *alig, float maximumIdent)
   repres[0] = count;
   for (int i = 0; i < count; i++) repres[i + 1] = reps[i];
   return repres;
+}
+
+// ---------------------------------------------------------------------------
+// Post-trim scans and symbol validation (rank 2)
+// ---------------------------------------------------------------------------
+bool cudaRemoveAllGaps(Alignment *alig, bool seqs, bool cols, bool keepSequences)
+{
+  StartTiming("bool cudaRemoveAllGaps(Alignment *, bool, bool, bool) ");
+  const int n = alig->originalNumberOfSequences, L = alig->originalNumberOfResidues;
+  if (alig->sequences == nullptr || n <= 0 || L <= 0) return false;
+  std::shared_ptr<CUDAContext> ctx = CUDAContext::acquire(alig);
+  if (!ctx) return false;
+  // A sequence that holds only gaps over the kept columns adds only gaps to every kept
+  // column, so dropping it (first loop of the reference) cannot change which columns hold
+  // only gaps (second loop): both questions are answered from the masks as they are now.
+  std::vector<int> rowResidues, colGaps;
+  int keptRows = 0;
+  for (int i = 0; i < n; i++) keptRows += alig->saveSequences[i] != -1;
+  {
+    std::lock_guard<std::recursive_mutex> lk(ctx->mutex);
+    if (seqs) {
+      rowResidues.resize((size_t)n);
+      if (tcu_row_residues(ctx->handle, alig->saveResidues, rowResidues.data()) != TCU_OK) {
+        report_failure("CUDA platform: row scan failed");
+        return false;
+      }
+    }
+    if (cols) {
+      colGaps.resize((size_t)L);
+      if (tcu_gaps(ctx->handle, alig->saveSequences, colGaps.data(), nullptr, nullptr) != TCU_OK) {
+        report_failure("CUDA platform: column scan failed");
+        return false;
+      }
+    }
+  }
+  if (seqs) {  // Cleaner.cpp:1338-1370
+    int counter = 0;
+    for (int i = 0; i < n; i++) {
+      if (alig->saveSequences[i] == -1) continue;
+      if (rowResidues[i] == 0) {
+        if (keepSequences) {
+          debug.report(WarningCode::KeepingOnlyGapsSequence, new std::string[1]{alig->seqsName[i]});
+          counter++;
+        } else {
+          debug.report(WarningCode::RemovingOnlyGapsSequence, new std::string[1]{alig->seqsName[i]});
+          alig->saveSequences[i] = -1;
+        }
+      } else
+        counter++;
+    }
+    alig->numberOfSequences = counter;
+  }
+  if (cols) {  // Cleaner.cpp:1372-1395; the counts were taken over the rows kept at entry
+    int counter = 0;
+    for (int j = 0; j < L; j++) {
+      if (alig->saveResidues[j] == -1) continue;
+      if (colGaps[j] == keptRows)
+        alig->saveResidues[j] = -1;
+      else
+        counter++;
+    }
+    alig->numberOfResidues = counter;
+  }
+  return true;
+}
+
+bool cudaRemoveDuplicates(Alignment *alig)
+{
+  StartTiming("bool cudaRemoveDuplicates(Alignment *) ");
+  const int n = alig->originalNumberOfSequences, L = alig->originalNumberOfResidues;
+  if (alig->sequences == nullptr || n <= 1 || L <= 0) return false;
+  for (int i = 0; i < n; i++)
+    if (alig->sequences[i].size() != (size_t)L) return false;
+  std::shared_ptr<CUDAContext> ctx = CUDAContext::acquire(alig);
+  if (!ctx) return false;
+  std::vector<unsigned long long> h((size_t)2 * n);
+  {
+    std::lock_guard<std::recursive_mutex> lk(ctx->mutex);
+    if (tcu_row_hashes(ctx->handle, h.data()) != TCU_OK) {
+      report_failure("CUDA platform: row hashes failed");
+      return false;
+    }
+  }
+  // rows ordered by (hash, index): equal rows are neighbours inside a run of equal hashes
+  std::vector<int> idx((size_t)n);
+  for (int i = 0; i < n; i++) idx[i] = i;
+  std::sort(idx.begin(), idx.end(), [&](int a, int b) {
+    if (h[2 * (size_t)a] != h[2 * (size_t)b]) return h[2 * (size_t)a] < h[2 * (size_t)b];
+    if (h[2 * (size_t)a + 1] != h[2 * (size_t)b + 1]) return h[2 * (size_t)a + 1] < h[2 * (size_t)b + 1];
+    return a < b;
+  });
+  // Cleaner.cpp:1493-1508: row i goes iff some later row x equals it, and the report names
+  // the FIRST such x.  Inside a run (indices ascending) that is the first later member that
+  // compares equal byte for byte -- the hashes only chose who is compared.
+  std::vector<int> partner((size_t)n, -1);
+  for (size_t a = 0; a < (size_t)n;) {
+    size_t b = a + 1;
+    while (b < (size_t)n && h[2 * (size_t)idx[b]] == h[2 * (size_t)idx[a]] &&
+           h[2 * (size_t)idx[b] + 1] == h[2 * (size_t)idx[a] + 1])
+      b++;
+    for (size_t u = a; u + 1 < b; u++)
+      for (size_t v = u + 1; v < b; v++)
+        if (alig->sequences[idx[u]] == alig->sequences[idx[v]]) {
+          partner[idx[u]] = idx[v];
+          break;
+        }
+    a = b;
+  }
+  for (int i = 0; i < n; i++) {  // reports in the reference's order (i ascending)
+    if (partner[i] < 0) continue;
+    alig->saveSequences[i] = -1;
+    debug.report(InfoCode::RemovingDuplicateSequences,
+                 new std::string[2]{alig->seqsName[i], alig->seqsName[partner[i]]});
+  }
+  return true;
+}
+
+bool cudaValidateSymbols(Alignment *alig, bool *valid)
+{
+  StartTiming("bool cudaValidateSymbols(Alignment *, bool *) ");
+  static const bool enabled = [] {
+    const char *e = getenv("TRIMAL_CUDA_INGEST");
+    return e != nullptr && *e != 0 && *e != '0';
+  }();
+  if (!enabled) return false;
+  const int n = alig->numberOfSequences;
+  if (alig->sequences == nullptr || n <= 0) return false;
+  const size_t L = alig->sequences[0].size();
+  if (L == 0 || (size_t)n * L < ((size_t)1 << 20)) return false;  // the scan is cheaper than an upload
+  for (int i = 0; i < n; i++)
+    if (alig->sequences[i].size() != L) return false;  // ragged: the reference reports it
+  if (tcu_device_count() < 1) return false;
+  const int savedResidues = alig->numberOfResidues;
+  alig->numberOfResidues = (int)L;  // what acquire() uploads (not set yet for file inputs)
+  std::shared_ptr<CUDAContext> ctx = CUDAContext::acquire(alig);
+  alig->numberOfResidues = savedResidues;
+  if (!ctx) return false;
+  unsigned long long hist[256];
+  {
+    std::lock_guard<std::recursive_mutex> lk(ctx->mutex);
+    if (tcu_byte_histogram(ctx->handle, hist) != TCU_OK) {
+      report_failure("CUDA platform: byte histogram failed");
+      return false;
+    }
+  }
+  *valid = true;
+  for (int b = 0; b < 256; b++) {
+    const char c = (char)b;
+    if (hist[b] != 0 && (!isalpha(c)) && (!ispunct(c))) *valid = false;  // Alignment.cpp:660
+  }
+  return true;
 }
 
 bool CUDAOverlap::calculateSpuriousVector(float overlap, float *spuriousVector)

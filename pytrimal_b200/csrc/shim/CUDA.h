@@ -114,6 +114,22 @@ void cudaMaterializeIdentity(Identity *identity);
 // applicable (trimmed alignment, ragged rows) or failed: the caller runs the reference scan.
 bool cudaAlignmentType(const Alignment *alig, int *type);
 
+// Post-trim scans of the host layer on the device; called from
+// patches/Cleaner.cpp.patch, each returns false when it does not apply or failed (the caller
+// then runs the reference loop).
+//   cudaRemoveAllGaps   Cleaner::removeAllGapsSeqsAndCols (Cleaner.cpp:1331-1396): same mask
+//                       updates, same warnings, same counters
+//   cudaRemoveDuplicates Cleaner::removeDuplicates (Cleaner.cpp:1489-1509): row hashes on the
+//                       device, byte compares only inside groups of equal hashes
+bool cudaRemoveAllGaps(Alignment *alig, bool seqs, bool cols, bool keepSequences);
+bool cudaRemoveDuplicates(Alignment *alig);
+
+// Alignment::fillMatrices' symbol validation (Alignment.cpp:657-664) from the device byte
+// histogram: true = decided, *valid says whether every byte is isalpha or
+// ispunct; false = not applicable (small or ragged alignment, no device, TRIMAL_CUDA_INGEST
+// not set).  The upload it makes is the one the statistics of a later trim() use.
+bool cudaValidateSymbols(Alignment *alig, bool *valid);
+
 // Number of usable devices; 0 makes the Cython layer refuse platform="cuda".
 int cudaPlatformDeviceCount();
 

@@ -191,6 +191,11 @@ cudaError_t launch_similarity(const uint8_t *codesT, int nseq, int npad, int nco
 cudaError_t launch_row_lengths(const uint8_t *raw, int nseq, int ncol, size_t pitch, int *lengths,
                                cudaStream_t stream);
 
+cudaError_t launch_row_residues(const uint8_t *raw, int nseq, size_t pitch, const uint8_t *keep01,
+                                int *residues, cudaStream_t stream);
+cudaError_t launch_row_hashes(const uint8_t *raw, int nseq, size_t pitch, unsigned long long *hashes,
+                              cudaStream_t stream);
+
 // consumers of the device-resident identity matrix (clusters.cu)
 cudaError_t launch_identity_bits(const float *id, int n, float thr, uint32_t *bits, int row_begin,
                                  int row_end, cudaStream_t stream);

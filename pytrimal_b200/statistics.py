@@ -296,6 +296,19 @@ class DeviceAlignment:
         _lib.check(self.lib.tcu_sequence_lengths(self._h, _p(out, _i32p)))
         return out
 
+    def row_residues(self, save_res=None):
+        """Non-gap bytes of every row over the kept columns (Cleaner.cpp:1338-1370)."""
+        sr = _mask(save_res, self.ncol)
+        out = np.zeros(self.nseq, np.int32)
+        _lib.check(self.lib.tcu_row_residues(self._h, _p(sr, _i32p), _p(out, _i32p)))
+        return out
+
+    def row_hashes(self):
+        """(nseq, 2) uint64: equal rows have equal hashes (candidates for removeDuplicates)."""
+        out = np.zeros((self.nseq, 2), np.uint64)
+        _lib.check(self.lib.tcu_row_hashes(self._h, out.ctypes.data_as(C.POINTER(C.c_ulonglong))))
+        return out
+
     def clusters(self, order, threshold, count_only=False):
         """Greedy clustering (Cleaner.cpp:1427-1447 / 1100-1118): representatives in
         creation order, or only their number."""

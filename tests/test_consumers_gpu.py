@@ -265,3 +265,35 @@ def test_pinned_strided_upload_equals_staged(gpu, port, n, L):
                 np.bincount(m.reshape(-1), minlength=256).astype(np.uint64)).all()
         assert (lengths == port.sequence_lengths(m)).all()
         assert (gaps == port.gaps(m)[0]).all()
+
+
+# ---- post-trim scans -------------------------------------------------------
+@pytest.mark.parametrize("n,L", [(1, 1), (7, 15), (33, 129), (500, 777), (3000, 260)])
+def test_row_residues_and_hashes(gpu, n, L):
+    """tcu_row_residues (rows of Cleaner::removeAllGapsSeqsAndCols, Cleaner.cpp:1338-1370) and
+    tcu_row_hashes (candidates of removeDuplicates, :1489-1509) against numpy."""
+    rng = np.random.default_rng(n * 17 + L)
+    m = random_msa(rng, n, L, gap=0.6)
+    m[rng.random(n) < 0.1] = ord("-")                         # rows of gaps only
+    dup = rng.random(n) < 0.2
+    for r in np.nonzero(dup)[0]:
+        m[r] = m[rng.integers(0, n)]                          # exact duplicates
+    if n > 2:
+        m[n - 1] = m[0]
+        m[n - 1, L - 1] = ord("A") if m[0, L - 1] != ord("A") else ord("C")   # differs in the last byte only
+    sr = np.arange(L, dtype=np.int32)
+    sr[rng.random(L) < 0.5] = -1
+    with gpu.DeviceAlignment(m) as d:
+        assert (d.row_residues() == (m != ord("-")).sum(1)).all()
+        assert (d.row_residues(save_res=sr) == (m[:, sr != -1] != ord("-")).sum(1)).all()
+        h = d.row_hashes()
+    keys = {}
+    for i in range(n):
+        keys.setdefault((int(h[i, 0]), int(h[i, 1])), []).append(i)
+    for group in keys.values():                               # equal hashes <=> equal rows here
+        for i in group[1:]:
+            assert (m[i] == m[group[0]]).all()
+    rows = {}
+    for i in range(n):
+        rows.setdefault(bytes(m[i]), []).append(i)
+    assert len(rows) == len(keys)

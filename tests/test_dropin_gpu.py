@@ -206,3 +206,31 @@ def test_cuda_platform_alignment_type_cases(dropin):
             continue
         got = dropin(m, platform=oracle.PLATFORM_CUDA, datatype=0).detect_type()
         assert got == want, name
+
+
+# ---- removeDuplicates / removeAllGapsSeqsAndCols on the device -------------
+def test_cuda_platform_noduplicateseqs_and_all_gap_scans(dropin):
+    """Cleaner::removeDuplicates (row hashes on the device) and removeAllGapsSeqsAndCols (row /
+    column gap scans on the device) through the patched reference, against the AVX2 platform =
+    the reference's own host loops."""
+    from pytrimal_b200.synthetic import synthetic_msa
+    rng = np.random.default_rng(21)
+    m = synthetic_msa(1200, 300, 13)
+    for r in rng.choice(1200, 150, replace=False):             # duplicates, some in chains
+        m[r] = m[rng.integers(0, 1200)]
+    m[5] = m[900]
+    m[900] = m[1100]
+    ks_a, kr_a = dropin(m, platform=oracle.PLATFORM_AVX2).trim("noduplicateseqs")
+    ks_c, kr_c = dropin(m, platform=oracle.PLATFORM_CUDA).trim("noduplicateseqs")
+    assert (ks_a == ks_c).all() and (kr_a == kr_c).all()
+    assert int((ks_a == -1).sum()) >= 100
+    # rows and columns that hold only gaps once other rows / columns are gone
+    m2 = synthetic_msa(400, 500, 14)
+    m2[:, 100:140] = ord("-")
+    m2[::7, :] = ord("-")
+    m2[3, 100:140] = ord("A")                                  # one row keeps those columns alive ...
+    for method, params in (("noallgaps", []), ("overlap", [0.3, 30]), ("gappyout", []),
+                           ("representative", [-1, 0.9])):
+        a = dropin(m2, platform=oracle.PLATFORM_AVX2).trim(method, params)
+        c = dropin(m2, platform=oracle.PLATFORM_CUDA).trim(method, params)
+        assert (a[0] == c[0]).all() and (a[1] == c[1]).all(), method

@@ -61,7 +61,25 @@ def main():
                 t_sim = d.timings
                 idm2 = d.identity(X, save_seq=save_seq, comm=comm)
                 rep2 = d.representatives(0.6, indet=X, comm=comm)
+            # sharded upload (each rank 1/N of the rows + all-gather) must give the same device
+            # matrix as uploading everything: compare byte histogram, lengths and representatives
+            import ctypes as C
+            from pytrimal_b200 import _lib
+            lib = pb.load()
+            hm = torch.from_numpy(m).pin_memory()
+            h = C.c_void_p()
+            _lib.check(lib.tcu_msa_create_all(comm._h, C.c_void_p(hm.data_ptr()), n, L, L, C.byref(h)))
+            hist = (C.c_ulonglong * 256)()
+            _lib.check(lib.tcu_byte_histogram(h, hist))
+            rep3 = np.zeros(n, np.int32)
+            k3 = C.c_int(0)
+            _lib.check(lib.tcu_representatives_all(h, comm._h, None, X, C.c_float(0.6),
+                                                   rep3.ctypes.data_as(C.POINTER(C.c_int)), C.byref(k3)))
+            lib.tcu_msa_destroy(h)
             checks = {
+                "create_all": (np.array(hist[:], np.uint64) ==
+                               np.bincount(m.reshape(-1), minlength=256).astype(np.uint64)).all()
+                and rep3[:k3.value].tolist() == rep1.tolist(),
                 "representatives": rep1.tolist() == rep2.tolist(),
                 "gaps": (g1 == g2).all() and (h1 == h2).all() and mx1 == mx2,
                 "gaps_masked": (gm1 == gm2).all(),

@@ -1,13 +1,16 @@
 #!/usr/bin/env python
 """trim() wall time through the reference's own Python API (BASELINE.json's second metric):
-pytrimal built with the CUDA platform (integration/build_pytrimal.py), platform="cuda"
-against platform="avx2" on the same synthetic alignment, one JSON line per configuration.
+pytrimal built with the CUDA platform (integration/build_pytrimal.py), platform="cuda", on the
+full-size seeded alignments of BASELINE's configurations, one JSON line per configuration.
 
-    python tools/trim_wall.py [--configs C2,C3,C4,C5] [--avx2-rows 4000]
+    python tools/trim_wall.py [--configs C2,C3,C4,C5] [--devices all|0,1,..] [--ingest]
 
-The AVX2 run is limited to the first --avx2-rows rows where the full size would take
-minutes on one core (the statistics are single-threaded); its pair-column
-rate is what scales.
+Every result is compared with what the unmodified reference (AVX2 platform) produced for the
+same input at FULL size (tests/golden/full/*.npz, tests/golden/make_golden_full.py; the
+reference needs 6-40 minutes of one core per configuration, so it is not rerun here -- its
+own wall time is in the fixture).  --devices sets TRIMAL_CUDA_DEVICES (one process, several
+GPUs); --ingest sets TRIMAL_CUDA_INGEST=1 (symbol validation of Alignment() on the device, the
+upload it makes is reused by trim()).
 """
 from __future__ import annotations
 
@@ -21,56 +24,95 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "integration", "_build", "pkg"))
 
-TRIMMERS = {
-    "C2": ("ManualTrimmer", dict(gap_threshold=0.9, similarity_threshold=0.1, window=3)),
-    "C3": ("AutomaticTrimmer", dict(method="strictplus")),
-    "C4": ("RepresentativeTrimmer", dict(identity_threshold=0.8)),
-    "C5": ("OverlapTrimmer", dict(sequence_overlap=0.5, residue_overlap=0.5)),
+CASES = {
+    "C2": ("ManualTrimmer", dict(gap_threshold=0.5, similarity_threshold=0.001, window=3), "C2", "gt50_st001"),
+    "C2literal": ("ManualTrimmer", dict(gap_threshold=0.9, similarity_threshold=0.1, window=3), "C2", "literal"),
+    "C3": ("AutomaticTrimmer", dict(method="strictplus"), "C3.strictplus", "strictplus"),
+    "C3strict": ("AutomaticTrimmer", dict(method="strict"), "C3.strict", "strict"),
+    "C3gappyout": ("AutomaticTrimmer", dict(method="gappyout"), "C3", "gappyout"),
+    "C4": ("RepresentativeTrimmer", dict(identity_threshold=0.8), "C4", "maxidentity80"),
+    "C5": ("OverlapTrimmer", dict(sequence_overlap=0.5, residue_overlap=0.5), "C5.seq0.5", "overlap_seq0p5"),
+    "C5seq50": ("OverlapTrimmer", dict(sequence_overlap=50, residue_overlap=0.5), "C5.seq50", "overlap_seq50"),
 }
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="C2,C4,C5")
-    ap.add_argument("--avx2-rows", type=int, default=4000)
-    ap.add_argument("--repeats", type=int, default=2)
+    ap.add_argument("--configs", default="C2,C3,C4,C5")
+    ap.add_argument("--devices", default="")
+    ap.add_argument("--ingest", action="store_true")
+    ap.add_argument("--repeats", type=int, default=3)
     args = ap.parse_args()
+    if args.devices:
+        os.environ["TRIMAL_CUDA_DEVICES"] = args.devices
+    if args.ingest:
+        os.environ["TRIMAL_CUDA_INGEST"] = "1"
+    import numpy as np
     import pytrimal
+    import pytrimal_b200 as pb
     from pytrimal_b200.synthetic import CONFIGS, synthetic_msa
 
-    for cfg in args.configs.split(","):
+    cache = {}
+    for case in args.configs.split(","):
+        cls, kwargs, job, tag = CASES[case]
+        cfg = case[:2]
         n, L, seed = CONFIGS[cfg]
-        m = synthetic_msa(n, L, seed)
+        if cfg not in cache:
+            cache.clear()
+            cache[cfg] = synthetic_msa(n, L, seed)
+        m = cache[cfg]
         names = [b"s%d" % i for i in range(n)]
-        t0 = time.perf_counter()
-        ali = pytrimal.Alignment(names, [bytes(r) for r in m])
-        build_s = time.perf_counter() - t0
-        cls, kwargs = TRIMMERS[cfg]
+        seqs = [bytes(r) for r in m]
+        build = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            ali = pytrimal.Alignment(names, seqs)
+            build.append(time.perf_counter() - t0)
         trimmer = getattr(pytrimal, cls)(platform="cuda", **kwargs)
-        times = []
+        times, out = [], None
         for _ in range(args.repeats + 1):
             t0 = time.perf_counter()
-            out = trimmer.trim(ali)
+            try:
+                out = trimmer.trim(ali)
+            except Exception as exc:      # the reference raises when nothing is left
+                out = exc
             times.append(time.perf_counter() - t0)
-        rec = {"config": cfg, "shape": [n, L], "trimmer": cls, "kwargs": kwargs,
-               "alignment_build_s": build_s, "cuda_trim_s_first": times[0],
-               "cuda_trim_s_best": min(times[1:]), "kept_sequences": len(out.sequences),
-               "kept_columns": len(out.sequences[0]) if len(out.sequences) else 0}
-        # C3 also runs the scalar similarity loop on the CPU (1e9 pair-col/s): fewer rows there
-        rows = min(n, args.avx2_rows if cfg != "C3" else min(args.avx2_rows, 1500))
-        sub = pytrimal.Alignment(names[:rows], [bytes(r) for r in m[:rows]])
-        cpu = getattr(pytrimal, cls)(platform="avx2", **kwargs)
-        cpu.trim(sub)                       # platform applies from the 2nd call
+        # first call on a fresh alignment object (upload included unless --ingest made it already)
         t0 = time.perf_counter()
-        ref = cpu.trim(sub)
-        rec["avx2_trim_s"] = time.perf_counter() - t0
-        rec["avx2_rows"] = rows
-        gpu_sub = getattr(pytrimal, cls)(platform="cuda", **kwargs).trim(sub)
-        rec["identical_to_avx2_on_subsample"] = (
-            list(gpu_sub.names) == list(ref.names) and list(gpu_sub.sequences) == list(ref.sequences))
-        t0 = time.perf_counter()
-        getattr(pytrimal, cls)(platform="cuda", **kwargs).trim(sub)
-        rec["cuda_trim_s_subsample"] = time.perf_counter() - t0
+        fresh = pytrimal.Alignment(names, seqs)
+        t1 = time.perf_counter()
+        try:
+            getattr(pytrimal, cls)(platform="cuda", **kwargs).trim(fresh)
+        except Exception:
+            pass
+        t2 = time.perf_counter()
+        rec = {"config": case, "shape": [n, L], "trimmer": cls, "kwargs": kwargs,
+               "devices": pb.get_devices(), "ingest_on_device": bool(args.ingest),
+               "alignment_build_s": min(build), "cuda_trim_s_first": times[0],
+               "cuda_trim_s_best": min(times[1:]),
+               "fresh_alignment_plus_trim_s": t2 - t0, "fresh_build_s": t1 - t0, "fresh_trim_s": t2 - t1}
+        if isinstance(out, Exception):
+            rec["result"] = "error: " + type(out).__name__
+            kept = (0, 0)
+        else:
+            kept = (len(out.sequences), len(out.sequences[0]) if len(out.sequences) else 0)
+            rec["kept_sequences"], rec["kept_columns"] = kept
+        gpath = os.path.join(ROOT, "tests", "golden", "full", job + ".npz")
+        if os.path.exists(gpath):
+            g = np.load(gpath)
+            ks, kr = g[f"trim_{tag}_seq"], g[f"trim_{tag}_res"]
+            rows, cols = np.nonzero(ks != -1)[0], np.nonzero(kr != -1)[0]
+            rec["reference_avx2_seconds_full_size_job"] = float(g["reference_seconds"])
+            if len(cols) == 0 or len(rows) == 0:
+                rec["identical_to_reference_full_size"] = kept[0] == 0 or kept[1] == 0
+            elif isinstance(out, Exception):
+                rec["identical_to_reference_full_size"] = False
+            else:
+                sub = m[np.ix_(rows, cols)]
+                got = list(out.sequences)
+                rec["identical_to_reference_full_size"] = bool(
+                    list(out.names) == [names[i] for i in rows] and len(got) == len(rows) and
+                    all(got[k].encode() == bytes(sub[k]) for k in range(len(rows))))
         print(json.dumps(rec), flush=True)
 
 
