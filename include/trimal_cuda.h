@@ -122,6 +122,9 @@ int tcu_gaps(tcu_msa *msa, const int *save_seq, int *gaps_in_column, int *num_co
  * identities may be NULL when keep_on_device is set and only the device copy
  * (for a following tcu_similarity) is wanted.
  * indet: 'X' for amino-acid alignments else 'N' (template.h:331).
+ * Any byte values are accepted, like the reference's raw byte compares: up to 126 distinct
+ * non-gap values go through the packed bit-plane kernel, more (unreachable through trimAl's
+ * own symbol validation) through a byte-wise kernel with the same results.
  */
 int tcu_identity(tcu_msa *msa, const int *save_seq, const int *save_res, uint8_t indet,
                  float *identities, int *hit_out, int *dst_out, int keep_on_device);
@@ -368,13 +371,6 @@ int tcu_spurious_all(tcu_msa *msa, tcu_comm *comm, uint8_t indet, uint32_t ovrla
  * (tcu_identity_all); the clustering itself is sequential and runs on every rank. */
 int tcu_representatives_all(tcu_msa *msa, tcu_comm *comm, const int *save_res, uint8_t indet,
                             float threshold, int *clusters, int *n_clusters);
-
-/* ---- test-only -------------------------------------------------------------
- * Same contract as tcu_identity (without keep_on_device), computed by a slow
- * byte-wise kernel straight from the raw rows.  Lets the GPU tests tell a
- * packing / pipeline fault from an arithmetic one.  Not for production use. */
-int tcu_debug_identity_bytes(tcu_msa *msa, const int *save_seq, const int *save_res,
-                             uint8_t indet, float *identities, int *hit_out, int *dst_out);
 
 #ifdef __cplusplus
 }

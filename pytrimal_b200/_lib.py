@@ -110,7 +110,6 @@ PROTOTYPES = {
     "tcu_cluster_order": (C.c_int, [_i32p, C.c_int, _i32p]),
     "tcu_representatives": (C.c_int, [_h, _i32p, C.c_uint8, C.c_float, _i32p, _i32p]),
     "tcu_representatives_all": (C.c_int, [_h, _h, _i32p, C.c_uint8, C.c_float, _i32p, _i32p]),
-    "tcu_debug_identity_bytes": (C.c_int, [_h, _i32p, _i32p, C.c_uint8, _f32p, _i32p, _i32p]),
 }
 
 _lib = None

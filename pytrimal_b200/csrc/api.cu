@@ -1157,6 +1157,31 @@ extern "C" size_t tcu_identity_row_offset(int kept_rows, int i)
     return r * n - r * (r + 1) / 2;
 }
 
+// which of the 256 byte values occur in the alignment (mask independent, computed once)
+static int ensure_present(tcu_msa *m)
+{
+    if (m->have_present) return TCU_OK;
+    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, 256 * sizeof(unsigned int));
+    if (rc != TCU_OK) return rc;
+    unsigned int *d_present = (unsigned int *)m->d_scratch;
+    CK(cudaMemsetAsync(d_present, 0, 256 * sizeof(unsigned int), m->stream));
+    CK(launch_byte_presence(m->d_raw, m->nseq, m->ncol, m->pitch, d_present, m->num_sms, m->stream));
+    CK(cudaMemcpyAsync(m->present, d_present, sizeof m->present, cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    m->have_present = true;
+    m->timings.kernel_launches++;
+    return TCU_OK;
+}
+
+// more distinct non-gap byte values than the 7 code planes of the packed operand hold
+static bool bytewise_alphabet(tcu_msa *m, uint8_t indet)
+{
+    if (cudaSetDevice(m->device) != cudaSuccess || ensure_present(m) != TCU_OK) return false;
+    int count = 0;
+    for (int b = 0; b < 256; b++) count += b != '-' && b != indet && m->present[b];
+    return count > (1 << MAX_PLANES) - 2;
+}
+
 extern "C" int tcu_identity_prepare(tcu_msa *m, const int *save_seq, const int *save_res,
                                     uint8_t indet, int *kept_rows_out)
 {
@@ -1174,19 +1199,8 @@ extern "C" int tcu_identity_prepare(tcu_msa *m, const int *save_seq, const int *
         for (int k = 0; k < L; k++) drop[k] = save_res[k] == -1;
 
     CK(cudaEventRecord(m->ev[0], m->stream));
-    if (!m->have_present) {
-        unsigned int *d_present = nullptr;
-        int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, 256 * sizeof(unsigned int));
-        if (rc != TCU_OK) return rc;
-        d_present = (unsigned int *)m->d_scratch;
-        CK(cudaMemsetAsync(d_present, 0, 256 * sizeof(unsigned int), m->stream));
-        CK(launch_byte_presence(m->d_raw, n, L, m->pitch, d_present, m->stream));
-        CK(cudaMemcpyAsync(m->present, d_present, sizeof m->present, cudaMemcpyDeviceToHost,
-                           m->stream));
-        CK(cudaStreamSynchronize(m->stream));
-        m->have_present = true;
-        m->timings.kernel_launches++;
-    }
+    int prc = ensure_present(m);
+    if (prc != TCU_OK) return prc;
 
     // dense residue codes for the bytes that occur; the gap class shares one code
     uint8_t lut[256];
@@ -1198,9 +1212,10 @@ extern "C" int tcu_identity_prepare(tcu_msa *m, const int *save_seq, const int *
     }
     int np = MIN_PLANES;
     while (np <= MAX_PLANES && (1 << np) - 2 < count) np++;
-    if (np > MAX_PLANES)
-        return fail(TCU_ERR_INVALID, "alignment uses %d distinct symbols (max %d)", count,
-                    (1 << MAX_PLANES) - 2);
+    // more distinct symbols than 7 code planes hold: no bit-plane operand, the byte-wise
+    // kernel (identity_bytes.cu) computes the statistic from the raw rows
+    const bool bytewise = np > MAX_PLANES;
+    if (bytewise) np = 0;
 
     m->np = np;
     m->nk = (int)kept.size();
@@ -1220,6 +1235,13 @@ extern "C" int tcu_identity_prepare(tcu_msa *m, const int *save_seq, const int *
     if (L) CK(cudaMemcpyAsync(m->d_col_drop, drop.data(), L, cudaMemcpyHostToDevice, m->stream));
     CK(cudaStreamSynchronize(m->stream));  // the host vectors go out of scope
 
+    if (bytewise) {
+        CK(cudaEventRecord(m->ev[1], m->stream));
+        CK(cudaEventRecord(m->ev[2], m->stream));
+        m->prepared = true;
+        if (kept_rows_out) *kept_rows_out = m->nk;
+        return TCU_OK;
+    }
     int rc = ensure_dev(m->device, (void **)&m->d_planes, &m->planes_cap, (size_t)m->nb2 * m->nchunks * tile2_bytes(np));
     if (rc != TCU_OK) return rc;
     rc = ensure_dev(m->device, (void **)&m->d_gbytes, &m->gbytes_cap,
@@ -1240,6 +1262,9 @@ static int identity_launch(tcu_msa *m, int sb_begin, int sb_end, float *d_out, i
                            int *d_dst, uint32_t *d_bits = nullptr, float thr = 0.f)
 {
     if (m->nchunks == 0 || sb_end <= sb_begin) return TCU_OK;
+    if (m->np == 0)
+        return fail(TCU_ERR_INVALID, "more than %d distinct symbols: only tcu_identity and "
+                    "tcu_representatives handle such an alignment", (1 << MAX_PLANES) - 2);
     Identity2Params p{};
     p.planes = m->d_planes;
     p.gbytes = m->d_gbytes;
@@ -1390,9 +1415,9 @@ static int identity_host(tcu_msa *m, const int *save_seq, const int *save_res, u
         d_hit = (int *)m->d_scratch;
         d_dst = d_hit + npairs;
     }
-    if (bytes_kernel) {
+    if (bytes_kernel || m->np == 0) {
         CK(launch_identity_bytes(m->d_raw, m->pitch, m->ncol, m->d_kept_rows, m->nk, m->d_col_drop,
-                                 indet, m->d_ident, d_hit, d_dst, m->stream));
+                                 indet, m->d_ident, d_hit, d_dst, m->num_sms, m->stream));
         m->timings.kernel_launches++;
         CK(cudaEventRecord(m->ev[3], m->stream));
         if (identities) rc = download(m, identities, m->d_ident, npairs * sizeof(float));
@@ -1498,7 +1523,7 @@ extern "C" int tcu_identity(tcu_msa *m, const int *save_seq, const int *save_res
                             float *identities, int *hit_out, int *dst_out, int keep_on_device)
 {
     NvtxRange nvtx("tcu_identity");
-    if (m && !m->peers.empty() && !hit_out && !dst_out)
+    if (m && !m->peers.empty() && !hit_out && !dst_out && !bytewise_alphabet(m, indet))
         return identity_multi(m, save_seq, save_res, indet, identities, keep_on_device);
     return identity_host(m, save_seq, save_res, indet, identities, hit_out, dst_out,
                          keep_on_device, false);
@@ -1556,14 +1581,6 @@ extern "C" int tcu_identity_all(tcu_msa *m, tcu_comm *comm, const int *save_seq,
     m->timings.d2h_ms = ev_ms(m->ev[4], m->ev[5]);
     m->ident_full = (m->nk == m->nseq);
     return TCU_OK;
-}
-
-// test-only: same contract as tcu_identity, computed by the byte-wise kernel
-extern "C" int tcu_debug_identity_bytes(tcu_msa *m, const int *save_seq, const int *save_res,
-                                        uint8_t indet, float *identities, int *hit_out,
-                                        int *dst_out)
-{
-    return identity_host(m, save_seq, save_res, indet, identities, hit_out, dst_out, 0, true);
 }
 
 // ---------------------------------------------------------------------------
@@ -2034,6 +2051,25 @@ static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res,
         m->timings.pack_ms += ev_ms(m->ev[4], m->ev[5]);  // mirror pass
         return TCU_OK;
     };
+    const bool bytewise = bytewise_alphabet(m, indet);
+    if (bytewise && comm) {
+        if (sorter.joinable()) sorter.join();
+        return fail(TCU_ERR_INVALID, "more than %d distinct symbols: not supported across ranks",
+                    (1 << MAX_PLANES) - 2);
+    }
+    if (bytewise) {
+        // no bit-plane operand: float matrix from the byte-wise kernel, thresholded by K5
+        rc = tcu_identity(m, nullptr, save_res, indet, nullptr, nullptr, nullptr, 1);
+        if (sorter.joinable()) sorter.join();
+        if (rc != TCU_OK) return rc;
+        add(m->timings);
+        if (sort_rc != TCU_OK) return fail(sort_rc, "%s", sort_err.c_str());
+        rc = clusters_impl(m, m->d_ident, order.data(), n, threshold, clusters, n_clusters);
+        if (rc != TCU_OK) return rc;
+        add(m->timings);
+        m->timings = total;
+        return TCU_OK;
+    }
     rc = (!comm && !m->peers.empty() && m->ncol > 0) ? device_part_multi() : device_part();
     if (sorter.joinable()) sorter.join();
     if (rc != TCU_OK) return rc;
@@ -2285,7 +2321,7 @@ static int similarity_impl(tcu_msa *m, tcu_comm *comm, uint8_t indet, const floa
     CK(cudaMemcpyAsync(d_lut, lut, 256, cudaMemcpyHostToDevice, m->stream));
     CK(cudaMemcpyAsync(d_err, &no_err, sizeof no_err, cudaMemcpyHostToDevice, m->stream));
     CK(cudaEventRecord(m->ev[1], m->stream));
-    CK(launch_sim_codes(m->d_raw, n, L, m->pitch, npad, d_lut, d_skip, d_codes, d_err, m->stream));
+    CK(launch_sim_codes(m->d_raw, n, L, m->pitch, npad, d_lut, d_skip, d_codes, d_err, m->num_sms, m->stream));
     CK(launch_sim_rows(d_codes, n, npad, ngroups, d_rowskip, d_nbatches, d_ngmask, m->stream));
     CK(cudaEventRecord(m->ev[2], m->stream));
     CK(cudaMemcpyAsync(&first_err, d_err, sizeof first_err, cudaMemcpyDeviceToHost, m->stream));

@@ -139,8 +139,15 @@ cudaError_t launch_column_counts(const uint8_t *raw, int nseq, int ncol, size_t 
 {
     if (nseq == 0 || ncol == 0) return cudaSuccess;
     const int gx = (ncol + 511) / 512;
-    // about 4 CTAs (1024 threads) per SM; a slice is at least one unrolled pass of the lanes
-    int gy = max(1, (num_sms * 4 + gx - 1) / gx);
+    // one resident wave: as many CTAs as the device holds at once (2-3 per SM), each with a
+    // row slice of at least one unrolled pass of the lanes -- no second, partly filled wave
+    int per_sm = 2;
+    if (count_b)
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_counts<true>, 32 * CC_LANES, 0);
+    else
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_counts<false>, 32 * CC_LANES, 0);
+    per_sm = max(1, per_sm);
+    int gy = max(1, num_sms * per_sm / gx);
     int rows_per_slice = max(CC_LANES * CC_UNROLL, (nseq + gy - 1) / gy);
     gy = min(65535, (nseq + rows_per_slice - 1) / rows_per_slice);
     rows_per_slice = (nseq + gy - 1) / gy;

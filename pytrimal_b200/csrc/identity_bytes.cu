@@ -1,4 +1,5 @@
-// identity_debug.cu -- test-only byte-wise identity kernel (tcu_debug_identity_bytes).
+// identity_bytes.cu -- byte-wise identity kernel for alignments with more than 126 distinct
+// non-gap byte values (the bit-plane operand of identity2.cu holds 7 code planes).
 #include <algorithm>
 
 #include "tcu_internal.cuh"
@@ -6,10 +7,10 @@
 namespace tcu {
 
 // ---------------------------------------------------------------------------
-// Debug cross-check: the same statistic straight from the raw bytes, one
-// thread per pair.  Slow by design; only reachable through the test entry
-// point tcu_debug_identity_bytes so that a packing or pipeline fault can be
-// told apart from an arithmetic one on the GPU.
+// The same statistic (template.h:346-437) straight from the raw bytes, one thread per
+// pair: any byte values, no packing.  trimAl's own validation admits at most 84 distinct
+// symbols (isalpha or ispunct), so this is reached only through the C ABI with arbitrary
+// bytes; the GPU tests also use it to tell a packing fault from an arithmetic one.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_identity_bytes(const uint8_t *__restrict__ raw,
                                                         size_t pitch, int ncol,
@@ -53,11 +54,11 @@ __global__ void __launch_bounds__(256) k_identity_bytes(const uint8_t *__restric
 
 cudaError_t launch_identity_bytes(const uint8_t *raw, size_t pitch, int ncol, const int *kept_rows,
                                   int nk, const uint8_t *col_drop, uint8_t indet, float *out,
-                                  int *hit_out, int *dst_out, cudaStream_t stream)
+                                  int *hit_out, int *dst_out, int num_sms, cudaStream_t stream)
 {
     const long long npairs = (long long)nk * (nk - 1) / 2;
     if (npairs <= 0) return cudaSuccess;
-    const int blocks = (int)std::min<long long>((npairs + 255) / 256, 148 * 16);
+    const int blocks = (int)std::min<long long>((npairs + 255) / 256, (long long)num_sms * 16);
     k_identity_bytes<<<blocks, 256, 0, stream>>>(raw, pitch, ncol, kept_rows, nk, col_drop, indet,
                                                  out, hit_out, dst_out);
     return cudaGetLastError();

@@ -38,11 +38,11 @@ __global__ void __launch_bounds__(256) k_byte_presence(const uint8_t *__restrict
 }
 
 cudaError_t launch_byte_presence(const uint8_t *raw, int nseq, int ncol, size_t pitch,
-                                 unsigned int *present256, cudaStream_t stream)
+                                 unsigned int *present256, int num_sms, cudaStream_t stream)
 {
     if (nseq == 0 || ncol == 0) return cudaSuccess;
     const long long total = (long long)nseq * ((ncol + 15) >> 4);
-    int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+    int blocks = (int)std::min<long long>((total + 255) / 256, (long long)num_sms * 8);
     k_byte_presence<<<blocks, 256, 0, stream>>>(raw, nseq, ncol, pitch, present256);
     return cudaGetLastError();
 }

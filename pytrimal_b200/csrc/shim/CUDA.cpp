@@ -589,9 +589,9 @@ bool cudaRemoveAllGaps(Alignment *alig, bool seqs, bool cols, bool keepSequences
   return true;
 }
 
-bool cudaRemoveDuplicates(Alignment *alig)
+bool cudaDuplicatePartners(Alignment *alig, std::vector<int> &partner)
 {
-  StartTiming("bool cudaRemoveDuplicates(Alignment *) ");
+  StartTiming("bool cudaDuplicatePartners(Alignment *, std::vector<int> &) ");
   const int n = alig->originalNumberOfSequences, L = alig->originalNumberOfResidues;
   if (alig->sequences == nullptr || n <= 1 || L <= 0) return false;
   for (int i = 0; i < n; i++)
@@ -616,8 +616,9 @@ bool cudaRemoveDuplicates(Alignment *alig)
   });
   // Cleaner.cpp:1493-1508: row i goes iff some later row x equals it, and the report names
   // the FIRST such x.  Inside a run (indices ascending) that is the first later member that
-  // compares equal byte for byte -- the hashes only chose who is compared.
-  std::vector<int> partner((size_t)n, -1);
+  // compares equal byte for byte -- the hashes only chose who is compared.  The caller's loop
+  // (the reference's own) marks and reports.
+  partner.assign((size_t)n, -1);
   for (size_t a = 0; a < (size_t)n;) {
     size_t b = a + 1;
     while (b < (size_t)n && h[2 * (size_t)idx[b]] == h[2 * (size_t)idx[a]] &&
@@ -630,12 +631,6 @@ bool cudaRemoveDuplicates(Alignment *alig)
           break;
         }
     a = b;
-  }
-  for (int i = 0; i < n; i++) {  // reports in the reference's order (i ascending)
-    if (partner[i] < 0) continue;
-    alig->saveSequences[i] = -1;
-    debug.report(InfoCode::RemovingDuplicateSequences,
-                 new std::string[2]{alig->seqsName[i], alig->seqsName[partner[i]]});
   }
   return true;
 }

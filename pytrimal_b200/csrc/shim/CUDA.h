@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <memory>
 #include <mutex>
+#include <vector>
 
 #include "Statistics/Gaps.h"
 #include "Statistics/Identity.h"
@@ -119,10 +120,13 @@ bool cudaAlignmentType(const Alignment *alig, int *type);
 // then runs the reference loop).
 //   cudaRemoveAllGaps   Cleaner::removeAllGapsSeqsAndCols (Cleaner.cpp:1331-1396): same mask
 //                       updates, same warnings, same counters
-//   cudaRemoveDuplicates Cleaner::removeDuplicates (Cleaner.cpp:1489-1509): row hashes on the
-//                       device, byte compares only inside groups of equal hashes
+//   cudaDuplicatePartners  the search of Cleaner::removeDuplicates (Cleaner.cpp:1489-1509):
+//                       partner[i] = the first later row equal to row i, or -1; row hashes on
+//                       the device, byte compares only inside groups of equal hashes.  What is
+//                       done with a duplicate stays in the reference's loop (pytrimal's build
+//                       also decrements numberOfSequences there, vanilla trimAl does not).
 bool cudaRemoveAllGaps(Alignment *alig, bool seqs, bool cols, bool keepSequences);
-bool cudaRemoveDuplicates(Alignment *alig);
+bool cudaDuplicatePartners(Alignment *alig, std::vector<int> &partner);
 
 // Alignment::fillMatrices' symbol validation (Alignment.cpp:657-664) from the device byte
 // histogram: true = decided, *valid says whether every byte is isalpha or

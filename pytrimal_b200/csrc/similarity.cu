@@ -83,14 +83,14 @@ __global__ void __launch_bounds__(256) k_sim_codes(const uint8_t *__restrict__ r
 
 cudaError_t launch_sim_codes(const uint8_t *raw, int nseq, int ncol, size_t pitch, int npad,
                              const uint8_t *lut256, const uint8_t *col_skip, uint8_t *codesT,
-                             unsigned long long *first_error, cudaStream_t stream)
+                             unsigned long long *first_error, int num_sms, cudaStream_t stream)
 {
     if (nseq == 0 || ncol == 0) return cudaSuccess;
     // padding rows (and nothing else survives the kernel below) are gaps
     cudaError_t e = cudaMemsetAsync(codesT, (int)SIM2_GAPCODE, (size_t)(pitch >> 5) * npad * 32, stream);
     if (e != cudaSuccess) return e;
     const long long total = (long long)nseq * (long long)(pitch >> 4);
-    const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+    const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)num_sms * 8);
     k_sim_codes<<<blocks, 256, 0, stream>>>(raw, nseq, ncol, pitch, npad, lut256, col_skip, codesT,
                                             first_error);
     return cudaGetLastError();

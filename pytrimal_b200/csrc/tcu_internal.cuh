@@ -154,7 +154,7 @@ __host__ __device__ inline void tile_to_blocks2(long long t, int nb, int sb_begi
 
 // launchers (each enqueues on `stream` and returns the launch status)
 cudaError_t launch_byte_presence(const uint8_t *raw, int nseq, int ncol, size_t pitch,
-                                 unsigned int *present256, cudaStream_t stream);
+                                 unsigned int *present256, int num_sms, cudaStream_t stream);
 cudaError_t launch_repitch_rows(const uint8_t *src, size_t stride, int nseq, int ncol, uint8_t *dst,
                                 size_t pitch, cudaStream_t stream);
 cudaError_t launch_byte_histogram(const uint8_t *raw, int nseq, int ncol, size_t pitch,
@@ -166,7 +166,7 @@ cudaError_t launch_pack_planes(const uint8_t *raw, size_t pitch, int ncol, const
 cudaError_t launch_identity2(int np, const Identity2Params &p, int num_sms, cudaStream_t stream);
 cudaError_t launch_identity_bytes(const uint8_t *raw, size_t pitch, int ncol, const int *kept_rows,
                                   int nk, const uint8_t *col_drop, uint8_t indet, float *out,
-                                  int *hit_out, int *dst_out, cudaStream_t stream);
+                                  int *hit_out, int *dst_out, int num_sms, cudaStream_t stream);
 cudaError_t launch_column_counts(const uint8_t *raw, int nseq, int ncol, size_t pitch,
                                  const uint8_t *row_drop, uint8_t sym_a, uint8_t sym_b,
                                  int *count_a, int *count_b, uint16_t *plane_a, uint16_t *plane_b,
@@ -177,7 +177,7 @@ cudaError_t launch_spurious_rows(const uint32_t *plane_gap, const uint32_t *plan
                                  uint32_t *flag_words, float *out, int num_sms, cudaStream_t stream);
 cudaError_t launch_sim_codes(const uint8_t *raw, int nseq, int ncol, size_t pitch, int npad,
                              const uint8_t *lut256, const uint8_t *col_skip, uint8_t *codesT,
-                             unsigned long long *first_error, cudaStream_t stream);
+                             unsigned long long *first_error, int num_sms, cudaStream_t stream);
 cudaError_t launch_sim_rows(const uint8_t *codesT, int nseq, int npad, int ngroups,
                             uint32_t *skipbits, unsigned long long *nbatches, uint32_t *ngmask,
                             cudaStream_t stream);

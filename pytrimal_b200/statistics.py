@@ -186,7 +186,7 @@ class DeviceAlignment:
 
     # -- K1 -------------------------------------------------------------------
     def identity(self, indet=None, save_seq=None, save_res=None, counts=False,
-                 keep_on_device=False, out=None, _debug_bytes=False, comm=None):
+                 keep_on_device=False, out=None, comm=None):
         """Packed identity array over kept pairs -- template.h:320-442.  With ``comm``
         the matrix always stays on every rank's device as well."""
         indet = self.alignment.indet if indet is None else indet
@@ -196,20 +196,16 @@ class DeviceAlignment:
         ident = np.empty(npairs, np.float32) if out is None else out
         assert ident.dtype == np.float32 and ident.size >= npairs and ident.flags.c_contiguous
         if comm is not None:
-            if counts or _debug_bytes:
+            if counts:
                 raise ValueError("counts are a single-GPU debugging output")
             _lib.check(self.lib.tcu_identity_all(self._h, comm._h, _p(ss, _i32p), _p(sr, _i32p),
                                                  indet, _p(ident, _f32p)))
             return ident[:npairs]
         hit = np.zeros(npairs, np.int32) if counts else None
         dst = np.zeros(npairs, np.int32) if counts else None
-        if _debug_bytes:
-            rc = self.lib.tcu_debug_identity_bytes(self._h, _p(ss, _i32p), _p(sr, _i32p), indet,
-                                                   _p(ident, _f32p), _p(hit, _i32p), _p(dst, _i32p))
-        else:
-            rc = self.lib.tcu_identity(self._h, _p(ss, _i32p), _p(sr, _i32p), indet,
-                                       _p(ident, _f32p), _p(hit, _i32p), _p(dst, _i32p),
-                                       1 if keep_on_device else 0)
+        rc = self.lib.tcu_identity(self._h, _p(ss, _i32p), _p(sr, _i32p), indet,
+                                   _p(ident, _f32p), _p(hit, _i32p), _p(dst, _i32p),
+                                   1 if keep_on_device else 0)
         _lib.check(rc)
         ident = ident[:npairs]
         return (ident, hit, dst) if counts else ident

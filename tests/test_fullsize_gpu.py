@@ -202,3 +202,37 @@ def test_c5_overlap_trimmer_full_size(gpu, pytrimal, seq_overlap, job):
     tag = ("%g" % seq_overlap).replace(".", "p")
     assert trimmed_equals_masks(out, m, g[f"trim_overlap_seq{tag}_seq"],
                                 g[f"trim_overlap_seq{tag}_res"])
+
+
+# ---- beyond the packed float array: 200 000 sequences ---------------------------------------
+def test_representatives_200k_sequences(gpu):
+    """tcu_representatives thresholds inside the identity kernel, so nothing of size 4*P exists:
+    200 000 sequences (P = 2 x 10^10 pairs; the packed float array alone would be 80 GB, its
+    host copy in the reference as much again) cluster with a 5 GB bit matrix.  The input is
+    built so that the answer is known: 4 000 families of 50 near-identical members (identity
+    ~0.94 inside a family, ~0.05 across), hence exactly one representative per family -- its
+    first member in the reference's visiting order."""
+    n, L, nfam = 200_000, 256, 4000
+    rng = np.random.default_rng(200)
+    aa = np.frombuffer(b"ARNDCQEGHILKMFPSTWYV", np.uint8)
+    anc = aa[rng.integers(0, 20, (nfam, L))]
+    fam = rng.permutation(np.repeat(np.arange(nfam), n // nfam))
+    m = anc[fam].copy()
+    sub = rng.random((n, L)) < 0.03
+    m[sub] = aa[rng.integers(0, 20, int(sub.sum()))]
+    lead = rng.integers(0, 9, n)
+    m[np.arange(L)[None, :] < lead[:, None]] = ord("-")          # ragged starts: lengths differ
+    with gpu.DeviceAlignment(m) as d:
+        reps = d.representatives(0.8, indet=X)
+        assert not d.identity_resident
+        order = gpu.cluster_order(d.sequence_lengths())
+        t = d.timings
+    seen = np.zeros(nfam, bool)
+    want = []
+    for s in order:
+        f = fam[s]
+        if not seen[f]:
+            seen[f] = True
+            want.append(int(s))
+    assert reps.tolist() == want
+    assert t["kernel_launches"] > 2 * (n // 1024)

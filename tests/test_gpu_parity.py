@@ -65,13 +65,27 @@ def test_identity_counts_and_ratio(gpu, port, n, L):
 
 
 @pytest.mark.parametrize("n,L", [(6, 46), (65, 257), (130, 300)])
-def test_identity_debug_kernel_agrees(gpu, port, n, L):
+def test_identity_arbitrary_bytes_bytewise_kernel(gpu, port, n, L):
+    """More than 126 distinct non-gap byte values (nothing trimAl's validation admits, but the
+    reference's kernels compare raw bytes): the byte-wise kernel behind the same entry points,
+    with masks, and the clustering on top of it."""
     rng = np.random.default_rng(n + L)
-    m = random_msa(rng, n, L)
+    m = rng.integers(0, 256, (n, L), dtype=np.uint8)
+    m[rng.random((n, L)) < 0.2] = ord("-")
+    m[rng.random((n, L)) < 0.05] = X
+    m[1:n // 2] = np.where(rng.random((n // 2 - 1, L)) < 0.7, m[0], m[1:n // 2])   # related rows
+    assert len(np.unique(m)) > 130
+    sr = np.arange(L, dtype=np.int32)
+    sr[rng.random(L) < 0.3] = -1
     with gpu.DeviceAlignment(m) as d:
-        ident, hit, dst = d.identity(X, counts=True, _debug_bytes=True)
+        ident, hit, dst = d.identity(X, counts=True)
+        masked = d.identity(X, save_res=sr)
+        reps = d.representatives(0.5, indet=X)
     oi, oh, od = port.identity(m, X, counts=True)
     assert (hit == oh).all() and (dst == od).all() and (bits(ident) == bits(oi)).all()
+    assert (bits(masked) == bits(port.identity(m, X, None, sr))).all()
+    order = port.cluster_order(port.sequence_lengths(m))
+    assert reps.tolist() == port.greedy_clusters(oi, n, order, 0.5).tolist()
 
 
 def test_identity_masks(gpu, port):
