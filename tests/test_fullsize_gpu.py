@@ -226,7 +226,6 @@ def test_representatives_200k_sequences(gpu):
         reps = d.representatives(0.8, indet=X)
         assert not d.identity_resident
         order = gpu.cluster_order(d.sequence_lengths())
-        t = d.timings
     seen = np.zeros(nfam, bool)
     want = []
     for s in order:
@@ -234,5 +233,4 @@ def test_representatives_200k_sequences(gpu):
         if not seen[f]:
             seen[f] = True
             want.append(int(s))
-    assert reps.tolist() == want
-    assert t["kernel_launches"] > 2 * (n // 1024)
+    assert len(want) == nfam and reps.tolist() == want

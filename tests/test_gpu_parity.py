@@ -64,7 +64,7 @@ def test_identity_counts_and_ratio(gpu, port, n, L):
     assert (bits(ident) == bits(oi)).all()
 
 
-@pytest.mark.parametrize("n,L", [(6, 46), (65, 257), (130, 300)])
+@pytest.mark.parametrize("n,L", [(12, 100), (65, 257), (130, 300)])
 def test_identity_arbitrary_bytes_bytewise_kernel(gpu, port, n, L):
     """More than 126 distinct non-gap byte values (nothing trimAl's validation admits, but the
     reference's kernels compare raw bytes): the byte-wise kernel behind the same entry points,
@@ -74,7 +74,7 @@ def test_identity_arbitrary_bytes_bytewise_kernel(gpu, port, n, L):
     m[rng.random((n, L)) < 0.2] = ord("-")
     m[rng.random((n, L)) < 0.05] = X
     m[1:n // 2] = np.where(rng.random((n // 2 - 1, L)) < 0.7, m[0], m[1:n // 2])   # related rows
-    assert len(np.unique(m)) > 130
+    assert len(np.unique(m)) > 128
     sr = np.arange(L, dtype=np.int32)
     sr[rng.random(L) < 0.3] = -1
     with gpu.DeviceAlignment(m) as d:
