@@ -319,15 +319,20 @@ def timed_device_steps(env, step, sync, steps, warmup, stream):
     sync()
     env.barrier()
     clock_note = None
-    if env.rank == 0 and len(sampler.rows) < 3:
-        # the timed region was shorter than a few 100 ms sampling periods: keep the same steps
-        # running, untimed, until the sampler has seen the clocks under this load
+    # the timed region may be shorter than a few 100 ms sampling periods: every rank then keeps
+    # the same steps running, untimed, for the same number of rounds (the steps of some
+    # workloads are collective: all ranks must make the same calls) until rank 0's sampler
+    # has seen the clocks under this load
+    short = env.max_over_ranks([1.0 if (env.rank == 0 and len(sampler.rows) < 3) else 0.0])[0] > 0
+    if short:
         clock_note = ("timed region shorter than the sampling period: clocks sampled over the "
                       "same steps repeated untimed right after it")
-        t_end = time.perf_counter() + 1.5
-        while len(sampler.rows) < 4 and time.perf_counter() < t_end:
+        ms_step = max(e0.elapsed_time(e1) / max(steps, 1), 1e-3)
+        rounds = int(env.max_over_ranks([min(2000.0, max(1.0, 600.0 / ms_step))])[0])
+        for _ in range(rounds):
             step()
-            sync()
+        sync()
+        env.barrier()
     clocks = sampler.stop() if env.rank == 0 else None
     if clocks is not None and clock_note:
         clocks["note"] = clock_note
@@ -646,7 +651,9 @@ def run_spurious(args, env):
     e2e_s = wall_steps(env, e2e_step, args.e2e_steps)
     if rank == 0:
         peaks = measured_peaks()
-        byts = (n * L + 4 * n) / world            # SURVEY 8d algorithmic bytes, this rank's share
+        # the closed-form (column-histogram) mode is accounted as two passes over the
+        # alignment, 2*n*L + 4*n bytes; this rank's share of the rows
+        byts = (2 * n * L + 4 * n) / world
         achieved = byts / (kernel_ms_max * 1e-3) / 1e9
         line = {
             "metric": METRICS["C5"], "value": value, "unit": UNIT, "n_gpus": world,
@@ -671,8 +678,9 @@ def run_spurious(args, env):
                          "traffic": ncu_traffic(f"spurious C5 {n}x{L}") if world == 1 and not args.rows else None,
                          "kernel": "tcu::k_column_counts<true> + k_spurious_flags + k_spurious_rows",
                          "kernel_ms": kernel_ms_max, "peak_source": peaks["source"],
-                         "note": "algorithmic bytes n*L + 4*n (SURVEY 8d); the kernels move n*L read + "
-                                 "n*L/4 written + n*L/4 read (bit planes for the row pass)"},
+                         "note": "algorithmic bytes 2*n*L + 4*n (SURVEY 8d, histogram mode = two passes); "
+                                 "the kernels move n*L read + n*L/4 written + n*L/4 read (the row pass "
+                                 "reads bit planes the column pass left behind)"},
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline("C5", n, L, seed)

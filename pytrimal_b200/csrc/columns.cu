@@ -21,6 +21,19 @@ __device__ __forceinline__ uint32_t byte_eq_ones(uint32_t x, uint32_t pat)
     return __vcmpeq4(x, pat) & 0x01010101u;
 }
 
+// The same test with the answer in bit 7 of every byte lane (0x80 = equal), four
+// instructions instead of the six of __vcmpeq4 + mask (an emulation on sm_100): a byte of
+// x ^ pat is zero iff neither its top bit nor a carry out of its low seven bits + 0x7f is set.
+__device__ __forceinline__ uint32_t byte_eq_flags80(uint32_t x, uint32_t pat)
+{
+    const uint32_t d = x ^ pat;
+    const uint32_t t = (d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+    return ~(t | d) & 0x80808080u;
+}
+// four 0x80 flags -> one nibble (bit k = byte k): the product lines flag k up at bit 28 + k,
+// all partial products land on distinct bits
+__device__ __forceinline__ uint32_t flags80_to_nibble(uint32_t f) { return (f * 0x00204081u) >> 28; }
+
 // One CTA = 32 column groups of 16 columns (512 columns, one warp-wide 512-byte row segment)
 // x CC_LANES row lanes; grid.x tiles the columns, grid.y cuts the rows into slices.  Each
 // thread streams its rows CC_UNROLL at a time (that many independent 16-byte loads in
@@ -84,15 +97,14 @@ __global__ void __launch_bounds__(32 * CC_LANES) k_column_counts(
                 uint32_t bits_a = 0, bits_b = 0;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    const uint32_t ea = byte_eq_ones(w[q], pat_a);
-                    acc_a[q] += ea;
-                    // the four 0/1 bytes -> one nibble (bit k = column 4q + k): the product
-                    // lines byte k up at bit 24 + k
-                    if (TWO) bits_a |= ((ea * 0x01020408u) >> 24 & 0xFu) << (4 * q);
+                    const uint32_t fa = byte_eq_flags80(w[q], pat_a);
+                    acc_a[q] += fa >> 7;
                     if (TWO) {
-                        const uint32_t eb = byte_eq_ones(w[q], pat_b);
-                        acc_b[q] += eb;
-                        bits_b |= ((eb * 0x01020408u) >> 24 & 0xFu) << (4 * q);
+                        const uint32_t fb = byte_eq_flags80(w[q], pat_b);
+                        acc_b[q] += fb >> 7;
+                        // nibble q of the row's 16-column plane word (bit k = column 4q + k)
+                        bits_a += flags80_to_nibble(fa) << (4 * q);
+                        bits_b += flags80_to_nibble(fb) << (4 * q);
                     }
                 }
                 if (TWO && plane_a) {
