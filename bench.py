@@ -411,6 +411,11 @@ def run_identity(args, env):
     kernel_ms, pack_ms = t["kernel_ms"], t["pack_ms"]
     ms_total_max, kernel_ms_max = env.max_over_ranks([ms_total, kernel_ms])
     value = pairs_total * L * args.steps / (ms_total_max * 1e-3)
+    kernel_ms_ranks = [kernel_ms]
+    if world > 1:
+        box = [None] * world
+        env.dist.all_gather_object(box, float(kernel_ms))
+        kernel_ms_ranks = box
 
     # ---------------- bit-identity of this rank's band with the reference ----------------
     verify = {"checked": False}
@@ -546,6 +551,7 @@ def run_identity(args, env):
                 "unit": "TFLOP/s", "frac": achieved_tops / peaks["int8_tops"],
                 "traffic": ncu_traffic(f"{kernel_name} {args.workload} {n}x{L}") if full_size else None,
                 "kernel": kernel_name, "kernel_ms": kernel_ms_max, "pack_ms": pack_ms,
+                "kernel_ms_per_rank": [round(v, 3) for v in kernel_ms_ranks],
                 "peak_source": peaks["int8_source"],
                 "frac_vs_2x_bf16_dense": achieved_tops / (2.0 * peaks["bf16_tflops"]),
                 "note": "algorithmic int8 tensor ops = 42 per pair-column (SURVEY 8d: the one-hot GEMM "

@@ -10,6 +10,7 @@
 #include <time.h>
 
 #include <algorithm>
+#include <map>
 #include <mutex>
 #include <new>
 #include <string>
@@ -352,7 +353,15 @@ static float ev_ms(cudaEvent_t a, cudaEvent_t b)
 struct tcu_comm {
     NcclComm comm = nullptr;
     int rank = 0, world = 1, device = 0;
+    // peer memory over CUDA IPC: device allocations of the other ranks mapped into this
+    // process (per rank: handle bytes -> mapped base), so that bands are pulled device to
+    // device by the copy engines over NVLink instead of going through NCCL's transfer kernels
+    std::vector<std::map<std::string, void *>> opened;
+    uint8_t *d_sync = nullptr;   // handle exchange area + the word of the stream-ordered barriers
+    uint8_t *h_sync = nullptr;   // pinned mirror
+    bool ipc_usable = true;      // cleared for good on the first failure (agreed by all ranks)
 };
+constexpr size_t COMM_SYNC_BYTES = 64 * 64 + 256;  // up to 64 ranks x 64-byte IPC handles + flags
 
 static int nccl_fail(int r, const char *what)
 {
@@ -447,6 +456,14 @@ extern "C" int tcu_comm_create(const void *id, int rank, int world, int device, 
         delete c;
         return nccl_fail(r, "ncclCommInitRank");
     }
+    c->opened.resize((size_t)world);
+    if (world > 64 || cudaMalloc((void **)&c->d_sync, COMM_SYNC_BYTES) != cudaSuccess ||
+        cudaHostAlloc((void **)&c->h_sync, COMM_SYNC_BYTES, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        c->ipc_usable = false;  // the NCCL path needs neither
+    } else {
+        cudaMemset(c->d_sync, 0, COMM_SYNC_BYTES);
+    }
     *out = c;
     return TCU_OK;
 }
@@ -454,10 +471,13 @@ extern "C" int tcu_comm_create(const void *id, int rank, int world, int device, 
 extern "C" void tcu_comm_destroy(tcu_comm *c)
 {
     if (!c) return;
-    if (c->comm) {
-        cudaSetDevice(c->device);
-        nccl_api().CommDestroy(c->comm);
-    }
+    cudaSetDevice(c->device);
+    for (auto &per_rank : c->opened)
+        for (auto &kv : per_rank) cudaIpcCloseMemHandle(kv.second);
+    if (c->d_sync) cudaFree(c->d_sync);
+    if (c->h_sync) cudaFreeHost(c->h_sync);
+    if (c->comm) nccl_api().CommDestroy(c->comm);
+    cudaGetLastError();
     delete c;
 }
 
@@ -489,6 +509,100 @@ static int comm_allgatherv(tcu_comm *c, void *buf, const size_t *off, const size
     }
     NK(api.GroupEnd());
     return TCU_OK;
+}
+
+// ---------------------------------------------------------------------------
+// All-gather over peer memory.  `buf` is the base of a cudaMalloc allocation of the same
+// size on every rank; rank r owns [off[r], off[r] + cnt[r]).  Step 1 (peer_prepare, before
+// the producing kernel is launched): the ranks exchange CUDA IPC handles of `buf` and map
+// the ones they have not seen yet (allocations come from the library's pool, so after the
+// first call nothing is mapped any more); all ranks agree on whether that worked.  Step 2
+// (peer_allgatherv, after the producing kernel, stream-ordered): a one-word all-reduce tells
+// every rank that all bands are written, each rank then PULLS the other bands with plain
+// device-to-device copies (copy engines, NVLink / NVSwitch: no SM is taken from the compute
+// kernels and the transfer runs at link speed), and a second one-word all-reduce keeps any
+// rank from running ahead and rewriting its band while a peer still reads it.
+// ---------------------------------------------------------------------------
+static int comm_allreduce_i32(tcu_comm *c, int *buf, size_t count, cudaStream_t stream);
+static int comm_allgatherv(tcu_comm *c, void *buf, const size_t *off, const size_t *cnt,
+                           cudaStream_t stream);
+
+static bool peer_prepare(tcu_comm *c, void *buf, std::vector<void *> &peer_base, cudaStream_t stream)
+{
+    if (!c->ipc_usable || !c->d_sync) return false;
+    peer_base.assign((size_t)c->world, nullptr);
+    int ok = 1;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof mine);
+    if (cudaIpcGetMemHandle(&mine, buf) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    // my handle into my slot, slots all-gathered (tiny), back to the host
+    memcpy(c->h_sync + 64 * (size_t)c->rank, &mine, 64);
+    std::vector<size_t> off((size_t)c->world), cnt((size_t)c->world, 64);
+    for (int r = 0; r < c->world; r++) off[r] = 64 * (size_t)r;
+    bool comm_ok = cudaMemcpyAsync(c->d_sync + off[c->rank], c->h_sync + off[c->rank], 64,
+                                   cudaMemcpyHostToDevice, stream) == cudaSuccess &&
+                   comm_allgatherv(c, c->d_sync, off.data(), cnt.data(), stream) == TCU_OK &&
+                   cudaMemcpyAsync(c->h_sync, c->d_sync, 64 * (size_t)c->world, cudaMemcpyDeviceToHost,
+                                   stream) == cudaSuccess &&
+                   cudaStreamSynchronize(stream) == cudaSuccess;
+    if (!comm_ok) {
+        cudaGetLastError();
+        c->ipc_usable = false;  // a failed collective: nothing sensible can be agreed any more
+        return false;
+    }
+    for (int r = 0; r < c->world && ok; r++) {
+        if (r == c->rank) {
+            peer_base[r] = buf;
+            continue;
+        }
+        const std::string key((const char *)c->h_sync + 64 * (size_t)r, 64);
+        auto it = c->opened[r].find(key);
+        if (it == c->opened[r].end()) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, key.data(), 64);
+            void *p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ok = 0;
+                break;
+            }
+            it = c->opened[r].emplace(key, p).first;
+        }
+        peer_base[r] = it->second;
+    }
+    // agree: the sum of the ok flags must be `world`
+    int *flag = (int *)(c->h_sync + 64 * 64);
+    *flag = ok;
+    int *d_flag = (int *)(c->d_sync + 64 * 64);
+    comm_ok = cudaMemcpyAsync(d_flag, flag, sizeof(int), cudaMemcpyHostToDevice, stream) == cudaSuccess &&
+              comm_allreduce_i32(c, d_flag, 1, stream) == TCU_OK &&
+              cudaMemcpyAsync(flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, stream) == cudaSuccess &&
+              cudaStreamSynchronize(stream) == cudaSuccess;
+    if (!comm_ok || *flag != c->world) {
+        cudaGetLastError();
+        c->ipc_usable = false;
+        return false;
+    }
+    return true;
+}
+
+static int peer_allgatherv(tcu_comm *c, void *buf, const std::vector<void *> &peer_base,
+                           const size_t *off, const size_t *cnt, cudaStream_t stream)
+{
+    int *d_word = (int *)(c->d_sync + 64 * 64 + 64);
+    int rc = comm_allreduce_i32(c, d_word, 1, stream);  // every band is written
+    if (rc != TCU_OK) return rc;
+    for (int d = 1; d < c->world; d++) {
+        const int r = (c->rank + d) % c->world;  // staggered: not everybody reads rank 0 first
+        if (cnt[r] == 0) continue;
+        CK(cudaMemcpyAsync((uint8_t *)buf + off[r], (const uint8_t *)peer_base[r] + off[r], cnt[r],
+                           cudaMemcpyDeviceToDevice, stream));
+    }
+    return comm_allreduce_i32(c, d_word, 1, stream);  // every band is read
 }
 
 static int comm_allreduce_i32(tcu_comm *c, int *buf, size_t count, cudaStream_t stream)
@@ -1655,7 +1769,8 @@ static size_t bits_bytes(int n) { return std::max<size_t>(bits_total_words(n), 4
 // NVLink while the other is computed was considered and dropped: the NCCL transfer kernels
 // would take SM slots from the persistent identity kernel, whose static tile schedule turns
 // every delayed CTA into tail latency.)
-static int bits_allgather(tcu_msa *m, tcu_comm *comm, cudaStream_t stream)
+static int bits_allgather(tcu_msa *m, tcu_comm *comm, const std::vector<void *> *peer_base,
+                          cudaStream_t stream)
 {
     std::vector<size_t> off(comm->world), cnt(comm->world);
     const size_t slab_b = bits_slab_words(m->nk) * sizeof(uint32_t);
@@ -1665,6 +1780,7 @@ static int bits_allgather(tcu_msa *m, tcu_comm *comm, cudaStream_t stream)
         off[r] = (size_t)b0 * slab_b;
         cnt[r] = (size_t)(b1 - b0) * slab_b;
     }
+    if (peer_base) return peer_allgatherv(comm, m->d_bits, *peer_base, off.data(), cnt.data(), stream);
     return comm_allgatherv(comm, m->d_bits, off.data(), cnt.data(), stream);
 }
 
@@ -1976,11 +2092,13 @@ static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res,
         } else {
             int b0 = 0, b1 = m->nsb;
             if (comm) tcu_shard_blocks(m->nk, comm->rank, comm->world, &b0, &b1);
+            std::vector<void *> peer_base;
+            const bool use_peer = comm && peer_prepare(comm, m->d_bits, peer_base, m->stream);
             r = identity_launch(m, b0, b1, nullptr, nullptr, nullptr, m->d_bits, threshold);
             if (r != TCU_OK) return r;
             CK(cudaEventRecord(m->ev[3], m->stream));
             if (comm) {
-                r = bits_allgather(m, comm, m->stream);
+                r = bits_allgather(m, comm, use_peer ? &peer_base : nullptr, m->stream);
                 if (r != TCU_OK) return r;
             }
             CK(cudaEventRecord(m->ev[4], m->stream));

@@ -20,6 +20,8 @@ Jobs
                 creation order, keep-masks, identity digests, selectMethod
   C5            Overlap::calculateSpuriousVector(0.5) on 100 000 x 2 000 (the vector itself)
   C5.seq0.5  C5.seq50    OverlapTrimmer(sequence_overlap=0.5 | 50, residue_overlap=.5) keep-masks
+  C5.seq75.res0.7        OverlapTrimmer(sequence_overlap=75, residue_overlap=.7): a selective variant
+                         (drops about a quarter of the sequences)
 """
 import json
 import os
@@ -117,12 +119,15 @@ def job_C5(out):
     out["gaps"] = oracle.Ref(m).gaps()[0]
 
 
-def job_C5_trim(seq_overlap):
+def job_C5_trim(seq_overlap, res_overlap=0.5):
     def run(out):
         m = msa_of("C5")
-        ks, kr = oracle.Ref(m).trim("overlap", [0.5, seq_overlap])
+        ks, kr = oracle.Ref(m).trim("overlap", [res_overlap, seq_overlap])
         tag = ("%g" % seq_overlap).replace(".", "p")
+        if res_overlap != 0.5:
+            tag += "_res" + ("%g" % res_overlap).replace(".", "p")
         out[f"trim_overlap_seq{tag}_seq"], out[f"trim_overlap_seq{tag}_res"] = ks, kr
+        out["params"] = np.array([seq_overlap, res_overlap], np.float64)
     return run
 
 
@@ -136,6 +141,8 @@ JOBS = {
     "C5": ("C5", job_C5),
     "C5.seq0.5": ("C5", job_C5_trim(0.5)),
     "C5.seq50": ("C5", job_C5_trim(50.0)),
+    # the literal configuration keeps every sequence of this alignment; a selective variant
+    "C5.seq75.res0.7": ("C5", job_C5_trim(75.0, 0.7)),
 }
 
 

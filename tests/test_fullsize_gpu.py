@@ -192,14 +192,19 @@ def test_c5_spurious_vector_full_size(gpu, port):
     assert (bits(port.spurious_hist(m, X, 0.5)) == bits(sp)).all()
 
 
-@pytest.mark.parametrize("seq_overlap,job", [(0.5, "C5.seq0.5"), (50, "C5.seq50")])
-def test_c5_overlap_trimmer_full_size(gpu, pytrimal, seq_overlap, job):
+@pytest.mark.parametrize("seq_overlap,res_overlap,job", [(0.5, 0.5, "C5.seq0.5"), (50, 0.5, "C5.seq50"),
+                                                         (75, 0.7, "C5.seq75.res0.7")])
+def test_c5_overlap_trimmer_full_size(gpu, pytrimal, seq_overlap, res_overlap, job):
+    """The literal configuration (sequence_overlap=0.5 is 0.5 %) and its 50 % reading
+    keep every sequence of this alignment; the third case drops about a quarter of them."""
     g = golden(job)
     m = msa_of("C5", g)
     ali = pytrimal.Alignment([b"s%d" % i for i in range(m.shape[0])], [bytes(r) for r in m])
-    out = pytrimal.OverlapTrimmer(sequence_overlap=seq_overlap, residue_overlap=0.5,
+    out = pytrimal.OverlapTrimmer(sequence_overlap=seq_overlap, residue_overlap=res_overlap,
                                   platform="cuda").trim(ali)
     tag = ("%g" % seq_overlap).replace(".", "p")
+    if res_overlap != 0.5:
+        tag += "_res" + ("%g" % res_overlap).replace(".", "p")
     assert trimmed_equals_masks(out, m, g[f"trim_overlap_seq{tag}_seq"],
                                 g[f"trim_overlap_seq{tag}_res"])
 
