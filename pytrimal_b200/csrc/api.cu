@@ -585,24 +585,47 @@ static bool peer_prepare(tcu_comm *c, void *buf, std::vector<void *> &peer_base,
     if (!comm_ok || *flag != c->world) {
         cudaGetLastError();
         c->ipc_usable = false;
+        if (getenv("TCU_TRACE")) fprintf(stderr, "[tcu] rank %d: peer memory unavailable (ok flags %d of %d), using NCCL transfers\n", c->rank, *flag, c->world);
         return false;
     }
     return true;
 }
 
+// A rank's share as a 2-D block: `height` lines of `width` bytes, `pitch` bytes apart, the
+// first at byte offset `off` of the common buffer (a 1-D range is one line).
+struct PeerBlock {
+    size_t off = 0, width = 0, height = 0, pitch = 0;
+};
+
 static int peer_allgatherv(tcu_comm *c, void *buf, const std::vector<void *> &peer_base,
-                           const size_t *off, const size_t *cnt, cudaStream_t stream)
+                           const PeerBlock *blk, cudaStream_t stream)
 {
     int *d_word = (int *)(c->d_sync + 64 * 64 + 64);
+    static const bool trace = getenv("TCU_TRACE") != nullptr;
+    cudaEvent_t te[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (trace)
+        for (auto &e : te) cudaEventCreate(&e);
+    if (trace) cudaEventRecord(te[0], stream);
     int rc = comm_allreduce_i32(c, d_word, 1, stream);  // every band is written
     if (rc != TCU_OK) return rc;
+    if (trace) cudaEventRecord(te[1], stream);
     for (int d = 1; d < c->world; d++) {
         const int r = (c->rank + d) % c->world;  // staggered: not everybody reads rank 0 first
-        if (cnt[r] == 0) continue;
-        CK(cudaMemcpyAsync((uint8_t *)buf + off[r], (const uint8_t *)peer_base[r] + off[r], cnt[r],
-                           cudaMemcpyDeviceToDevice, stream));
+        const PeerBlock &b = blk[r];
+        if (b.width == 0 || b.height == 0) continue;
+        CK(cudaMemcpy2DAsync((uint8_t *)buf + b.off, b.pitch, (const uint8_t *)peer_base[r] + b.off,
+                             b.pitch, b.width, b.height, cudaMemcpyDeviceToDevice, stream));
     }
-    return comm_allreduce_i32(c, d_word, 1, stream);  // every band is read
+    if (trace) cudaEventRecord(te[2], stream);
+    rc = comm_allreduce_i32(c, d_word, 1, stream);  // every band is read
+    if (trace) {
+        cudaEventRecord(te[3], stream);
+        cudaStreamSynchronize(stream);
+        fprintf(stderr, "[tcu] rank %d peer all-gather: barrier %.3f ms, copies %.3f ms, barrier %.3f ms\n",
+                c->rank, ev_ms(te[0], te[1]), ev_ms(te[1], te[2]), ev_ms(te[2], te[3]));
+        for (auto &e : te) cudaEventDestroy(e);
+    }
+    return rc;
 }
 
 static int comm_allreduce_i32(tcu_comm *c, int *buf, size_t count, cudaStream_t stream)
@@ -1780,7 +1803,21 @@ static int bits_allgather(tcu_msa *m, tcu_comm *comm, const std::vector<void *> 
         off[r] = (size_t)b0 * slab_b;
         cnt[r] = (size_t)(b1 - b0) * slab_b;
     }
-    if (peer_base) return peer_allgatherv(comm, m->d_bits, *peer_base, off.data(), cnt.data(), stream);
+    if (peer_base) {
+        // of slab S only the rows >= 128 S carry data before the mirror pass: a band's slabs
+        // are pulled as one 2-D block that starts at the band's first row
+        std::vector<PeerBlock> blk((size_t)comm->world);
+        for (int r = 0; r < comm->world; r++) {
+            int b0, b1;
+            tcu_shard_blocks(m->nk, r, comm->world, &b0, &b1);
+            const size_t first_row = std::min<size_t>((size_t)b0 * IB, (size_t)m->nk);
+            blk[r].pitch = slab_b;
+            blk[r].off = (size_t)b0 * slab_b + first_row * 16;
+            blk[r].width = ((size_t)m->nk - first_row) * 16;
+            blk[r].height = (size_t)(b1 - b0);
+        }
+        return peer_allgatherv(comm, m->d_bits, *peer_base, blk.data(), stream);
+    }
     return comm_allgatherv(comm, m->d_bits, off.data(), cnt.data(), stream);
 }
 
@@ -2153,10 +2190,13 @@ static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res,
         CK(cudaEventRecord(m->ev[3], m->stream));
         for (int k = 1; k < world; k++) {
             tcu_msa *p = m->peers[(size_t)k - 1];
-            if (bb[k + 1] > bb[k])
-                CK(cudaMemcpyPeerAsync(m->d_bits + (size_t)bb[k] * slab_w, m->device, p->d_bits,
-                                       p->device, (size_t)(bb[k + 1] - bb[k]) * slab_w * sizeof(uint32_t),
-                                       m->stream));
+            if (bb[k + 1] > bb[k]) {
+                // rows below the band's first row carry nothing before the mirror pass
+                const size_t first_row = std::min<size_t>((size_t)bb[k] * IB, (size_t)n);
+                CK(cudaMemcpy2DAsync(m->d_bits + (size_t)bb[k] * slab_w + first_row * 4, slab_w * 4,
+                                     p->d_bits + first_row * 4, slab_w * 4, ((size_t)n - first_row) * 16,
+                                     (size_t)(bb[k + 1] - bb[k]), cudaMemcpyDeviceToDevice, m->stream));
+            }
             m->timings.kernel_ms = std::max(m->timings.kernel_ms, p->timings.kernel_ms);
             m->timings.kernel_launches += p->timings.kernel_launches;
         }
