@@ -184,9 +184,11 @@ __global__ void __launch_bounds__(256) k_sim_rows(const uint8_t *__restrict__ co
 // ---------------------------------------------------------------------------
 constexpr int SIM2_NPROD = 9;
 constexpr int SIM2_MAX_SLOTS = 9;
-constexpr int SIM2_CS = 68;                          // floats per column of a slot: [column][num 32 | den 32 | pad 4],
-                                                     // 8 lanes x LDS.128 cover the 32 banks (68 % 32 == 4)
-constexpr int SIM2_SLOT_WORDS = 32 * SIM2_CS;
+constexpr int SIM2_CS = 36;                          // floats per column of a slot: [column][num 32 | pad 4],
+                                                     // 8 lanes x LDS.128 cover the 32 banks (36 % 32 == 4)
+constexpr int SIM2_W_OFF = 32 * SIM2_CS;             // then the batch's 32 weights w = 1 - id (one per inner row)
+constexpr int SIM2_M_OFF = SIM2_W_OFF + 32;          // and one word per column: in which inner rows the pair counts
+constexpr int SIM2_SLOT_WORDS = SIM2_M_OFF + 32;
 constexpr int SIM2_THREADS = 384;                    // 3 warps per sub-partition
 constexpr int SIM2_TROW = 64;                        // table row stride in floats (256 B: offset = a_j << 8 | 4 a_k)
 constexpr int SIM2_TABLE_WORDS = 32 * SIM2_TROW;
@@ -266,33 +268,277 @@ __device__ __forceinline__ float sim2_num_add(float acc, const Sim2NumBatch &B)
     return acc;
 }
 
-__device__ __forceinline__ float sim2_consume(Sim2Walk W, unsigned long long btot, int lane, int off,
-                                              uint32_t zero)
+// order-pinned forms (asm volatile keeps the relative order of these statements through the
+// compiler; ptxas schedules from that order)
+__device__ __forceinline__ float v_fadd(float a, float b)
 {
-    const bool lane0 = lane == 0;
-    lane = lane * SIM2_CS + off;  // word offset of the lane's terms inside a slot
+    float d;
+    asm volatile("add.rn.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
+__device__ __forceinline__ float4 v_lds128(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ uint32_t v_lds32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// One batch of a chain, refilling the registers in place: as soon as the four terms of an
+// LDS.128 have been added, the same four registers are loaded with the corresponding terms of
+// the NEXT batch.  A batch therefore lives in 32 registers (not 2 x 32), every load has a whole
+// batch (128 cycles of dependent additions) to return, and the loads issue in the shadow of
+// the chain without being tied to its results.
+//   numerator  : R = the lane's (column's) 32 terms w * D
+//   denominator: R = the batch's 32 weights w (the same for every column: broadcast loads, one
+//                wavefront each) and `mask` says in which inner rows the lane's column counts;
+//                a skipped row is a skipped (predicated-off) addition, i.e. + 0 exactly.
+template <bool DEN>
+__device__ __forceinline__ float sim2_chain_refill(float acc, Sim2NumBatch &R, uint32_t mask,
+                                                   uint32_t next_addr)
+{
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        if (!DEN || (mask & (1u << (4 * q + 0)))) acc = v_fadd(acc, R.a[q].x);
+        if (!DEN || (mask & (1u << (4 * q + 1)))) acc = v_fadd(acc, R.a[q].y);
+        if (!DEN || (mask & (1u << (4 * q + 2)))) acc = v_fadd(acc, R.a[q].z);
+        if (!DEN || (mask & (1u << (4 * q + 3)))) acc = v_fadd(acc, R.a[q].w);
+        R.a[q] = v_lds128(next_addr + 16u * q);
+    }
+    return acc;
+}
+template <bool DEN>
+__device__ __forceinline__ float sim2_chain(float acc, const Sim2NumBatch &R, uint32_t mask)
+{
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        if (!DEN || (mask & (1u << (4 * q + 0)))) acc = v_fadd(acc, R.a[q].x);
+        if (!DEN || (mask & (1u << (4 * q + 1)))) acc = v_fadd(acc, R.a[q].y);
+        if (!DEN || (mask & (1u << (4 * q + 2)))) acc = v_fadd(acc, R.a[q].z);
+        if (!DEN || (mask & (1u << (4 * q + 3)))) acc = v_fadd(acc, R.a[q].w);
+    }
+    return acc;
+}
+
+
+// The denominator chain of one batch as ONE block of PTX: a skipped inner row must cost nothing
+// in the dependent chain, so every addition is predicated on its bit of the column's mask, and the
+// predicates are formed well ahead of their use -- two rotating sets (4 + 3 predicate registers):
+// while the additions of one set issue, the other set already holds the bits of the next inner
+// rows, and is reloaded right after its last addition.  (Left to the compiler the tests become
+// one R2P per byte of the mask immediately in front of the eight additions that need it, whose
+// latency then sits in the chain four times per batch.)  With `refill`, the 32 weights of the
+// next batch are loaded in place as in sim2_chain_refill.
+__device__ __forceinline__ float sim2_den_chain_refill(float acc, Sim2NumBatch &R, uint32_t mask,
+                                                       uint32_t next_addr)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred a0, a1, a2, a3, b0, b1, b2;\n"
+        ".reg .b32 t;\n"
+        "and.b32 t, %33, 1; setp.ne.u32 a0, t, 0;\n"
+        "and.b32 t, %33, 2; setp.ne.u32 a1, t, 0;\n"
+        "and.b32 t, %33, 4; setp.ne.u32 a2, t, 0;\n"
+        "and.b32 t, %33, 8; setp.ne.u32 a3, t, 0;\n"
+        "and.b32 t, %33, 16; setp.ne.u32 b0, t, 0;\n"
+        "and.b32 t, %33, 32; setp.ne.u32 b1, t, 0;\n"
+        "and.b32 t, %33, 64; setp.ne.u32 b2, t, 0;\n"
+        "@a0 add.rn.f32 %0, %0, %1;\n"
+        "@a1 add.rn.f32 %0, %0, %2;\n"
+        "@a2 add.rn.f32 %0, %0, %3;\n"
+        "@a3 add.rn.f32 %0, %0, %4;\n"
+        "ld.shared.v4.f32 {%1, %2, %3, %4}, [%34+0];\n"
+        "and.b32 t, %33, 128; setp.ne.u32 a0, t, 0;\n"
+        "and.b32 t, %33, 256; setp.ne.u32 a1, t, 0;\n"
+        "and.b32 t, %33, 512; setp.ne.u32 a2, t, 0;\n"
+        "and.b32 t, %33, 1024; setp.ne.u32 a3, t, 0;\n"
+        "@b0 add.rn.f32 %0, %0, %5;\n"
+        "@b1 add.rn.f32 %0, %0, %6;\n"
+        "@b2 add.rn.f32 %0, %0, %7;\n"
+        "and.b32 t, %33, 2048; setp.ne.u32 b0, t, 0;\n"
+        "and.b32 t, %33, 4096; setp.ne.u32 b1, t, 0;\n"
+        "and.b32 t, %33, 8192; setp.ne.u32 b2, t, 0;\n"
+        "@a0 add.rn.f32 %0, %0, %8;\n"
+        "ld.shared.v4.f32 {%5, %6, %7, %8}, [%34+16];\n"
+        "@a1 add.rn.f32 %0, %0, %9;\n"
+        "@a2 add.rn.f32 %0, %0, %10;\n"
+        "@a3 add.rn.f32 %0, %0, %11;\n"
+        "and.b32 t, %33, 16384; setp.ne.u32 a0, t, 0;\n"
+        "and.b32 t, %33, 32768; setp.ne.u32 a1, t, 0;\n"
+        "and.b32 t, %33, 65536; setp.ne.u32 a2, t, 0;\n"
+        "and.b32 t, %33, 131072; setp.ne.u32 a3, t, 0;\n"
+        "@b0 add.rn.f32 %0, %0, %12;\n"
+        "ld.shared.v4.f32 {%9, %10, %11, %12}, [%34+32];\n"
+        "@b1 add.rn.f32 %0, %0, %13;\n"
+        "@b2 add.rn.f32 %0, %0, %14;\n"
+        "and.b32 t, %33, 262144; setp.ne.u32 b0, t, 0;\n"
+        "and.b32 t, %33, 524288; setp.ne.u32 b1, t, 0;\n"
+        "and.b32 t, %33, 1048576; setp.ne.u32 b2, t, 0;\n"
+        "@a0 add.rn.f32 %0, %0, %15;\n"
+        "@a1 add.rn.f32 %0, %0, %16;\n"
+        "ld.shared.v4.f32 {%13, %14, %15, %16}, [%34+48];\n"
+        "@a2 add.rn.f32 %0, %0, %17;\n"
+        "@a3 add.rn.f32 %0, %0, %18;\n"
+        "and.b32 t, %33, 2097152; setp.ne.u32 a0, t, 0;\n"
+        "and.b32 t, %33, 4194304; setp.ne.u32 a1, t, 0;\n"
+        "and.b32 t, %33, 8388608; setp.ne.u32 a2, t, 0;\n"
+        "and.b32 t, %33, 16777216; setp.ne.u32 a3, t, 0;\n"
+        "@b0 add.rn.f32 %0, %0, %19;\n"
+        "@b1 add.rn.f32 %0, %0, %20;\n"
+        "ld.shared.v4.f32 {%17, %18, %19, %20}, [%34+64];\n"
+        "@b2 add.rn.f32 %0, %0, %21;\n"
+        "and.b32 t, %33, 33554432; setp.ne.u32 b0, t, 0;\n"
+        "and.b32 t, %33, 67108864; setp.ne.u32 b1, t, 0;\n"
+        "and.b32 t, %33, 134217728; setp.ne.u32 b2, t, 0;\n"
+        "@a0 add.rn.f32 %0, %0, %22;\n"
+        "@a1 add.rn.f32 %0, %0, %23;\n"
+        "@a2 add.rn.f32 %0, %0, %24;\n"
+        "ld.shared.v4.f32 {%21, %22, %23, %24}, [%34+80];\n"
+        "@a3 add.rn.f32 %0, %0, %25;\n"
+        "and.b32 t, %33, 268435456; setp.ne.u32 a0, t, 0;\n"
+        "and.b32 t, %33, 536870912; setp.ne.u32 a1, t, 0;\n"
+        "and.b32 t, %33, 1073741824; setp.ne.u32 a2, t, 0;\n"
+        "and.b32 t, %33, 2147483648; setp.ne.u32 a3, t, 0;\n"
+        "@b0 add.rn.f32 %0, %0, %26;\n"
+        "@b1 add.rn.f32 %0, %0, %27;\n"
+        "@b2 add.rn.f32 %0, %0, %28;\n"
+        "ld.shared.v4.f32 {%25, %26, %27, %28}, [%34+96];\n"
+        "@a0 add.rn.f32 %0, %0, %29;\n"
+        "@a1 add.rn.f32 %0, %0, %30;\n"
+        "@a2 add.rn.f32 %0, %0, %31;\n"
+        "@a3 add.rn.f32 %0, %0, %32;\n"
+        "ld.shared.v4.f32 {%29, %30, %31, %32}, [%34+112];\n"
+        "}\n"
+        : "+f"(acc), "+f"(R.a[0].x), "+f"(R.a[0].y), "+f"(R.a[0].z), "+f"(R.a[0].w), "+f"(R.a[1].x), "+f"(R.a[1].y), "+f"(R.a[1].z), "+f"(R.a[1].w), "+f"(R.a[2].x), "+f"(R.a[2].y), "+f"(R.a[2].z), "+f"(R.a[2].w), "+f"(R.a[3].x), "+f"(R.a[3].y), "+f"(R.a[3].z), "+f"(R.a[3].w), "+f"(R.a[4].x), "+f"(R.a[4].y), "+f"(R.a[4].z), "+f"(R.a[4].w), "+f"(R.a[5].x), "+f"(R.a[5].y), "+f"(R.a[5].z), "+f"(R.a[5].w), "+f"(R.a[6].x), "+f"(R.a[6].y), "+f"(R.a[6].z), "+f"(R.a[6].w), "+f"(R.a[7].x), "+f"(R.a[7].y), "+f"(R.a[7].z), "+f"(R.a[7].w)
+        : "r"(mask), "r"(next_addr)
+        : "memory");
+    return acc;
+}
+__device__ __forceinline__ float sim2_den_chain(float acc, Sim2NumBatch &R, uint32_t mask)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred a0, a1, a2, a3, b0, b1, b2;\n"
+        ".reg .b32 t;\n"
+        "and.b32 t, %33, 1; setp.ne.u32 a0, t, 0;\n"
+        "and.b32 t, %33, 2; setp.ne.u32 a1, t, 0;\n"
+        "and.b32 t, %33, 4; setp.ne.u32 a2, t, 0;\n"
+        "and.b32 t, %33, 8; setp.ne.u32 a3, t, 0;\n"
+        "and.b32 t, %33, 16; setp.ne.u32 b0, t, 0;\n"
+        "and.b32 t, %33, 32; setp.ne.u32 b1, t, 0;\n"
+        "and.b32 t, %33, 64; setp.ne.u32 b2, t, 0;\n"
+        "@a0 add.rn.f32 %0, %0, %1;\n"
+        "@a1 add.rn.f32 %0, %0, %2;\n"
+        "@a2 add.rn.f32 %0, %0, %3;\n"
+        "@a3 add.rn.f32 %0, %0, %4;\n"
+        "and.b32 t, %33, 128; setp.ne.u32 a0, t, 0;\n"
+        "and.b32 t, %33, 256; setp.ne.u32 a1, t, 0;\n"
+        "and.b32 t, %33, 512; setp.ne.u32 a2, t, 0;\n"
+        "and.b32 t, %33, 1024; setp.ne.u32 a3, t, 0;\n"
+        "@b0 add.rn.f32 %0, %0, %5;\n"
+        "@b1 add.rn.f32 %0, %0, %6;\n"
+        "@b2 add.rn.f32 %0, %0, %7;\n"
+        "and.b32 t, %33, 2048; setp.ne.u32 b0, t, 0;\n"
+        "and.b32 t, %33, 4096; setp.ne.u32 b1, t, 0;\n"
+        "and.b32 t, %33, 8192; setp.ne.u32 b2, t, 0;\n"
+        "@a0 add.rn.f32 %0, %0, %8;\n"
+        "@a1 add.rn.f32 %0, %0, %9;\n"
+        "@a2 add.rn.f32 %0, %0, %10;\n"
+        "@a3 add.rn.f32 %0, %0, %11;\n"
+        "and.b32 t, %33, 16384; setp.ne.u32 a0, t, 0;\n"
+        "and.b32 t, %33, 32768; setp.ne.u32 a1, t, 0;\n"
+        "and.b32 t, %33, 65536; setp.ne.u32 a2, t, 0;\n"
+        "and.b32 t, %33, 131072; setp.ne.u32 a3, t, 0;\n"
+        "@b0 add.rn.f32 %0, %0, %12;\n"
+        "@b1 add.rn.f32 %0, %0, %13;\n"
+        "@b2 add.rn.f32 %0, %0, %14;\n"
+        "and.b32 t, %33, 262144; setp.ne.u32 b0, t, 0;\n"
+        "and.b32 t, %33, 524288; setp.ne.u32 b1, t, 0;\n"
+        "and.b32 t, %33, 1048576; setp.ne.u32 b2, t, 0;\n"
+        "@a0 add.rn.f32 %0, %0, %15;\n"
+        "@a1 add.rn.f32 %0, %0, %16;\n"
+        "@a2 add.rn.f32 %0, %0, %17;\n"
+        "@a3 add.rn.f32 %0, %0, %18;\n"
+        "and.b32 t, %33, 2097152; setp.ne.u32 a0, t, 0;\n"
+        "and.b32 t, %33, 4194304; setp.ne.u32 a1, t, 0;\n"
+        "and.b32 t, %33, 8388608; setp.ne.u32 a2, t, 0;\n"
+        "and.b32 t, %33, 16777216; setp.ne.u32 a3, t, 0;\n"
+        "@b0 add.rn.f32 %0, %0, %19;\n"
+        "@b1 add.rn.f32 %0, %0, %20;\n"
+        "@b2 add.rn.f32 %0, %0, %21;\n"
+        "and.b32 t, %33, 33554432; setp.ne.u32 b0, t, 0;\n"
+        "and.b32 t, %33, 67108864; setp.ne.u32 b1, t, 0;\n"
+        "and.b32 t, %33, 134217728; setp.ne.u32 b2, t, 0;\n"
+        "@a0 add.rn.f32 %0, %0, %22;\n"
+        "@a1 add.rn.f32 %0, %0, %23;\n"
+        "@a2 add.rn.f32 %0, %0, %24;\n"
+        "@a3 add.rn.f32 %0, %0, %25;\n"
+        "and.b32 t, %33, 268435456; setp.ne.u32 a0, t, 0;\n"
+        "and.b32 t, %33, 536870912; setp.ne.u32 a1, t, 0;\n"
+        "and.b32 t, %33, 1073741824; setp.ne.u32 a2, t, 0;\n"
+        "and.b32 t, %33, 2147483648; setp.ne.u32 a3, t, 0;\n"
+        "@b0 add.rn.f32 %0, %0, %26;\n"
+        "@b1 add.rn.f32 %0, %0, %27;\n"
+        "@b2 add.rn.f32 %0, %0, %28;\n"
+        "@a0 add.rn.f32 %0, %0, %29;\n"
+        "@a1 add.rn.f32 %0, %0, %30;\n"
+        "@a2 add.rn.f32 %0, %0, %31;\n"
+        "@a3 add.rn.f32 %0, %0, %32;\n"
+        "}\n"
+        : "+f"(acc), "+f"(R.a[0].x), "+f"(R.a[0].y), "+f"(R.a[0].z), "+f"(R.a[0].w), "+f"(R.a[1].x), "+f"(R.a[1].y), "+f"(R.a[1].z), "+f"(R.a[1].w), "+f"(R.a[2].x), "+f"(R.a[2].y), "+f"(R.a[2].z), "+f"(R.a[2].w), "+f"(R.a[3].x), "+f"(R.a[3].y), "+f"(R.a[3].z), "+f"(R.a[3].w), "+f"(R.a[4].x), "+f"(R.a[4].y), "+f"(R.a[4].z), "+f"(R.a[4].w), "+f"(R.a[5].x), "+f"(R.a[5].y), "+f"(R.a[5].z), "+f"(R.a[5].w), "+f"(R.a[6].x), "+f"(R.a[6].y), "+f"(R.a[6].z), "+f"(R.a[6].w), "+f"(R.a[7].x), "+f"(R.a[7].y), "+f"(R.a[7].z), "+f"(R.a[7].w)
+        : "r"(mask), "r"(0u));
+    return acc;
+}
+
+template <bool DEN>
+__device__ __forceinline__ float sim2_consume(Sim2Walk W, unsigned long long btot, int lane)
+{
     float acc = 0.0f;
     if (btot == 0) return acc;
-    Sim2NumBatch A, B;
+    // lane id and the lane's byte addresses inside slot 0, made opaque once: the compiler would
+    // otherwise re-derive them (S2R / S2UR, ~25 cycles each) in every iteration
+    uint32_t lane0, ring0, mask0 = 0;
+    {
+        const uint32_t base = smem_u32(W.ring);
+        const uint32_t a = base + 4u * (uint32_t)(DEN ? SIM2_W_OFF : lane * SIM2_CS);
+        const uint32_t m = base + 4u * (uint32_t)(SIM2_M_OFF + lane);
+        asm volatile("mov.u32 %0, %1;" : "=r"(ring0) : "r"(a));
+        asm volatile("mov.u32 %0, %1;" : "=r"(mask0) : "r"(m));
+        asm volatile("mov.u32 %0, %1;" : "=r"(lane0) : "r"((uint32_t)(lane == 0)));
+    }
+    constexpr uint32_t SLOT_B = SIM2_SLOT_WORDS * 4u;
+    Sim2NumBatch R;
+    uint32_t mask = 0;
     mbar_wait(&W.full[0], 0);
-    sim2_num_load(A, W.ring, 0, lane, 0);
+#pragma unroll
+    for (int q = 0; q < 8; q++) R.a[q] = v_lds128(ring0 + 16u * q);
+    if (DEN) mask = v_lds32(mask0);
     if (btot > 1) mbar_wait(&W.full[1], 0);
-    // invariant at the top of a batch: its terms are in registers (X), the barrier of the
-    // next batch (if any) has been seen complete
-    auto iter = [&](const Sim2NumBatch &X, Sim2NumBatch &Y) {   // batches b+1 and b+2 exist
+    // invariant at the top of a batch: its terms are in R (and mask), the barrier of the next
+    // batch (if any) has been seen complete
+    auto iter = [&]() {   // batches b+1 and b+2 exist
         uint64_t *const f2 = &W.full[W.s2], *const e0 = &W.empty[W.s0];
         const uint32_t par2 = W.p2;
         const uint32_t ready2 = mbar_try_wait(f2, par2);
-        acc = sim2_num_add<0, 1>(acc, X);
-        sim2_num_load(Y, W.ring, W.s1, lane, __float_as_uint(acc) & zero);
-        W.rotate();  // here, not after the arrive: integer work in the shadow of the chain
-        acc = sim2_num_add<1, 32>(acc, X);
+        const uint32_t next_off = (uint32_t)W.s1 * SLOT_B;
+        uint32_t next_mask = 0;
+        if (DEN) next_mask = v_lds32(mask0 + next_off);
+        W.rotate();
+        if (DEN) acc = sim2_den_chain_refill(acc, R, mask, ring0 + next_off);
+        else acc = sim2_chain_refill<false>(acc, R, 0u, ring0 + next_off);
+        mask = next_mask;
         if (!ready2) mbar_wait(f2, par2);
         __syncwarp();
         if (lane0) mbar_arrive(e0);
     };
-    // pairs of batches with two more behind them: floor((btot - 2) / 2); a 32-bit counter in
-    // the loop (a 64-bit compare chain per iteration is not hidden by anything)
     unsigned long long pairs = btot > 3 ? (btot - 2) / 2 : 0;
     unsigned long long remaining = btot - 2 * pairs;
     while (pairs) {
@@ -300,22 +546,29 @@ __device__ __forceinline__ float sim2_consume(Sim2Walk W, unsigned long long bto
         pairs -= chunk;
 #pragma unroll 1
         for (uint32_t i = 0; i < chunk; i++) {
-            iter(A, B);
-            iter(B, A);
+            iter();
+            iter();
         }
     }
-    auto tail = [&](const Sim2NumBatch &X, Sim2NumBatch &Y) {
-        if (remaining > 1) sim2_num_load(Y, W.ring, W.s1, lane, 0);
-        acc = sim2_num_add<0, 32>(acc, X);
+    // the last (up to three) batches: refill while a next batch exists, no more probes
+    while (remaining) {
+        if (remaining > 1) {
+            const uint32_t next_off = (uint32_t)W.s1 * SLOT_B;
+            uint32_t next_mask = 0;
+            if (DEN) next_mask = v_lds32(mask0 + next_off);
+            if (DEN) acc = sim2_den_chain_refill(acc, R, mask, ring0 + next_off);
+            else acc = sim2_chain_refill<false>(acc, R, 0u, ring0 + next_off);
+            mask = next_mask;
+        } else {
+            if (DEN) acc = sim2_den_chain(acc, R, mask);
+            else acc = sim2_chain<false>(acc, R, 0u);
+        }
         if (remaining > 2) mbar_wait(&W.full[W.s2], W.p2);
         __syncwarp();
         if (lane0) mbar_arrive(&W.empty[W.s0]);
         W.rotate();
         remaining--;
-    };
-    tail(A, B);
-    if (remaining) tail(B, A);
-    if (remaining) tail(A, B);
+    }
     return acc;
 }
 
@@ -359,7 +612,8 @@ __global__ void __launch_bounds__(SIM2_THREADS, 2) k_similarity2(const Sim2Param
         W.full = full;
         W.empty = empty;
         W.slots = p.slots;
-        const float acc = sim2_consume(W, p.nbatches[group], lane, warp == cn ? 0 : SIM2_KB, p.zero);
+        const float acc = warp == cn ? sim2_consume<false>(W, p.nbatches[group], lane)
+                                     : sim2_consume<true>(W, p.nbatches[group], lane);
         const int col = group * 32 + lane;
         if (col < p.ncol && !p.col_skip[col]) (warp == cn ? p.num_out : p.den_out)[col] = acc;
     } else if (sp != cn) {
@@ -473,8 +727,23 @@ __global__ void __launch_bounds__(SIM2_THREADS, 2) k_similarity2(const Sim2Param
                 for (int u = 0; u < 16; u++) {
                     const int c = h * 16 + u;
                     dst[c * SIM2_CS] = __fmul_rn(w, t[u]);                              // numerator term
-                    dst[c * SIM2_CS + SIM2_KB] = (counted & (1u << c)) ? w : 0.0f;     // denominator term
                 }
+            }
+            // denominator: the weight of this inner row once, and -- instead of 32 x 32 float
+            // terms -- one word per column saying in which inner rows the pair counts: the
+            // rows' masks (lane = inner row, bit = column) transposed across the warp
+            {
+                uint32_t x = counted;
+                uint32_t low = 0x0000FFFFu;
+#pragma unroll
+                for (int jj = 16; jj >= 1; jj >>= 1) {
+                    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, jj);
+                    x = (lane & jj) ? ((x & ~low) | ((y & ~low) >> jj)) : ((x & low) | ((y & low) << jj));
+                    low ^= low << (jj >> 1);
+                }
+                float *slot0 = ring + (size_t)slot * SIM2_SLOT_WORDS;
+                slot0[SIM2_W_OFF + lane] = w;
+                reinterpret_cast<uint32_t *>(slot0)[SIM2_M_OFF + lane] = x;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[slot]);
@@ -525,7 +794,7 @@ cudaError_t launch_similarity(const uint8_t *codesT, int nseq, int npad, int nco
     p.group_begin = group_begin;
     p.num_sms = num_sms;
     const int ngroups = group_end - group_begin;
-    p.slots = SIM2_MAX_SLOTS;  // 85 KB: two CTAs fit an SM when there are more groups than SMs
+    p.slots = SIM2_MAX_SLOTS;  // 52 KB: two CTAs fit an SM when there are more groups than SMs
     const size_t smem = sim2_smem_bytes(p.slots);
     cudaError_t e = cudaFuncSetAttribute(k_similarity2, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
