@@ -539,8 +539,47 @@ __device__ __forceinline__ float sim2_consume(Sim2Walk W, unsigned long long bto
         __syncwarp();
         if (lane0) mbar_arrive(e0);
     };
-    unsigned long long pairs = btot > 3 ? (btot - 2) / 2 : 0;
-    unsigned long long remaining = btot - 2 * pairs;
+    // Whole turns of the ring (SIM2_MAX_SLOTS batches, starting at slot 0) with the slot numbers
+    // as compile-time constants: no slot arithmetic, no address computation and one loop branch
+    // per nine batches in the warp that can least afford extra instructions.  `turn` is the
+    // phase parity of the slots of the current turn.
+    unsigned long long remaining = btot;
+    if (W.slots == SIM2_MAX_SLOTS) {
+        uint32_t turn = 0;
+        unsigned long long turns = remaining > 2 ? (remaining - 2) / SIM2_MAX_SLOTS : 0;
+        remaining -= turns * SIM2_MAX_SLOTS;
+        while (turns) {
+            const uint32_t chunk = (uint32_t)min(turns, 1ull << 30);
+            turns -= chunk;
+#pragma unroll 1
+            for (uint32_t t = 0; t < chunk; t++) {
+#pragma unroll
+                for (int i = 0; i < SIM2_MAX_SLOTS; i++) {
+                    constexpr int S = SIM2_MAX_SLOTS;
+                    const int i1 = (i + 1) % S, i2 = (i + 2) % S;
+                    const uint32_t par2 = i + 2 >= S ? turn ^ 1u : turn;
+                    const uint32_t ready2 = mbar_try_wait(&W.full[i2], par2);
+                    const uint32_t next_off = (uint32_t)i1 * SLOT_B;
+                    uint32_t next_mask = 0;
+                    if (DEN) next_mask = v_lds32(mask0 + next_off);
+                    if (DEN) acc = sim2_den_chain_refill(acc, R, mask, ring0 + next_off);
+                    else acc = sim2_chain_refill<false>(acc, R, 0u, ring0 + next_off);
+                    mask = next_mask;
+                    if (!ready2) mbar_wait(&W.full[i2], par2);
+                    __syncwarp();
+                    if (lane0) mbar_arrive(&W.empty[i]);
+                }
+                turn ^= 1u;
+            }
+        }
+        // back to the general walk at slot 0 of the next turn
+        W.s0 = 0;
+        W.s1 = 1;
+        W.s2 = 2;
+        W.p1 = W.p2 = turn;
+    }
+    unsigned long long pairs = remaining > 3 ? (remaining - 2) / 2 : 0;
+    remaining -= 2 * pairs;
     while (pairs) {
         const uint32_t chunk = (uint32_t)min(pairs, 1ull << 30);
         pairs -= chunk;
