@@ -96,7 +96,7 @@ int tcu_msa_create_strided(const uint8_t *data, int nseq, int ncol, size_t strid
 void tcu_msa_destroy(tcu_msa *msa);
 
 /*
- * The library keeps the large device buffers of destroyed handles (at most 16 per
+ * The library keeps the large device buffers of destroyed handles (at most 24 per
  * device: identity matrix, threshold bit matrix, packed planes, raw rows) and its pinned
  * staging buffers for reuse by later handles, so that a create / compute / destroy
  * cycle does not go through cudaMalloc / cudaFree; this returns them to the driver.

@@ -234,6 +234,8 @@ def cythonize_and_link(objs):
     # the pure-Python side of the package and its test data (symlinks dereferenced)
     for f in ["__init__.py", "py.typed", "_trimal.pyi"]:
         shutil.copyfile(os.path.join(REF, "src/pytrimal", f), os.path.join(pkg, f))
+    # the type stub learns the new platform literal
+    run(["patch", "-s", "-p3", "-d", pkg, "-i", os.path.join(HERE, "patches", "_trimal.pyi.patch")])
     tests = os.path.join(pkg, "tests")
     if os.path.isdir(tests):
         shutil.rmtree(tests)

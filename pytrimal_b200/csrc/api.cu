@@ -185,18 +185,18 @@ struct DevSlot {
     void *ptr = nullptr;
     size_t cap = 0;
 };
-constexpr int POOL_SLOTS = 16;
+constexpr int POOL_SLOTS = 24;
 std::mutex g_dev_cache_mutex;
 DevSlot g_dev_cache[64][POOL_SLOTS];
 
 // best fit: the smallest cached buffer that holds `need` without wasting more than
-// half of itself (plus 64 MB of slack for the small ones)
+// half of itself (plus 1 MB of slack for the small ones)
 void *dev_cache_take(int device, size_t need, size_t *cap)
 {
     std::lock_guard<std::mutex> lk(g_dev_cache_mutex);
     DevSlot *best = nullptr;
     for (DevSlot &s : g_dev_cache[device & 63])
-        if (s.ptr && s.cap >= need && s.cap <= 2 * need + (64u << 20) && (!best || s.cap < best->cap))
+        if (s.ptr && s.cap >= need && s.cap <= 2 * need + (1u << 20) && (!best || s.cap < best->cap))
             best = &s;
     if (!best) return nullptr;
     void *p = best->ptr;
@@ -230,6 +230,54 @@ void dev_cache_give(int device, void *ptr, size_t cap)
 }
 }  // namespace
 
+// Streams and events of destroyed handles, per device: creating and destroying two streams and
+// eight events costs 0.2-0.3 ms per handle life cycle, which is a tenth of an 8-GPU step.
+namespace {
+struct StreamSet {
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t cev[2] = {nullptr, nullptr};
+};
+std::mutex g_streams_mutex;
+std::vector<StreamSet> g_streams[64];
+
+bool streams_take(int device, StreamSet &out)
+{
+    std::lock_guard<std::mutex> lk(g_streams_mutex);
+    auto &v = g_streams[device & 63];
+    if (v.empty()) return false;
+    out = v.back();
+    v.pop_back();
+    return true;
+}
+void streams_destroy(StreamSet &s)
+{
+    for (auto &e : s.ev)
+        if (e) cudaEventDestroy(e);
+    for (auto &e : s.cev)
+        if (e) cudaEventDestroy(e);
+    if (s.stream) cudaStreamDestroy(s.stream);
+    if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
+    s = StreamSet{};
+}
+void streams_give(int device, StreamSet &s)  // the streams must be idle
+{
+    bool complete = s.stream && s.copy_stream;
+    for (auto &e : s.ev) complete = complete && e;
+    for (auto &e : s.cev) complete = complete && e;
+    if (complete) {
+        std::lock_guard<std::mutex> lk(g_streams_mutex);
+        auto &v = g_streams[device & 63];
+        if (v.size() < 16) {
+            v.push_back(s);
+            s = StreamSet{};
+            return;
+        }
+    }
+    streams_destroy(s);
+}
+}  // namespace
+
 extern "C" void tcu_release_cached_memory(void)
 {
     int cur = 0;
@@ -247,6 +295,15 @@ extern "C" void tcu_release_cached_memory(void)
                 cudaFree(p);
             }
         }
+    }
+    for (int d = 0; d < 64; d++) {
+        std::vector<StreamSet> v;
+        {
+            std::lock_guard<std::mutex> lk(g_streams_mutex);
+            v.swap(g_streams[d]);
+        }
+        if (!v.empty()) cudaSetDevice(d);
+        for (StreamSet &s : v) streams_destroy(s);
     }
     cudaSetDevice(cur);
     {
@@ -281,9 +338,11 @@ struct tcu_msa {
     size_t planes_cap = 0;
     uint8_t *d_gbytes = nullptr;
     size_t gbytes_cap = 0;
-    int *d_kept_rows = nullptr;
-    uint8_t *d_col_drop = nullptr;
-    uint8_t *d_lut = nullptr;
+    int *d_kept_rows = nullptr;    // the three small tables of the operand live in one pooled
+    uint8_t *d_col_drop = nullptr; // buffer (d_small): cudaMalloc / cudaFree per handle would
+    uint8_t *d_lut = nullptr;      // synchronise the whole device
+    void *d_small = nullptr;
+    size_t small_cap = 0;
     uint8_t prepared_indet = 0;
 
     // identities kept on the device
@@ -312,10 +371,20 @@ struct tcu_msa {
 };
 
 // grow-only device buffer, pooled (see the device buffer cache above)
-static int ensure_dev(int device, void **p, size_t *cap, size_t need)
+static int ensure_dev(int device, void **p, size_t *cap, size_t need, tcu_msa *owner = nullptr)
 {
     if (*cap >= need && *p) return TCU_OK;
-    if (*p) cudaDeviceSynchronize();  // growth: queued work may still read the old buffer
+    if (*p) {
+        // growth: queued work may still read the old buffer.  Only this handle's own streams
+        // can hold such work (a buffer belongs to one handle), so only they are waited for --
+        // not the whole device, which would stall every other thread's handle.
+        if (owner) {
+            if (owner->stream) cudaStreamSynchronize(owner->stream);
+            if (owner->copy_stream) cudaStreamSynchronize(owner->copy_stream);
+        } else {
+            cudaDeviceSynchronize();
+        }
+    }
     dev_cache_give(device, *p, *cap);
     *p = nullptr;
     *cap = 0;
@@ -333,7 +402,7 @@ static int ensure_dev(int device, void **p, size_t *cap, size_t need)
 
 static int ensure_ident(tcu_msa *m, size_t need)
 {
-    return ensure_dev(m->device, (void **)&m->d_ident, &m->ident_cap, need);
+    return ensure_dev(m->device, (void **)&m->d_ident, &m->ident_cap, need, m);
 }
 
 static float ev_ms(cudaEvent_t a, cudaEvent_t b)
@@ -357,6 +426,9 @@ struct tcu_comm {
     // process (per rank: handle bytes -> mapped base), so that bands are pulled device to
     // device by the copy engines over NVLink instead of going through NCCL's transfer kernels
     std::vector<std::map<std::string, void *>> opened;
+    // a communicator is used by one call at a time (NCCL requires the ranks to issue the same
+    // operations in the same order; two threads of one rank interleaving theirs would break that)
+    std::mutex mutex;
     uint8_t *d_sync = nullptr;   // handle exchange area + the word of the stream-ordered barriers
     uint8_t *h_sync = nullptr;   // pinned mirror
     bool ipc_usable = true;      // cleared for good on the first failure (agreed by all ranks)
@@ -658,10 +730,19 @@ static int msa_alloc(int nseq, int ncol, int device, tcu_msa **out)
     m->ncol = ncol;
     m->pitch = ((size_t)ncol + 127) / 128 * 128;
     if (m->pitch == 0) m->pitch = 128;
-    cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventCreate(&m->ev[i]);
-    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreate(&m->cev[i]);
+    cudaError_t e = cudaSuccess;
+    StreamSet pooled;
+    if (streams_take(device, pooled)) {
+        m->stream = pooled.stream;
+        m->copy_stream = pooled.copy_stream;
+        for (int i = 0; i < 6; i++) m->ev[i] = pooled.ev[i];
+        for (int i = 0; i < 2; i++) m->cev[i] = pooled.cev[i];
+    } else {
+        e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking);
+        for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventCreate(&m->ev[i]);
+        for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreate(&m->cev[i]);
+    }
     if (e != cudaSuccess) {
         tcu_msa_destroy(m);
         return cuda_fail(e, "tcu_msa_create");
@@ -706,7 +787,7 @@ static int upload_strided_pinned(tcu_msa *m, const uint8_t *data, size_t stride,
     m->timings = tcu_timings{};
     if (r1 <= r0) return TCU_OK;
     const size_t bytes = (size_t)(r1 - r0 - 1) * stride + (size_t)m->ncol;
-    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, bytes);
+    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, bytes, m);
     if (rc != TCU_OK) return rc;
     CK(cudaEventRecord(m->ev[0], m->stream));
     CK(cudaMemcpyAsync(m->d_scratch, data + (size_t)r0 * stride, bytes, cudaMemcpyHostToDevice,
@@ -1067,6 +1148,7 @@ extern "C" int tcu_msa_create_all(tcu_comm *comm, const uint8_t *data, int nseq,
 {
     NvtxRange nvtx("tcu_msa_create_all");
     if (!comm || !out) return fail(TCU_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> comm_lock(comm->mutex);
     if (nseq > 0 && ncol > 0 && !data) return fail(TCU_ERR_INVALID, "data is NULL");
     if (stride < (size_t)ncol) return fail(TCU_ERR_INVALID, "stride smaller than ncol");
     *out = nullptr;
@@ -1119,17 +1201,17 @@ extern "C" void tcu_msa_destroy(tcu_msa *m)
     dev_cache_give(m->device, m->d_ident, m->ident_cap);
     dev_cache_give(m->device, m->d_bits, m->bits_cap);
     dev_cache_give(m->device, m->d_scratch, m->scratch_cap);
-    cudaFree(m->d_kept_rows);
-    cudaFree(m->d_col_drop);
-    cudaFree(m->d_lut);
-    for (auto &e : m->ev)
-        if (e) cudaEventDestroy(e);
-    for (auto &e : m->cev)
-        if (e) cudaEventDestroy(e);
+    dev_cache_give(m->device, m->d_small, m->small_cap);
     for (auto &e : m->band_done)
         if (e) cudaEventDestroy(e);
-    if (m->stream) cudaStreamDestroy(m->stream);
-    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+    {
+        StreamSet s;  // both streams were synchronised above
+        s.stream = m->stream;
+        s.copy_stream = m->copy_stream;
+        for (int i = 0; i < 6; i++) s.ev[i] = m->ev[i];
+        for (int i = 0; i < 2; i++) s.cev[i] = m->cev[i];
+        streams_give(m->device, s);
+    }
     cudaGetLastError();
     delete m;
 }
@@ -1183,7 +1265,7 @@ static int gaps_impl(tcu_msa *m, tcu_comm *comm, int srank, int sworld, const in
     const int n = m->nseq, L = m->ncol;
     if (L == 0) return TCU_OK;
     const size_t cnt_bytes = ((size_t)L * sizeof(int) + 255) / 256 * 256;
-    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, cnt_bytes + (size_t)n + 256);
+    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, cnt_bytes + (size_t)n + 256, m);
     if (rc != TCU_OK) return rc;
     int *d_cnt = (int *)m->d_scratch;
     uint8_t *d_drop = nullptr;
@@ -1258,6 +1340,7 @@ extern "C" int tcu_gaps_all(tcu_msa *m, tcu_comm *comm, const int *save_seq, int
                             int *num_cols_with_gaps, int *max_gaps)
 {
     if (!comm) return fail(TCU_ERR_INVALID, "comm is NULL");
+    std::lock_guard<std::mutex> comm_lock(comm->mutex);
     return gaps_impl(m, comm, 0, 1, save_seq, gaps_in_column, num_cols_with_gaps, max_gaps);
 }
 
@@ -1298,7 +1381,7 @@ extern "C" size_t tcu_identity_row_offset(int kept_rows, int i)
 static int ensure_present(tcu_msa *m)
 {
     if (m->have_present) return TCU_OK;
-    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, 256 * sizeof(unsigned int));
+    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, 256 * sizeof(unsigned int), m);
     if (rc != TCU_OK) return rc;
     unsigned int *d_present = (unsigned int *)m->d_scratch;
     CK(cudaMemsetAsync(d_present, 0, 256 * sizeof(unsigned int), m->stream));
@@ -1362,9 +1445,14 @@ extern "C" int tcu_identity_prepare(tcu_msa *m, const int *save_seq, const int *
     m->nchunks = (L + KC2 * 32 - 1) / (KC2 * 32);
     m->prepared_indet = indet;
 
-    if (!m->d_lut) CK(cudaMalloc((void **)&m->d_lut, 256));
-    if (!m->d_kept_rows) CK(cudaMalloc((void **)&m->d_kept_rows, std::max<size_t>(1, (size_t)n) * sizeof(int)));
-    if (!m->d_col_drop) CK(cudaMalloc((void **)&m->d_col_drop, m->pitch));
+    if (!m->d_small) {
+        const size_t rows_b = (std::max<size_t>(1, (size_t)n) * sizeof(int) + 255) / 256 * 256;
+        int src = ensure_dev(m->device, &m->d_small, &m->small_cap, rows_b + m->pitch + 256, m);
+        if (src != TCU_OK) return src;
+        m->d_kept_rows = (int *)m->d_small;
+        m->d_col_drop = (uint8_t *)m->d_small + rows_b;
+        m->d_lut = m->d_col_drop + m->pitch;
+    }
     CK(cudaMemcpyAsync(m->d_lut, lut, 256, cudaMemcpyHostToDevice, m->stream));
     if (m->nk)
         CK(cudaMemcpyAsync(m->d_kept_rows, kept.data(), (size_t)m->nk * sizeof(int),
@@ -1379,10 +1467,10 @@ extern "C" int tcu_identity_prepare(tcu_msa *m, const int *save_seq, const int *
         if (kept_rows_out) *kept_rows_out = m->nk;
         return TCU_OK;
     }
-    int rc = ensure_dev(m->device, (void **)&m->d_planes, &m->planes_cap, (size_t)m->nb2 * m->nchunks * tile2_bytes(np));
+    int rc = ensure_dev(m->device, (void **)&m->d_planes, &m->planes_cap, (size_t)m->nb2 * m->nchunks * tile2_bytes(np), m);
     if (rc != TCU_OK) return rc;
     rc = ensure_dev(m->device, (void **)&m->d_gbytes, &m->gbytes_cap,
-                (size_t)m->nb2 * m->nchunks * G_STAGES_PER_CHUNK * G_BLOCK_BYTES);
+                (size_t)m->nb2 * m->nchunks * G_STAGES_PER_CHUNK * G_BLOCK_BYTES, m);
     if (rc != TCU_OK) return rc;
     CK(cudaEventRecord(m->ev[1], m->stream));
     CK(launch_pack_planes(m->d_raw, m->pitch, L, m->d_kept_rows, m->nk, m->d_col_drop, m->d_lut, np,
@@ -1547,7 +1635,7 @@ static int identity_host(tcu_msa *m, const int *save_seq, const int *save_res, u
     int *d_hit = nullptr, *d_dst = nullptr;
     if (hit_out || dst_out) {
         // the kernel writes both or neither
-        rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, 2 * npairs * sizeof(int));
+        rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, 2 * npairs * sizeof(int), m);
         if (rc != TCU_OK) return rc;
         d_hit = (int *)m->d_scratch;
         d_dst = d_hit + npairs;
@@ -1673,6 +1761,7 @@ extern "C" int tcu_identity_all(tcu_msa *m, tcu_comm *comm, const int *save_seq,
                                 const int *save_res, uint8_t indet, float *identities)
 {
     if (!m || !comm) return fail(TCU_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> comm_lock(comm->mutex);
     int rc = comm_check(m, comm);
     if (rc != TCU_OK) return rc;
     m->timings = tcu_timings{};
@@ -1764,7 +1853,7 @@ extern "C" int tcu_identity_row_stats(tcu_msa *m, int upper_only, float *row_max
     const int n = m->nseq;
     if (n == 0) return TCU_OK;
     const size_t vec = ((size_t)n * sizeof(float) + 255) / 256 * 256;
-    rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, 3 * vec);
+    rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, 3 * vec, m);
     if (rc != TCU_OK) return rc;
     float *d_max = (float *)m->d_scratch;
     float *d_min = (float *)((uint8_t *)m->d_scratch + vec);
@@ -1843,10 +1932,10 @@ static int clusters_impl(tcu_msa *m, const float *id0, const int *order, int cou
     const size_t ord_b = up((size_t)count * 4), alive_b = up((size_t)mis_block());
     const size_t adj_b = up((size_t)mis_block() * 32 * 4);
     if (id0) {
-        rc = ensure_dev(m->device, (void **)&m->d_bits, &m->bits_cap, bits_bytes(n));
+        rc = ensure_dev(m->device, (void **)&m->d_bits, &m->bits_cap, bits_bytes(n), m);
         if (rc != TCU_OK) return rc;
     }
-    rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, rep_b + 2 * ord_b + alive_b + adj_b);
+    rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, rep_b + 2 * ord_b + alive_b + adj_b, m);
     if (rc != TCU_OK) return rc;
     uint8_t *p = (uint8_t *)m->d_scratch;
     uint32_t *d_rep = (uint32_t *)p;  // 4 * nslab words, then the cluster counter
@@ -1900,7 +1989,7 @@ extern "C" int tcu_byte_histogram(tcu_msa *m, unsigned long long *hist256)
     m->timings = tcu_timings{};
     memset(hist256, 0, 256 * sizeof(unsigned long long));
     if (m->nseq == 0 || m->ncol == 0) return TCU_OK;
-    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, 256 * sizeof(unsigned long long));
+    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, 256 * sizeof(unsigned long long), m);
     if (rc != TCU_OK) return rc;
     unsigned long long *d_hist = (unsigned long long *)m->d_scratch;
     CK(cudaMemsetAsync(d_hist, 0, 256 * sizeof(unsigned long long), m->stream));
@@ -1923,7 +2012,7 @@ extern "C" int tcu_sequence_lengths(tcu_msa *m, int *lengths)
     CK(cudaSetDevice(m->device));
     m->timings = tcu_timings{};
     if (m->nseq == 0) return TCU_OK;
-    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, (size_t)m->nseq * sizeof(int));
+    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, (size_t)m->nseq * sizeof(int), m);
     if (rc != TCU_OK) return rc;
     CK(cudaEventRecord(m->ev[1], m->stream));
     CK(launch_row_lengths(m->d_raw, m->nseq, m->ncol, m->pitch, (int *)m->d_scratch, m->stream));
@@ -1951,7 +2040,7 @@ extern "C" int tcu_row_residues(tcu_msa *m, const int *save_res, int *residues)
     const int n = m->nseq, L = m->ncol;
     if (n == 0) return TCU_OK;
     const size_t out_b = ((size_t)n * sizeof(int) + 255) / 256 * 256;
-    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, out_b + m->pitch);
+    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, out_b + m->pitch, m);
     if (rc != TCU_OK) return rc;
     std::vector<uint8_t> keep(m->pitch, 0);
     for (int k = 0; k < L; k++) keep[k] = save_res[k] != -1;
@@ -1983,7 +2072,7 @@ extern "C" int tcu_row_hashes(tcu_msa *m, unsigned long long *hashes)
     m->timings = tcu_timings{};
     const int n = m->nseq;
     if (n == 0) return TCU_OK;
-    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, (size_t)n * 16);
+    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, (size_t)n * 16, m);
     if (rc != TCU_OK) return rc;
     CK(cudaEventRecord(m->ev[1], m->stream));
     CK(launch_row_hashes(m->d_raw, n, m->pitch, (unsigned long long *)m->d_scratch, m->stream));
@@ -2120,7 +2209,7 @@ static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res,
         m->ident_full = false;
         int r = tcu_identity_prepare(m, nullptr, save_res, indet, nullptr);
         if (r != TCU_OK) return r;
-        r = ensure_dev(m->device, (void **)&m->d_bits, &m->bits_cap, bits_bytes(n));
+        r = ensure_dev(m->device, (void **)&m->d_bits, &m->bits_cap, bits_bytes(n), m);
         if (r != TCU_OK) return r;
         if (m->nchunks == 0) {
             // no columns: every identity is 0 (template.h:427-434)
@@ -2171,7 +2260,7 @@ static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res,
             bb[k + 1] = b1;
             const size_t need = k == 0 ? bits_bytes(n)
                                        : std::max<size_t>((size_t)(b1 - b0) * slab_w, 4) * sizeof(uint32_t);
-            e = ensure_dev(d->device, (void **)&d->d_bits, &d->bits_cap, need);
+            e = ensure_dev(d->device, (void **)&d->d_bits, &d->bits_cap, need, d);
             if (e != TCU_OK) return e;
             // K1 indexes slabs absolutely: a device that holds only its band passes the address
             // slab 0 would have
@@ -2252,6 +2341,7 @@ extern "C" int tcu_representatives_all(tcu_msa *m, tcu_comm *comm, const int *sa
                                        int *n_clusters)
 {
     if (!comm) return fail(TCU_ERR_INVALID, "comm is NULL");
+    std::lock_guard<std::mutex> comm_lock(comm->mutex);
     return representatives_impl(m, comm, save_res, indet, threshold, clusters, n_clusters);
 }
 
@@ -2288,7 +2378,7 @@ static int spurious_impl(tcu_msa *m, tcu_comm *comm, const SpuriousShare &sh, ui
     const size_t flag_bytes = (3 * (m->pitch >> 5) * sizeof(uint32_t) + 255) / 256 * 256;
     const size_t plane_bytes = (size_t)n * (m->pitch >> 3);  // one bit per cell, pitch % 128 == 0
     int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap,
-                        2 * cnt_bytes + out_bytes + flag_bytes + 2 * plane_bytes);
+                        2 * cnt_bytes + out_bytes + flag_bytes + 2 * plane_bytes, m);
     if (rc != TCU_OK) return rc;
     int *d_cg = (int *)m->d_scratch;
     int *d_cx = (int *)((uint8_t *)m->d_scratch + cnt_bytes);
@@ -2398,6 +2488,7 @@ extern "C" int tcu_spurious_all(tcu_msa *m, tcu_comm *comm, uint8_t indet, uint3
                                 float *spurious)
 {
     if (!comm) return fail(TCU_ERR_INVALID, "comm is NULL");
+    std::lock_guard<std::mutex> comm_lock(comm->mutex);
     return spurious_impl(m, comm, SpuriousShare{}, indet, ovrlap, spurious);
 }
 
@@ -2455,7 +2546,7 @@ static int similarity_impl(tcu_msa *m, tcu_comm *comm, uint8_t indet, const floa
     const size_t ngm_bytes = (size_t)ngroups * npad * sizeof(uint32_t);
     const size_t need = codes_bytes + 2 * vec_bytes + dist_bytes + m->pitch + 256 + 64 + skip_bytes +
                         nb_bytes + ngm_bytes;
-    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, need);
+    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, need, m);
     if (rc != TCU_OK) return rc;
     uint8_t *base = (uint8_t *)m->d_scratch;
     float *d_num = (float *)base;
@@ -2564,6 +2655,7 @@ extern "C" int tcu_similarity_all(tcu_msa *m, tcu_comm *comm, uint8_t indet, con
                                   int *err_byte)
 {
     if (!comm) return fail(TCU_ERR_INVALID, "comm is NULL");
+    std::lock_guard<std::mutex> comm_lock(comm->mutex);
     return similarity_impl(m, comm, indet, dist, npos, vhash, gaps, gap_threshold, nullptr, num,
                            den, mdk, err_col, err_row, err_byte);
 }
