@@ -280,8 +280,12 @@ __global__ void __launch_bounds__(256) k_mis_scan(const uint32_t *__restrict__ b
     // (2 048 warps per block of 1 024 sequences)
     __shared__ int s_ord[MIS_NB];
     __shared__ uint32_t s_hit[2][4];
+    asm volatile("griddepcontrol.launch_dependents;");  // the resolve kernel may be set up now
     for (int k = threadIdx.x; k < cnt; k += 256) s_ord[k] = order[base + k];
     __syncthreads();
+    // programmatic dependent launch: everything above ran under the tail of the previous
+    // block's resolve kernel; `rep` is its output
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int lane = threadIdx.x & 31, part = (threadIdx.x >> 5) & 3, sub = threadIdx.x >> 7;
     const int t = blockIdx.x * 2 + sub;
     const bool live = t < cnt;
@@ -293,7 +297,10 @@ __global__ void __launch_bounds__(256) k_mis_scan(const uint32_t *__restrict__ b
     if (live) {
         for (int S = lane + 32 * part; S < nslab; S += 128) {
             const uint4 a = slabs[(size_t)S * n];
-            const uint4 r = rep4[S];
+            // L2 only: under programmatic dependent launch this grid was already resident
+            // while the previous resolve kernel wrote `rep`; an L1 line left by an earlier
+            // block's scan on this SM would be stale
+            const uint4 r = __ldcg(rep4 + S);
             acc |= (a.x & r.x) | (a.y & r.y) | (a.z & r.z) | (a.w & r.w);
         }
     }
@@ -341,10 +348,13 @@ __global__ void __launch_bounds__(1024) k_mis_resolve(const uint32_t *__restrict
 {
     __shared__ uint32_t s_in[32], s_und[32], s_pre[32];
     const int t = threadIdx.x, lane = t & 31, g = t >> 5;
+    asm volatile("griddepcontrol.launch_dependents;");  // the next block's scan may be set up now
+    const int my_seq = t < cnt ? order[base + t] : 0;  // does not depend on the scan kernel
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // adj / alive8 are its output
     uint32_t a[32];
 #pragma unroll
-    for (int w = 0; w < 32; w++) a[w] = (w <= g && t < cnt) ? adj[w * MIS_NB + t] : 0u;
-    bool undec = t < cnt && alive8[t] != 0;
+    for (int w = 0; w < 32; w++) a[w] = (w <= g && t < cnt) ? __ldcg(adj + w * MIS_NB + t) : 0u;  // L2 only, as above
+    bool undec = t < cnt && __ldcg(alive8 + t) != 0;
     {
         const uint32_t b = __ballot_sync(0xffffffffu, undec);
         if (lane == 0) {
@@ -382,10 +392,10 @@ __global__ void __launch_bounds__(1024) k_mis_resolve(const uint32_t *__restrict
         s_pre[lane] = x - c;
     }
     __syncthreads();
-    const int c0 = *count;
+    const int c0 = __ldcg(count);
     const uint32_t mine = s_in[g];
     if ((mine >> lane) & 1u) {
-        const int v = order[base + t];
+        const int v = my_seq;
         if (clusters) clusters[c0 + s_pre[g] + __popc(mine & ((1u << lane) - 1u))] = v;
         atomicOr(&rep[v >> 5], 1u << (v & 31));
     }
@@ -402,10 +412,32 @@ cudaError_t launch_greedy_clusters(const uint32_t *bits, int n, const int *order
                                    uint32_t *rep, uint8_t *alive8, uint32_t *adj, int *clusters,
                                    int *count, cudaStream_t stream)
 {
+    // the 2 x ceil(total / 1024) launches depend on each other one after the other: each is
+    // launched with programmatic stream serialization, so that its launch latency and its
+    // prologue overlap the tail of its predecessor (griddepcontrol.wait inside the kernels)
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
     for (int base = 0; base < total; base += MIS_NB) {
         const int cnt = min(MIS_NB, total - base);
-        k_mis_scan<<<(cnt + 1) / 2, 256, 0, stream>>>(bits, n, order, base, cnt, rep, alive8, adj);
-        k_mis_resolve<<<1, 1024, 0, stream>>>(adj, alive8, order, base, cnt, rep, clusters, count);
+        cudaLaunchConfig_t cfg = {};
+        cfg.stream = stream;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        // the very first launch follows copies / memsets / other kernels of the caller: it keeps
+        // the ordinary stream dependency
+        cfg.numAttrs = base == 0 ? 0 : 1;
+        cfg.gridDim = dim3((cnt + 1) / 2);
+        cfg.blockDim = dim3(256);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, k_mis_scan, bits, n, order, base, cnt,
+                                           (const uint32_t *)rep, alive8, adj);
+        if (e != cudaSuccess) return e;
+        cfg.numAttrs = 1;
+        cfg.gridDim = dim3(1);
+        cfg.blockDim = dim3(1024);
+        e = cudaLaunchKernelEx(&cfg, k_mis_resolve, (const uint32_t *)adj, (const uint8_t *)alive8,
+                               order, base, cnt, rep, clusters, count);
+        if (e != cudaSuccess) return e;
     }
     return cudaGetLastError();
 }
