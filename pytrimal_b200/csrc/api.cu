@@ -361,6 +361,7 @@ struct tcu_msa {
     // several GPUs in one process (tcu_set_devices / TRIMAL_CUDA_DEVICES): the handle the
     // caller holds lives on the first device; one replica per further device hangs off it
     std::vector<tcu_msa *> peers;
+    bool peer_direct = false;  // kernels of the peers' devices may store into this device's memory
 
     cudaStream_t copy_stream = nullptr;       // D2H of finished sub-bands, overlapping the kernel
     std::vector<cudaEvent_t> band_done;       // one per sub-band (no timing)
@@ -584,16 +585,14 @@ static int comm_allgatherv(tcu_comm *c, void *buf, const size_t *off, const size
 }
 
 // ---------------------------------------------------------------------------
-// All-gather over peer memory.  `buf` is the base of a cudaMalloc allocation of the same
-// size on every rank; rank r owns [off[r], off[r] + cnt[r]).  Step 1 (peer_prepare, before
-// the producing kernel is launched): the ranks exchange CUDA IPC handles of `buf` and map
-// the ones they have not seen yet (allocations come from the library's pool, so after the
-// first call nothing is mapped any more); all ranks agree on whether that worked.  Step 2
-// (peer_allgatherv, after the producing kernel, stream-ordered): a one-word all-reduce tells
-// every rank that all bands are written, each rank then PULLS the other bands with plain
-// device-to-device copies (copy engines, NVLink / NVSwitch: no SM is taken from the compute
-// kernels and the transfer runs at link speed), and a second one-word all-reduce keeps any
-// rank from running ahead and rewriting its band while a peer still reads it.
+// Peer memory between ranks.  `buf` is the base of a cudaMalloc allocation of the same size
+// on every rank.  peer_prepare (before the producing kernel is launched): the ranks exchange
+// CUDA IPC handles of `buf` and map the ones they have not seen yet (allocations come from
+// the library's pool, so after the first call nothing is mapped any more); all ranks agree on
+// whether that worked.  The producing kernel then stores its results into every rank's copy
+// (NVLink / NVSwitch), and a one-word all-reduce behind it tells everybody that all parts
+// have landed.  (Round 2 first PULLED the finished bands with 2-D device-to-device copies
+// between two such barriers: 0.9 ms at 8 GPUs that the stores inside K1 do not cost.)
 // ---------------------------------------------------------------------------
 static int comm_allreduce_i32(tcu_comm *c, int *buf, size_t count, cudaStream_t stream);
 static int comm_allgatherv(tcu_comm *c, void *buf, const size_t *off, const size_t *cnt,
@@ -661,43 +660,6 @@ static bool peer_prepare(tcu_comm *c, void *buf, std::vector<void *> &peer_base,
         return false;
     }
     return true;
-}
-
-// A rank's share as a 2-D block: `height` lines of `width` bytes, `pitch` bytes apart, the
-// first at byte offset `off` of the common buffer (a 1-D range is one line).
-struct PeerBlock {
-    size_t off = 0, width = 0, height = 0, pitch = 0;
-};
-
-static int peer_allgatherv(tcu_comm *c, void *buf, const std::vector<void *> &peer_base,
-                           const PeerBlock *blk, cudaStream_t stream)
-{
-    int *d_word = (int *)(c->d_sync + 64 * 64 + 64);
-    static const bool trace = getenv("TCU_TRACE") != nullptr;
-    cudaEvent_t te[4] = {nullptr, nullptr, nullptr, nullptr};
-    if (trace)
-        for (auto &e : te) cudaEventCreate(&e);
-    if (trace) cudaEventRecord(te[0], stream);
-    int rc = comm_allreduce_i32(c, d_word, 1, stream);  // every band is written
-    if (rc != TCU_OK) return rc;
-    if (trace) cudaEventRecord(te[1], stream);
-    for (int d = 1; d < c->world; d++) {
-        const int r = (c->rank + d) % c->world;  // staggered: not everybody reads rank 0 first
-        const PeerBlock &b = blk[r];
-        if (b.width == 0 || b.height == 0) continue;
-        CK(cudaMemcpy2DAsync((uint8_t *)buf + b.off, b.pitch, (const uint8_t *)peer_base[r] + b.off,
-                             b.pitch, b.width, b.height, cudaMemcpyDeviceToDevice, stream));
-    }
-    if (trace) cudaEventRecord(te[2], stream);
-    rc = comm_allreduce_i32(c, d_word, 1, stream);  // every band is read
-    if (trace) {
-        cudaEventRecord(te[3], stream);
-        cudaStreamSynchronize(stream);
-        fprintf(stderr, "[tcu] rank %d peer all-gather: barrier %.3f ms, copies %.3f ms, barrier %.3f ms\n",
-                c->rank, ev_ms(te[0], te[1]), ev_ms(te[1], te[2]), ev_ms(te[2], te[3]));
-        for (auto &e : te) cudaEventDestroy(e);
-    }
-    return rc;
 }
 
 static int comm_allreduce_i32(tcu_comm *c, int *buf, size_t count, cudaStream_t stream)
@@ -1018,17 +980,29 @@ static int for_each_replica(tcu_msa *m, F f)
 
 // direct access between every pair of devices of a set (NVLink / NVSwitch); copies between
 // devices without it still work, staged by the driver
-static void enable_peer_access(const std::vector<int> &devs)
+// (returns whether every device can address the memory of the first one: kernels on the
+// other devices may then store into it directly)
+static bool enable_peer_access(const std::vector<int> &devs)
 {
+    bool first_reachable = true;
     for (int a : devs) {
-        if (cudaSetDevice(a) != cudaSuccess) continue;
+        if (cudaSetDevice(a) != cudaSuccess) {
+            first_reachable = false;
+            continue;
+        }
         for (int b : devs) {
             if (a == b) continue;
             int can = 0;
-            if (cudaDeviceCanAccessPeer(&can, a, b) == cudaSuccess && can) cudaDeviceEnablePeerAccess(b, 0);
+            bool ok = false;
+            if (cudaDeviceCanAccessPeer(&can, a, b) == cudaSuccess && can) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+                ok = e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled;
+            }
+            if (b == devs[0] && !ok) first_reachable = false;
         }
     }
     cudaGetLastError();  // cudaErrorPeerAccessAlreadyEnabled
+    return first_reachable;
 }
 
 // the caller's rows: separate row pointers, or one strided block (page-locked or not)
@@ -1076,7 +1050,7 @@ static int msa_create_any(const HostRows &h, int nseq, int ncol, int device, tcu
     } else if (rc == TCU_OK) {
         // every device takes 1/N of the rows over its own PCIe link, at their place in its
         // copy of the matrix; the shards are then exchanged device to device
-        enable_peer_access(devs);
+        m->peer_direct = enable_peer_access(devs);
         const int world = (int)devs.size();
         rc = for_each_replica(m, [&](tcu_msa *r, int k) {
             int r0, r1;
@@ -1484,7 +1458,8 @@ extern "C" int tcu_identity_prepare(tcu_msa *m, const int *save_seq, const int *
 
 // super-blocks [sb_begin, sb_end) of IB = 128 kept rows each
 static int identity_launch(tcu_msa *m, int sb_begin, int sb_end, float *d_out, int *d_hit,
-                           int *d_dst, uint32_t *d_bits = nullptr, float thr = 0.f)
+                           int *d_dst, uint32_t *d_bits = nullptr, float thr = 0.f,
+                           const std::vector<uint32_t *> *bits_peers = nullptr)
 {
     if (m->nchunks == 0 || sb_end <= sb_begin) return TCU_OK;
     if (m->np == 0)
@@ -1498,6 +1473,10 @@ static int identity_launch(tcu_msa *m, int sb_begin, int sb_end, float *d_out, i
     p.dst_out = d_dst;
     p.bits_out = d_bits;
     p.thr = thr;
+    if (bits_peers) {
+        if (bits_peers->size() > (size_t)ID2_MAX_PEERS) return fail(TCU_ERR_INVALID, "too many peer matrices");
+        for (uint32_t *q : *bits_peers) p.bits_peer[p.n_bits_peer++] = q;
+    }
     p.nb = m->nb;
     p.nb2 = m->nb2;
     p.nchunks = m->nchunks;
@@ -1876,13 +1855,10 @@ extern "C" int tcu_identity_row_stats(tcu_msa *m, int upper_only, float *row_max
 // bytes of the threshold bit matrix of n sequences (slab layout, tcu_internal.cuh)
 static size_t bits_bytes(int n) { return std::max<size_t>(bits_total_words(n), 4) * sizeof(uint32_t); }
 
-// All-gather of the slabs the ranks' bands own: band [b0, b1) of 128-row blocks = slabs
-// [b0, b1), contiguous in the slab layout.  (Splitting the band so that one half crosses
-// NVLink while the other is computed was considered and dropped: the NCCL transfer kernels
-// would take SM slots from the persistent identity kernel, whose static tile schedule turns
-// every delayed CTA into tail latency.)
-static int bits_allgather(tcu_msa *m, tcu_comm *comm, const std::vector<void *> *peer_base,
-                          cudaStream_t stream)
+// All-gather of the slabs the ranks' bands own (band [b0, b1) of 128-row blocks = slabs
+// [b0, b1), contiguous in the slab layout) with NCCL point-to-point transfers: the path taken
+// when the ranks cannot map each other's memory.
+static int bits_allgather(tcu_msa *m, tcu_comm *comm, cudaStream_t stream)
 {
     std::vector<size_t> off(comm->world), cnt(comm->world);
     const size_t slab_b = bits_slab_words(m->nk) * sizeof(uint32_t);
@@ -1891,21 +1867,6 @@ static int bits_allgather(tcu_msa *m, tcu_comm *comm, const std::vector<void *> 
         tcu_shard_blocks(m->nk, r, comm->world, &b0, &b1);
         off[r] = (size_t)b0 * slab_b;
         cnt[r] = (size_t)(b1 - b0) * slab_b;
-    }
-    if (peer_base) {
-        // of slab S only the rows >= 128 S carry data before the mirror pass: a band's slabs
-        // are pulled as one 2-D block that starts at the band's first row
-        std::vector<PeerBlock> blk((size_t)comm->world);
-        for (int r = 0; r < comm->world; r++) {
-            int b0, b1;
-            tcu_shard_blocks(m->nk, r, comm->world, &b0, &b1);
-            const size_t first_row = std::min<size_t>((size_t)b0 * IB, (size_t)m->nk);
-            blk[r].pitch = slab_b;
-            blk[r].off = (size_t)b0 * slab_b + first_row * 16;
-            blk[r].width = ((size_t)m->nk - first_row) * 16;
-            blk[r].height = (size_t)(b1 - b0);
-        }
-        return peer_allgatherv(comm, m->d_bits, *peer_base, blk.data(), stream);
     }
     return comm_allgatherv(comm, m->d_bits, off.data(), cnt.data(), stream);
 }
@@ -2188,15 +2149,21 @@ static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res,
         total.comm_ms += t.comm_ms;
         total.kernel_launches += t.kernel_launches;
     };
+    static const bool trace = getenv("TCU_TRACE") != nullptr;
+    const double t_begin = now_ms();
     std::vector<int> lengths((size_t)n), order((size_t)n);
     rc = tcu_sequence_lengths(m, lengths.data());
     if (rc != TCU_OK) return rc;
     add(m->timings);
+    const double t_lengths = now_ms();
     int sort_rc = TCU_OK;
     std::string sort_err;
+    double sort_ms = 0;
     auto sort = [&]() {
+        const double t0 = now_ms();
         sort_rc = tcu_cluster_order(lengths.data(), n, order.data());
         if (sort_rc != TCU_OK) sort_err = g_last_error;  // thread-local: carry it over
+        sort_ms = now_ms() - t0;
     };
     std::thread sorter;
     try {
@@ -2218,13 +2185,27 @@ static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res,
         } else {
             int b0 = 0, b1 = m->nsb;
             if (comm) tcu_shard_blocks(m->nk, comm->rank, comm->world, &b0, &b1);
+            // With peer memory (CUDA IPC over NVLink) the band exchange is part of K1: its
+            // epilogue stores every column entry into all ranks' matrices, and one one-word
+            // all-reduce afterwards tells every rank that all bands have landed.  (peer_prepare
+            // ends with a collective the host waits for: every rank is inside this call, so
+            // nobody still clusters on the matrix the stores go to.)
             std::vector<void *> peer_base;
-            const bool use_peer = comm && peer_prepare(comm, m->d_bits, peer_base, m->stream);
-            r = identity_launch(m, b0, b1, nullptr, nullptr, nullptr, m->d_bits, threshold);
+            const bool use_peer = comm && comm->world - 1 <= ID2_MAX_PEERS &&
+                                  peer_prepare(comm, m->d_bits, peer_base, m->stream);
+            std::vector<uint32_t *> others;
+            if (use_peer)
+                for (int q = 1; q < comm->world; q++)  // staggered like the pulls were
+                    others.push_back((uint32_t *)peer_base[(size_t)((comm->rank + q) % comm->world)]);
+            r = identity_launch(m, b0, b1, nullptr, nullptr, nullptr, m->d_bits, threshold,
+                                use_peer ? &others : nullptr);
             if (r != TCU_OK) return r;
             CK(cudaEventRecord(m->ev[3], m->stream));
-            if (comm) {
-                r = bits_allgather(m, comm, use_peer ? &peer_base : nullptr, m->stream);
+            if (use_peer) {
+                r = comm_allreduce_i32(comm, (int *)(comm->d_sync + 64 * 64 + 64), 1, m->stream);
+                if (r != TCU_OK) return r;
+            } else if (comm) {
+                r = bits_allgather(m, comm, m->stream);
                 if (r != TCU_OK) return r;
             }
             CK(cudaEventRecord(m->ev[4], m->stream));
@@ -2243,13 +2224,19 @@ static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res,
         return TCU_OK;
     };
     // The replicas of a multi-device handle (one process, several GPUs): every device
-    // thresholds its band into its own run of slabs; the first device then pulls the other
-    // bands over NVLink (one contiguous peer copy each), mirrors and clusters.
+    // thresholds its band.  With peer access the epilogue of K1 stores straight into the
+    // first device's matrix over NVLink (nothing to exchange afterwards); otherwise a device
+    // keeps its run of slabs and the first device pulls it (one 2-D peer copy each).  The
+    // first device then mirrors and clusters.
     auto device_part_multi = [&]() -> int {
         const int world = 1 + (int)m->peers.size();
         const size_t slab_w = bits_slab_words(n);
+        const bool direct = m->peer_direct;
         std::vector<int> bb((size_t)world + 1, 0);
-        int r = for_each_replica(m, [&](tcu_msa *d, int k) -> int {
+        CK(cudaSetDevice(m->device));
+        int r = ensure_dev(m->device, (void **)&m->d_bits, &m->bits_cap, bits_bytes(n), m);
+        if (r != TCU_OK) return r;
+        r = for_each_replica(m, [&](tcu_msa *d, int k) -> int {
             d->timings = tcu_timings{};
             d->ident_full = false;
             int e = tcu_identity_prepare(d, nullptr, save_res, indet, nullptr);
@@ -2258,13 +2245,15 @@ static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res,
             tcu_shard_blocks(d->nk, k, world, &b0, &b1);
             bb[k] = b0;
             bb[k + 1] = b1;
-            const size_t need = k == 0 ? bits_bytes(n)
-                                       : std::max<size_t>((size_t)(b1 - b0) * slab_w, 4) * sizeof(uint32_t);
-            e = ensure_dev(d->device, (void **)&d->d_bits, &d->bits_cap, need, d);
-            if (e != TCU_OK) return e;
-            // K1 indexes slabs absolutely: a device that holds only its band passes the address
-            // slab 0 would have
-            uint32_t *base = k == 0 ? d->d_bits : d->d_bits - (size_t)b0 * slab_w;
+            uint32_t *base = m->d_bits;
+            if (k > 0 && !direct) {
+                e = ensure_dev(d->device, (void **)&d->d_bits, &d->bits_cap,
+                               std::max<size_t>((size_t)(b1 - b0) * slab_w, 4) * sizeof(uint32_t), d);
+                if (e != TCU_OK) return e;
+                // K1 indexes slabs absolutely: a device that holds only its band passes the
+                // address slab 0 would have
+                base = d->d_bits - (size_t)b0 * slab_w;
+            }
             e = identity_launch(d, b0, b1, nullptr, nullptr, nullptr, base, threshold);
             if (e != TCU_OK) return e;
             CK(cudaEventRecord(d->ev[3], d->stream));
@@ -2279,7 +2268,7 @@ static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res,
         CK(cudaEventRecord(m->ev[3], m->stream));
         for (int k = 1; k < world; k++) {
             tcu_msa *p = m->peers[(size_t)k - 1];
-            if (bb[k + 1] > bb[k]) {
+            if (!direct && bb[k + 1] > bb[k]) {
                 // rows below the band's first row carry nothing before the mirror pass
                 const size_t first_row = std::min<size_t>((size_t)bb[k] * IB, (size_t)n);
                 CK(cudaMemcpy2DAsync(m->d_bits + (size_t)bb[k] * slab_w + first_row * 4, slab_w * 4,
@@ -2318,13 +2307,21 @@ static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res,
         return TCU_OK;
     }
     rc = (!comm && !m->peers.empty() && m->ncol > 0) ? device_part_multi() : device_part();
+    const double t_device = now_ms();
     if (sorter.joinable()) sorter.join();
+    const double t_join = now_ms();
     if (rc != TCU_OK) return rc;
     add(m->timings);
     if (sort_rc != TCU_OK) return fail(sort_rc, "%s", sort_err.c_str());
     rc = clusters_impl(m, nullptr, order.data(), n, threshold, clusters, n_clusters);
     if (rc != TCU_OK) return rc;
     add(m->timings);
+    if (trace)
+        fprintf(stderr, "[tcu] representatives (host clock, ms): lengths %.3f, identity+exchange %.3f "
+                "(sort on its thread %.3f, waited for %.3f), clustering %.3f; device: pack %.3f K1 %.3f "
+                "comm %.3f greedy %.3f\n", t_lengths - t_begin, t_device - t_lengths, sort_ms,
+                t_join - t_device, now_ms() - t_join, total.pack_ms, total.kernel_ms - m->timings.kernel_ms,
+                total.comm_ms, m->timings.kernel_ms);
     m->timings = total;
     return TCU_OK;
 }

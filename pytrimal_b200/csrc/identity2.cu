@@ -313,6 +313,17 @@ __global__ void __launch_bounds__(ID2_THREADS, NP <= 5 ? 2 : 1) k_identity2(cons
         const int rowB0 = 32 * wj + lj;               // + 8*b
         const unsigned long long n = (unsigned long long)p.nk;
 
+        // threshold mode: the column entry this thread stores one tile late (see the epilogue)
+        bool have_prev = false;
+        size_t prev_at = 0;
+        int prev_buf = 0;
+        auto flush_bits = [&](size_t at, int kb) {
+            const uint32_t *w = s_xch + (4 * wj) * (32 * ID2_XS) + lane * ID2_XS + 32 + kb;
+            const uint4 v = make_uint4(w[0], w[32 * ID2_XS], w[2 * 32 * ID2_XS], w[3 * 32 * ID2_XS]);
+            *reinterpret_cast<uint4 *>(p.bits_out + at) = v;
+            for (int q = 0; q < p.n_bits_peer; q++) *reinterpret_cast<uint4 *>(p.bits_peer[q] + at) = v;
+        };
+
         int stage = 0;
         uint32_t phase = 0;
         long long k = 0;
@@ -432,8 +443,17 @@ __global__ void __launch_bounds__(ID2_THREADS, NP <= 5 ? 2 : 1) k_identity2(cons
                         colword |= ((mine >> (4 * (lane & 7))) & 0xFu) << (4 * a);
                     }
                 }
-                const int j = j0 + lane;
-                if (j < p.nk) p.bits_out[bits_word_index(p.nk, j, 4 * BI + wi)] = colword;
+                // The four words of a column (wi = 0..3) are 16 contiguous bytes of the slab
+                // layout, held by four warps.  Each warp parks its word in the padding of its
+                // patch (two buffers, by tile parity); one tile later -- the barrier above
+                // has then seen every warp finish this epilogue -- the warps with wi == 0
+                // store whole 16-byte column entries, 1 KB contiguous per tile: to the local
+                // matrix and, in a multi-GPU run, straight into every peer's over NVLink.
+                if (wi == 0 && have_prev) flush_bits(prev_at, prev_buf);
+                patch[lane * ID2_XS + 32 + (int)(k & 1)] = colword;
+                have_prev = j0 + lane < p.nk;
+                prev_at = bits_word_index(p.nk, j0 + lane, 4 * BI);
+                prev_buf = (int)(k & 1);
                 __syncwarp();  // the patch is rewritten by the next tile
                 continue;
             }
@@ -461,6 +481,10 @@ __global__ void __launch_bounds__(ID2_THREADS, NP <= 5 ? 2 : 1) k_identity2(cons
                 }
             }
             __syncwarp();  // the patch is rewritten by the next tile
+        }
+        if (p.bits_out != nullptr) {  // the last tile's column entries
+            asm volatile("bar.sync 1, %0;" ::"n"(ID2_MATH_THREADS) : "memory");
+            if (wi == 0 && have_prev) flush_bits(prev_at, prev_buf);
         }
     }
 

@@ -63,6 +63,8 @@ __host__ __device__ constexpr int tile2_bytes(int np) { return tile2_words(np) *
 __host__ __device__ constexpr int role_words(int np) { return KC2 * RB * (1 + rest_words(np)); }
 __host__ __device__ constexpr int role_bytes(int np) { return role_words(np) * 4; }
 
+constexpr int ID2_MAX_PEERS = 15;  // other devices whose bit matrix K1 may write
+
 struct Identity2Params {
     const uint32_t *planes;  // v2 plane tiles
     const uint8_t *gbytes;   // gap indicator bytes, UMMA canonical layout
@@ -82,6 +84,11 @@ struct Identity2Params {
     // pair in the slab layout below; out / hit_out / dst_out are not touched
     uint32_t *bits_out;
     float thr;
+    // the same words stored into the bit matrices of other devices as well (peer memory over
+    // NVLink: CUDA IPC mappings or peer access inside one process) -- the band exchange of a
+    // multi-GPU clustering happens inside the epilogue, tile by tile, under the computation
+    int n_bits_peer;
+    uint32_t *bits_peer[ID2_MAX_PEERS];
 };
 
 // ---------------------------------------------------------------------------
