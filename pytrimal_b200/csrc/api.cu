@@ -351,8 +351,10 @@ struct tcu_msa {
     bool ident_full = false;  // unmasked rows: usable by tcu_similarity
 
     // threshold bit matrix (slab layout, tcu_internal.cuh) of the clustering calls
-    uint32_t *d_bits = nullptr;
+    uint32_t *d_bits = nullptr;   // threshold bits as K1 leaves them (slab layout, column words)
     size_t bits_cap = 0;
+    uint32_t *d_brows = nullptr;  // full symmetric bit matrix, one row per sequence
+    size_t brows_cap = 0;
 
     // generic scratch
     void *d_scratch = nullptr;
@@ -1174,6 +1176,7 @@ extern "C" void tcu_msa_destroy(tcu_msa *m)
     dev_cache_give(m->device, m->d_gbytes, m->gbytes_cap);
     dev_cache_give(m->device, m->d_ident, m->ident_cap);
     dev_cache_give(m->device, m->d_bits, m->bits_cap);
+    dev_cache_give(m->device, m->d_brows, m->brows_cap);
     dev_cache_give(m->device, m->d_scratch, m->scratch_cap);
     dev_cache_give(m->device, m->d_small, m->small_cap);
     for (auto &e : m->band_done)
@@ -1854,6 +1857,8 @@ extern "C" int tcu_identity_row_stats(tcu_msa *m, int upper_only, float *row_max
 
 // bytes of the threshold bit matrix of n sequences (slab layout, tcu_internal.cuh)
 static size_t bits_bytes(int n) { return std::max<size_t>(bits_total_words(n), 4) * sizeof(uint32_t); }
+// bytes of the row-per-sequence form the clustering walk reads
+static size_t brows_bytes(int n) { return std::max<size_t>(brow_total_words(n), 4) * sizeof(uint32_t); }
 
 // All-gather of the slabs the ranks' bands own (band [b0, b1) of 128-row blocks = slabs
 // [b0, b1), contiguous in the slab layout) with NCCL point-to-point transfers: the path taken
@@ -1871,10 +1876,10 @@ static int bits_allgather(tcu_msa *m, tcu_comm *comm, cudaStream_t stream)
     return comm_allgatherv(comm, m->d_bits, off.data(), cnt.data(), stream);
 }
 
-// Greedy clustering in the given order over the threshold bit matrix m->d_bits.  When `id0`
-// is given the matrix is first derived from the resident float identities (K5: rows
-// [0, nseq), both mirror images); otherwise the caller has filled it (K1's threshold
-// epilogue + mirror pass).
+// Greedy clustering in the given order over the threshold bit matrix m->d_brows (one row per
+// sequence).  When `id0` is given the matrix is first derived from the resident float
+// identities (K5); otherwise the caller has filled it (K1's threshold epilogue + the mirror /
+// relayout pass).
 static int clusters_impl(tcu_msa *m, const float *id0, const int *order, int count,
                          float threshold, int *clusters, int *n_clusters)
 {
@@ -1887,36 +1892,29 @@ static int clusters_impl(tcu_msa *m, const float *id0, const int *order, int cou
             return fail(TCU_ERR_INVALID, "order[%d] = %d outside [0,%d)", k, order[k], n);
     *n_clusters = 0;
     if (count == 0) return TCU_OK;
-    const int nslab = (n + 127) / 128;
     auto up = [](size_t b) { return (b + 255) / 256 * 256; };
-    const size_t rep_b = up((size_t)nslab * 16 + 4);
-    const size_t ord_b = up((size_t)count * 4), alive_b = up((size_t)mis_block());
-    const size_t adj_b = up((size_t)mis_block() * 32 * 4);
+    const size_t ord_b = up((size_t)count * 4), walk_b = greedy_scratch_bytes(n, count);
     if (id0) {
-        rc = ensure_dev(m->device, (void **)&m->d_bits, &m->bits_cap, bits_bytes(n), m);
+        rc = ensure_dev(m->device, (void **)&m->d_brows, &m->brows_cap, brows_bytes(n), m);
         if (rc != TCU_OK) return rc;
     }
-    rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, rep_b + 2 * ord_b + alive_b + adj_b, m);
+    rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, 256 + 2 * ord_b + walk_b, m);
     if (rc != TCU_OK) return rc;
     uint8_t *p = (uint8_t *)m->d_scratch;
-    uint32_t *d_rep = (uint32_t *)p;  // 4 * nslab words, then the cluster counter
-    int *d_count = (int *)(d_rep + 4 * nslab);
-    p += rep_b;
+    int *d_count = (int *)p;
+    p += 256;
     int *d_order = (int *)p;
     p += ord_b;
     int *d_clusters = (int *)p;
     p += ord_b;
-    uint8_t *d_alive = p;
-    p += alive_b;
-    uint32_t *d_adj = (uint32_t *)p;
+    void *d_walk = p;
     CK(cudaEventRecord(m->ev[0], m->stream));
     CK(cudaMemcpyAsync(d_order, order, (size_t)count * 4, cudaMemcpyHostToDevice, m->stream));
-    CK(cudaMemsetAsync(d_rep, 0, rep_b, m->stream));
     CK(cudaEventRecord(m->ev[1], m->stream));
-    if (id0) CK(launch_identity_bits(id0, n, threshold, m->d_bits, 0, n, m->stream));
+    if (id0) CK(launch_identity_bits(id0, n, threshold, m->d_brows, 0, n, m->stream));
     CK(cudaEventRecord(m->ev[2], m->stream));
-    CK(launch_greedy_clusters(m->d_bits, n, d_order, count, d_rep, d_alive, d_adj, d_clusters,
-                              d_count, m->stream));
+    CK(launch_greedy_clusters(m->d_brows, n, d_order, count, d_walk, d_clusters, d_count, m->num_sms,
+                              m->stream));
     CK(cudaEventRecord(m->ev[3], m->stream));
     int found = 0;
     CK(cudaMemcpyAsync(&found, d_count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
@@ -1931,7 +1929,7 @@ static int clusters_impl(tcu_msa *m, const float *id0, const int *order, int cou
     m->timings.pack_ms = ev_ms(m->ev[1], m->ev[2]);    // threshold -> bit matrix (K5)
     m->timings.kernel_ms = ev_ms(m->ev[2], m->ev[3]);  // greedy clustering
     m->timings.d2h_ms = ev_ms(m->ev[3], m->ev[4]);
-    m->timings.kernel_launches = (id0 ? 1 : 0) + 2 * ((count + mis_block() - 1) / mis_block());
+    m->timings.kernel_launches = (id0 ? 1 : 0) + 1;
     return TCU_OK;
 }
 
@@ -2178,9 +2176,11 @@ static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res,
         if (r != TCU_OK) return r;
         r = ensure_dev(m->device, (void **)&m->d_bits, &m->bits_cap, bits_bytes(n), m);
         if (r != TCU_OK) return r;
+        r = ensure_dev(m->device, (void **)&m->d_brows, &m->brows_cap, brows_bytes(n), m);
+        if (r != TCU_OK) return r;
         if (m->nchunks == 0) {
             // no columns: every identity is 0 (template.h:427-434)
-            CK(cudaMemsetAsync(m->d_bits, threshold < 0.f ? 0xFF : 0, bits_bytes(n), m->stream));
+            CK(cudaMemsetAsync(m->d_brows, threshold < 0.f ? 0xFF : 0, brows_bytes(n), m->stream));
             CK(cudaEventRecord(m->ev[3], m->stream));
         } else {
             int b0 = 0, b1 = m->nsb;
@@ -2209,7 +2209,7 @@ static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res,
                 if (r != TCU_OK) return r;
             }
             CK(cudaEventRecord(m->ev[4], m->stream));
-            CK(launch_bits_symmetrize(m->d_bits, n, m->stream));
+            CK(launch_bits_rows(m->d_bits, n, m->d_brows, m->stream));
             m->timings.kernel_launches++;
         }
         CK(cudaEventRecord(m->ev[5], m->stream));
@@ -2235,6 +2235,8 @@ static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res,
         std::vector<int> bb((size_t)world + 1, 0);
         CK(cudaSetDevice(m->device));
         int r = ensure_dev(m->device, (void **)&m->d_bits, &m->bits_cap, bits_bytes(n), m);
+        if (r != TCU_OK) return r;
+        r = ensure_dev(m->device, (void **)&m->d_brows, &m->brows_cap, brows_bytes(n), m);
         if (r != TCU_OK) return r;
         r = for_each_replica(m, [&](tcu_msa *d, int k) -> int {
             d->timings = tcu_timings{};
@@ -2279,7 +2281,7 @@ static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res,
             m->timings.kernel_launches += p->timings.kernel_launches;
         }
         CK(cudaEventRecord(m->ev[4], m->stream));
-        CK(launch_bits_symmetrize(m->d_bits, n, m->stream));
+        CK(launch_bits_rows(m->d_bits, n, m->d_brows, m->stream));
         m->timings.kernel_launches++;
         CK(cudaEventRecord(m->ev[5], m->stream));
         CK(cudaStreamSynchronize(m->stream));

@@ -11,22 +11,22 @@
 // Here they run where the matrix already is:
 //
 //   K5 k_identity_bits   one streaming pass (HBM-bound, 4*P bytes read): identity > threshold
-//                        as a full symmetric nseq x nseq BIT matrix (nseq^2/8 bytes); only for
-//                        a matrix that is already resident as floats -- tcu_representatives gets
-//                        the bits from K1's epilogue + k_bits_symmetrize
+//                        as a full symmetric nseq x nseq BIT matrix, one row per sequence; only
+//                        for a matrix that is already resident as floats -- tcu_representatives
+//                        gets the bits from K1's epilogue + k_bits_rows
 //   K6 k_row_stats       per-row statistics; each lane owns one row and replays the
 //                        reference's fp32 additions in the reference's order (j ascending)
-//   K7 k_mis_scan  +  K8 k_mis_resolve
-//                        the greedy clustering.  Both reference loops are the same rule:
+//   K7 k_greedy_clusters the greedy clustering.  Both reference loops are the same rule:
 //                        in the given order, a sequence opens a new cluster iff no EARLIER
 //                        cluster representative has identity > threshold with it (the
 //                        lexicographically-first maximal independent set of the threshold
-//                        graph).  Processed in blocks of 1024 sequences: K7 tests each
-//                        sequence of the block against all representatives of earlier
-//                        blocks (one AND over two bit rows per sequence, whole GPU) and
-//                        gathers the 1024 x 1024 adjacency inside the block; K8 resolves
-//                        the block in one CTA (fixed point of the greedy rule, all 1024
-//                        sequences at once).
+//                        graph).  One persistent kernel walks the order in blocks of 1024
+//                        sequences: "scanner" CTAs (all SMs but one) test the sequences of a
+//                        block against the representatives of earlier blocks (one AND over two
+//                        bit rows per sequence) and gather the adjacency inside the block and
+//                        to the block before; the "resolver" CTA settles a block in one go
+//                        (fixed point of the greedy rule, all 1024 sequences at once) while
+//                        the scanners already work on the next one.
 //                        Result and order of the cluster list are exactly the reference's.
 #include "tcu_internal.cuh"
 
@@ -40,7 +40,7 @@ __device__ __forceinline__ long long pair_row_base(long long i, long long n)
 }
 
 // ---------------------------------------------------------------------------
-// K5: threshold -> symmetric bit matrix in the slab layout (tcu_internal.cuh), from a
+// K5: threshold -> symmetric bit matrix, one row per sequence (tcu_internal.cuh), from a
 // resident float matrix.  One warp per 32 x 32 block of the upper triangle: 32 coalesced row
 // reads (issued in batches of 16 before any is used, so that a warp keeps 2 KB in
 // flight); the ballots are the row words, the per-lane accumulated bits the words of the
@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(256) k_identity_bits(const float *__restrict__
                                                        float thr, uint32_t *__restrict__ bits,
                                                        int rb_begin)
 {
+    const size_t pitch = brow_pitch_words(n);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rb = rb_begin + blockIdx.y;  // 32-row block
     const int jw = blockIdx.x * 8 + warp;  // 32-column word
@@ -77,10 +78,10 @@ __global__ void __launch_bounds__(256) k_identity_bits(const float *__restrict__
     }
     if (jw == rb) {
         // diagonal block: bits j > i come from the row word, bits j < i from the column word
-        if (i0 + lane < n) bits[bits_word_index(n, i0 + lane, jw)] = mine | colword;
+        if (i0 + lane < n) bits[(size_t)(i0 + lane) * pitch + jw] = mine | colword;
     } else {
-        if (i0 + lane < n) bits[bits_word_index(n, i0 + lane, jw)] = mine;
-        if (j < n) bits[bits_word_index(n, j, rb)] = colword;
+        if (i0 + lane < n) bits[(size_t)(i0 + lane) * pitch + jw] = mine;
+        if (j < n) bits[(size_t)j * pitch + rb] = colword;
     }
 }
 
@@ -98,60 +99,72 @@ cudaError_t launch_identity_bits(const float *id, int n, float thr, uint32_t *bi
 }
 
 // ---------------------------------------------------------------------------
-// Mirror pass over a bit matrix of which K1's threshold epilogue wrote the "column words"
-// (row j against earlier sequences i < j; zeros where j <= i): every 128 x 128 block (BI, BJ),
-// BI < BJ, is transposed into its mirror image and a diagonal block becomes U | U^T.  One CTA
-// of 128 threads per block: thread = row, one 16-byte load, four 32 x 32 butterfly transposes,
-// the mirrored rows leave as 16-byte stores through shared memory.  HBM-bound: reads and
-// writes n^2 / 16 bytes each.
+// Mirror + relayout pass.  K1's threshold epilogue leaves, in the slab layout, the "column
+// words" of the pairs (row j against earlier sequences i < j; zeros where j <= i).  This
+// pass writes the full symmetric matrix with one contiguous row per sequence (what the
+// clustering walk reads, in an order that has nothing to do with the sequence index): output
+// block (R, C) of 128 x 128 bits is slab C's rows of R as they are when R > C, the transpose
+// of slab R's rows of C when R < C, and U | U^T on the diagonal.  One CTA of 128 threads per
+// row block and PAIR of column blocks (a thread's two 16-byte stores fill one 32-byte sector
+// of its row); a transpose is four 32 x 32 butterflies across the warp and a pass through
+// shared memory.  HBM-bound: reads and writes n^2 / 8 bytes each.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_bits_symmetrize(uint32_t *__restrict__ bits, int n)
+__global__ void __launch_bounds__(128) k_bits_rows(const uint32_t *__restrict__ slab_bits, int n,
+                                                   uint32_t *__restrict__ rows)
 {
-    // block (BI, BJ), BJ >= BI: rows of super-block BJ against the sequences of super-block BI
-    const int BI = blockIdx.x, BJ = blockIdx.y;
-    if (BJ < BI) return;
-    __shared__ uint4 s_out[128];  // [sequence of BI] = its words against the rows of BJ
+    __shared__ uint4 s_out[128];
+    const int R = blockIdx.y;
     const int lane = threadIdx.x & 31, u = threadIdx.x >> 5;
-    const int r = BJ * 128 + threadIdx.x;  // this thread's row of BJ (warp u = its 32-row group)
-    uint4 *slabs = reinterpret_cast<uint4 *>(bits);
+    const int nslab = (n + 127) >> 7;
+    const uint4 *slabs = reinterpret_cast<const uint4 *>(slab_bits);
+    const size_t pitch4 = brow_pitch_words(n) / 4;
+    const int r = R * 128 + threadIdx.x;  // the row this thread stores
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-    const uint4 own = r < n ? slabs[(size_t)BI * n + r] : zero;  // bits (r, i) for i < r
-    const uint32_t w4[4] = {own.x, own.y, own.z, own.w};
     uint32_t *s_words = reinterpret_cast<uint32_t *>(s_out);
+#pragma unroll 1
+    for (int c = 0; c < 2; c++) {
+        const int C = 2 * blockIdx.x + c;
+        if (C >= nslab) break;  // uniform
+        uint4 v = zero;
+        if (C <= R && r < n) v = slabs[(size_t)C * n + r];  // bits (r, i) for i in C, i < r
+        if (C >= R) {
+            // rows of C against the sequences of R, transposed
+            const int x = C * 128 + threadIdx.x;
+            const uint4 own = C == R ? v : (x < n ? slabs[(size_t)R * n + x] : zero);
+            const uint32_t w4[4] = {own.x, own.y, own.z, own.w};
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        // 32 x 32 bit transpose across the warp (lane = row): five butterfly stages, each
-        // swapping the off-diagonal j x j blocks with the lane j away; afterwards lane k
-        // holds sequence 128 BI + 32 q + k against rows 128 BJ + 32 u ..
-        uint32_t x = w4[q];
-        uint32_t low = 0x0000FFFFu;  // columns c with (c & j) == 0
+            for (int q = 0; q < 4; q++) {
+                // 32 x 32 bit transpose across the warp (lane = row): five butterfly stages,
+                // each swapping the off-diagonal j x j blocks with the lane j away; afterwards
+                // lane k holds sequence 128 R + 32 q + k against rows 128 C + 32 u ..
+                uint32_t xw = w4[q];
+                uint32_t low = 0x0000FFFFu;  // columns c with (c & j) == 0
 #pragma unroll
-        for (int j = 16; j >= 1; j >>= 1) {
-            const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
-            x = (lane & j) ? ((x & ~low) | ((y & ~low) >> j)) : ((x & low) | ((y & low) << j));
-            low ^= low << (j >> 1);  // 0x0000FFFF -> 0x00FF00FF -> 0x0F0F0F0F -> 0x33333333 -> 0x55555555
+                for (int j = 16; j >= 1; j >>= 1) {
+                    const uint32_t y = __shfl_xor_sync(0xffffffffu, xw, j);
+                    xw = (lane & j) ? ((xw & ~low) | ((y & ~low) >> j)) : ((xw & low) | ((y & low) << j));
+                    low ^= low << (j >> 1);  // 0x0000FFFF -> 0x00FF00FF -> ... -> 0x55555555
+                }
+                s_words[(32 * q + lane) * 4 + u] = xw;
+            }
+            __syncthreads();
+            const uint4 t4 = s_out[threadIdx.x];
+            v.x |= t4.x;
+            v.y |= t4.y;
+            v.z |= t4.z;
+            v.w |= t4.w;
+            __syncthreads();  // s_out is rewritten by the second column block
         }
-        s_words[(32 * q + lane) * 4 + u] = x;
+        if (r < n) reinterpret_cast<uint4 *>(rows)[(size_t)r * pitch4 + C] = v;
     }
-    __syncthreads();
-    const int c = BI * 128 + threadIdx.x;  // sequence of BI whose mirrored words this thread stores
-    if (c >= n) return;
-    uint4 t4 = s_out[threadIdx.x];
-    if (BI == BJ) {
-        t4.x |= own.x;
-        t4.y |= own.y;
-        t4.z |= own.z;
-        t4.w |= own.w;
-    }
-    slabs[(size_t)BJ * n + c] = t4;
 }
 
-cudaError_t launch_bits_symmetrize(uint32_t *bits, int n, cudaStream_t stream)
+cudaError_t launch_bits_rows(const uint32_t *slab_bits, int n, uint32_t *rows, cudaStream_t stream)
 {
     if (n <= 0) return cudaSuccess;
     const int nsb = (n + 127) / 128;
-    dim3 grid(nsb, nsb);
-    k_bits_symmetrize<<<grid, 128, 0, stream>>>(bits, n);
+    dim3 grid((nsb + 1) / 2, nsb);
+    k_bits_rows<<<grid, 128, 0, stream>>>(slab_bits, n, rows);
     return cudaGetLastError();
 }
 
@@ -259,187 +272,299 @@ cudaError_t launch_row_stats(const float *id, int n, bool upper_only, float *row
 }
 
 // ---------------------------------------------------------------------------
-// K7: four warps per sequence t of the current block (order[base .. base+cnt)).
-//   alive8[t]  = no representative found so far (bitset `rep`) is adjacent to it
-//   adj[l][t]  = adjacency bits to the block's sequences 32*l .. 32*l+31 that precede t
-//                (word-major, so that K8 reads one word of 32 consecutive sequences
-//                without bank conflicts); zero for a sequence that is not alive
-// A sequence's bits are one 16-byte entry per slab (tcu_internal.cuh); `rep` is padded to
-// whole slabs (4 * nslab words, zero beyond n).
+// K7: the greedy walk as ONE persistent kernel (cooperative launch: every CTA is resident).
+//
+// The order is cut into blocks of 1024 sequences.  CTA 0 is the resolver, the others scan:
+//
+//   scanner, block b, sequence t (four warps; its bit row is one contiguous read):
+//     alive[t]    = no representative of the blocks <= b-2 is adjacent to it
+//                   (`rep` bitset; waits until the resolver has finished block b-2)
+//     own[w][t]   = adjacency bits to the block's own sequences 32 w .. that precede t
+//     prev[w][t]  = adjacency bits to the sequences of block b-1
+//                   (word-major: the resolver reads one word of 32 consecutive sequences
+//                   without bank conflicts)
+//   resolver, block b (thread t = sequence t, its `own` words in registers):
+//     a sequence adjacent to a representative chosen in block b-1 (prev & the previous
+//     block's result) is out; then the greedy rule is iterated to its fixed point for the
+//     whole block at once:
+//       a sequence with an adjacent representative is out;
+//       one none of whose earlier neighbours is undecided or a representative becomes one.
+//     The earliest undecided sequence always decides, so the loop ends (after as many
+//     rounds as the longest chain of dependent decisions: a handful on real alignments)
+//     with exactly the sequential answer.  New representatives are appended in visiting
+//     order and entered into `rep`.
+//
+// Because the scan of block b needs nothing from block b-1's resolution, it runs while the
+// resolver is busy with b-1: the critical path is the resolver alone (round 2 launched a
+// scan and a resolve kernel per block, 2 x 49 dependent launches at 50 000 sequences).
+// Hand-over through global counters with release / acquire semantics: scanned[b] counts
+// the scanner CTAs done with block b, `resolved` the blocks the resolver has finished; the
+// per-block scratch (alive / own / prev) is double-buffered by block parity.  A scanner may
+// see `rep` while the resolver adds block b-1's representatives to it: harmless, those are
+// genuine earlier representatives and the union with the prev check is the same.
 // ---------------------------------------------------------------------------
 constexpr int MIS_NB = 1024;
+constexpr int MIS_SEQ_PER_CTA = 8;  // 1024 threads, four warps per sequence
 
-__global__ void __launch_bounds__(256) k_mis_scan(const uint32_t *__restrict__ bits, int n,
-                                                  const int *__restrict__ order, int base, int cnt,
-                                                  const uint32_t *__restrict__ rep,
-                                                  uint8_t *__restrict__ alive8,
-                                                  uint32_t *__restrict__ adj)
+struct GreedyParams {
+    const uint32_t *rows;  // symmetric bit matrix, one row per sequence
+    size_t pitch_w;
+    int n;
+    const int *order;
+    int total;
+    uint32_t *rep;  // 4 * ceil(n / 128) words, zero on entry
+    int *scanned;   // one counter per block, zero on entry
+    int *resolved;  // zero on entry
+    uint8_t *alive8;     // [2][MIS_NB]
+    uint32_t *adj_own;   // [2][32][MIS_NB]
+    uint32_t *adj_prev;  // [2][32][MIS_NB]
+    int *clusters;
+    int *count;
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int *p)
 {
-    // four warps per sequence, two sequences per CTA: the scan of a block is a chain of
-    // dependent memory latencies, so it is spread over many warps with few loads each
-    // (2 048 warps per block of 1 024 sequences)
-    __shared__ int s_ord[MIS_NB];
-    __shared__ uint32_t s_hit[2][4];
-    asm volatile("griddepcontrol.launch_dependents;");  // the resolve kernel may be set up now
-    for (int k = threadIdx.x; k < cnt; k += 256) s_ord[k] = order[base + k];
-    __syncthreads();
-    // programmatic dependent launch: everything above ran under the tail of the previous
-    // block's resolve kernel; `rep` is its output
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int lane = threadIdx.x & 31, part = (threadIdx.x >> 5) & 3, sub = threadIdx.x >> 7;
-    const int t = blockIdx.x * 2 + sub;
-    const bool live = t < cnt;
-    const int s = live ? s_ord[t] : 0;
-    const int nslab = (n + 127) >> 7;
-    const uint4 *slabs = reinterpret_cast<const uint4 *>(bits) + s;
-    const uint4 *rep4 = reinterpret_cast<const uint4 *>(rep);
-    uint32_t acc = 0;
-    if (live) {
-        for (int S = lane + 32 * part; S < nslab; S += 128) {
-            const uint4 a = slabs[(size_t)S * n];
-            // L2 only: under programmatic dependent launch this grid was already resident
-            // while the previous resolve kernel wrote `rep`; an L1 line left by an earlier
-            // block's scan on this SM would be stale
-            const uint4 r = __ldcg(rep4 + S);
-            acc |= (a.x & r.x) | (a.y & r.y) | (a.z & r.z) | (a.w & r.w);
-        }
-    }
-    const uint32_t any = __any_sync(0xffffffffu, acc != 0) ? 1u : 0u;
-    if (lane == 0) s_hit[sub][part] = any;
-    __syncthreads();
-    if (!live) return;
-    const bool dead = (s_hit[sub][0] | s_hit[sub][1] | s_hit[sub][2] | s_hit[sub][3]) != 0;
-    if (part == 0 && lane == 0) alive8[t] = dead ? 0 : 1;
-    // adjacency to the earlier sequences of the block: word w = 8 part + lane / 4 holds the
-    // block's sequences 32 w ..; four lanes gather 8 bits each
-    const int w = 8 * part + (lane >> 2);
-    const int a0 = w * 32 + (lane & 3) * 8;
-    uint32_t word = 0;
-    if (!dead && a0 < t) {
-        const int amax = min(8, t - a0);
-        uint32_t g[8];
-#pragma unroll
-        for (int a = 0; a < 8; a++) {
-            const int u = s_ord[min(a0 + a, cnt - 1)];
-            g[a] = a < amax ? (bits[bits_word_index(n, s, u >> 5)] >> (u & 31)) & 1u : 0u;
-        }
-#pragma unroll
-        for (int a = 0; a < 8; a++) word |= g[a] << ((lane & 3) * 8 + a);
-    }
-    word |= __shfl_xor_sync(0xffffffffu, word, 1);
-    word |= __shfl_xor_sync(0xffffffffu, word, 2);
-    if ((lane & 3) == 0) adj[w * MIS_NB + t] = word;
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void group_bar(int id)  // the 128 threads of one sequence
+{
+    asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
 }
 
-// K8: one CTA of 1024 threads resolves the block; thread t owns sequence t of the block and
-// keeps its adjacency words to the earlier sequences of the block in registers.  The greedy
-// rule is iterated to its fixed point for the whole block at once:
-//   a sequence with an adjacent representative is out;
-//   one none of whose earlier neighbours is undecided or a representative becomes one.
-// The earliest undecided sequence always decides, so the loop ends (after as many rounds as
-// the longest chain of dependent decisions: a handful on real alignments) with exactly the
-// sequential answer.  The new representatives are appended in visiting order.
-__global__ void __launch_bounds__(1024) k_mis_resolve(const uint32_t *__restrict__ adj,
-                                                      const uint8_t *__restrict__ alive8,
-                                                      const int *__restrict__ order, int base,
-                                                      int cnt, uint32_t *__restrict__ rep,
-                                                      int *__restrict__ clusters,
-                                                      int *__restrict__ count)
+__device__ void greedy_scanner(const GreedyParams &p, int (*s_ord)[MIS_NB], uint32_t (*s_hit)[4])
 {
-    __shared__ uint32_t s_in[32], s_und[32], s_pre[32];
+    const int tid = threadIdx.x, lane = tid & 31, part = (tid >> 5) & 3, sub = tid >> 7;
+    const int nscan = gridDim.x - 1;
+    const int slot0 = (blockIdx.x - 1) * MIS_SEQ_PER_CTA + sub, stride = nscan * MIS_SEQ_PER_CTA;
+    const int nblk = (p.total + MIS_NB - 1) / MIS_NB;
+    const int nslab = (p.n + 127) >> 7;
+    const uint4 *rep4 = reinterpret_cast<const uint4 *>(p.rep);
+    for (int b = 0; b < nblk; b++) {
+        const int base = b * MIS_NB, cnt = min(MIS_NB, p.total - base), buf = b & 1;
+        for (int k = tid; k < cnt; k += 1024) s_ord[buf][k] = p.order[base + k];
+        // `rep` must hold the blocks <= b-2, and the resolver must be done reading this
+        // parity's scratch (it did so for block b-2)
+        if (tid == 0 && b >= 2)
+            while (ld_acquire_gpu(p.resolved) < b - 1) {
+            }
+        __syncthreads();
+        uint8_t *alive8 = p.alive8 + buf * MIS_NB;
+        uint32_t *own = p.adj_own + (size_t)buf * 32 * MIS_NB;
+        uint32_t *prev = p.adj_prev + (size_t)buf * 32 * MIS_NB;
+        for (int t = slot0; t < cnt; t += stride) {
+            const int s = s_ord[buf][t];
+            const uint32_t *row = p.rows + (size_t)s * p.pitch_w;
+            const uint4 *row4 = reinterpret_cast<const uint4 *>(row);
+            uint32_t acc = 0;
+            for (int S = lane + 32 * part; S < nslab; S += 128) {
+                const uint4 a = row4[S];             // immutable: may stay in L1 for the gathers
+                const uint4 r = __ldcg(rep4 + S);    // written by the resolver: L2
+                acc |= (a.x & r.x) | (a.y & r.y) | (a.z & r.z) | (a.w & r.w);
+            }
+            const uint32_t any = __any_sync(0xffffffffu, acc != 0) ? 1u : 0u;
+            if (lane == 0) s_hit[sub][part] = any;
+            group_bar(1 + sub);
+            const bool dead = (s_hit[sub][0] | s_hit[sub][1] | s_hit[sub][2] | s_hit[sub][3]) != 0;
+            if (part == 0 && lane == 0) alive8[t] = dead ? 0 : 1;
+            if (!dead) {
+                // word w = 8 part + lane / 4 covers the block sequences 32 w ..; four lanes
+                // gather 8 bits each
+                const int w = 8 * part + (lane >> 2);
+                const int a0 = w * 32 + (lane & 3) * 8;
+                uint32_t word = 0, pword = 0;
+                if (a0 < t) {
+                    const int amax = min(8, t - a0);
+                    uint32_t g[8];
+#pragma unroll
+                    for (int a = 0; a < 8; a++) {
+                        const int v = s_ord[buf][min(a0 + a, cnt - 1)];
+                        g[a] = a < amax ? (row[v >> 5] >> (v & 31)) & 1u : 0u;
+                    }
+#pragma unroll
+                    for (int a = 0; a < 8; a++) word |= g[a] << ((lane & 3) * 8 + a);
+                }
+                if (b > 0) {  // the block before is always full
+                    uint32_t g[8];
+#pragma unroll
+                    for (int a = 0; a < 8; a++) {
+                        const int v = s_ord[buf ^ 1][a0 + a];
+                        g[a] = (row[v >> 5] >> (v & 31)) & 1u;
+                    }
+#pragma unroll
+                    for (int a = 0; a < 8; a++) pword |= g[a] << ((lane & 3) * 8 + a);
+                }
+                word |= __shfl_xor_sync(0xffffffffu, word, 1);
+                word |= __shfl_xor_sync(0xffffffffu, word, 2);
+                pword |= __shfl_xor_sync(0xffffffffu, pword, 1);
+                pword |= __shfl_xor_sync(0xffffffffu, pword, 2);
+                if ((lane & 3) == 0) {
+                    own[w * MIS_NB + t] = word;
+                    prev[w * MIS_NB + t] = pword;
+                }
+            }
+            group_bar(1 + sub);  // s_hit is rewritten by the group's next sequence
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicAdd(p.scanned + b, 1);
+    }
+}
+
+__device__ void greedy_resolver(const GreedyParams &p, uint32_t *s_in, uint32_t *s_und,
+                                uint32_t *s_pre, uint32_t *s_inprev)
+{
     const int t = threadIdx.x, lane = t & 31, g = t >> 5;
-    asm volatile("griddepcontrol.launch_dependents;");  // the next block's scan may be set up now
-    const int my_seq = t < cnt ? order[base + t] : 0;  // does not depend on the scan kernel
-    asm volatile("griddepcontrol.wait;" ::: "memory");  // adj / alive8 are its output
-    uint32_t a[32];
+    const int nscan = gridDim.x - 1;
+    const int nblk = (p.total + MIS_NB - 1) / MIS_NB;
+    int found = 0;
+    for (int b = 0; b < nblk; b++) {
+        const int base = b * MIS_NB, cnt = min(MIS_NB, p.total - base), buf = b & 1;
+        const int my_seq = t < cnt ? p.order[base + t] : 0;
+        if (t == 0)
+            while (ld_acquire_gpu(p.scanned + b) < nscan) {
+            }
+        __syncthreads();
+        // the scanners' output: L2 only (this SM's L1 may hold the lines of two blocks ago)
+        const uint32_t *own = p.adj_own + (size_t)buf * 32 * MIS_NB;
+        const uint32_t *prev = p.adj_prev + (size_t)buf * 32 * MIS_NB;
+        bool undec = t < cnt && __ldcg(p.alive8 + buf * MIS_NB + t) != 0;
+        uint32_t a[32];
 #pragma unroll
-    for (int w = 0; w < 32; w++) a[w] = (w <= g && t < cnt) ? __ldcg(adj + w * MIS_NB + t) : 0u;  // L2 only, as above
-    bool undec = t < cnt && __ldcg(alive8 + t) != 0;
-    {
-        const uint32_t b = __ballot_sync(0xffffffffu, undec);
-        if (lane == 0) {
-            s_und[g] = b;
-            s_in[g] = 0;
-        }
-    }
-    __syncthreads();
-    for (;;) {
-        uint32_t hit = 0, wait = 0;
+        for (int w = 0; w < 32; w++) a[w] = (w <= g && undec) ? __ldcg(own + w * MIS_NB + t) : 0u;
+        if (b > 0) {
+            uint32_t hitp = 0;
+            if (undec) {
 #pragma unroll
-        for (int w = 0; w < 32; w++) {
-            hit |= a[w] & s_in[w];
-            wait |= a[w] & s_und[w];
+                for (int w = 0; w < 32; w++) hitp |= __ldcg(prev + w * MIS_NB + t) & s_inprev[w];
+            }
+            undec = undec && hitp == 0;
         }
-        const bool out = undec && hit != 0;
-        const bool in = undec && hit == 0 && wait == 0;
-        const uint32_t bi = __ballot_sync(0xffffffffu, in), bo = __ballot_sync(0xffffffffu, out);
-        undec = undec && !in && !out;
-        __syncthreads();  // every thread has read the masks of this round
-        if (lane == 0) {
-            s_in[g] |= bi;
-            s_und[g] &= ~(bi | bo);
+        {
+            const uint32_t bu = __ballot_sync(0xffffffffu, undec);
+            if (lane == 0) {
+                s_und[g] = bu;
+                s_in[g] = 0;
+            }
         }
-        if (!__syncthreads_or(undec)) break;
-    }
-    if (g == 0) {  // exclusive prefix of the representatives per group
-        const uint32_t c = __popc(s_in[lane]);
-        uint32_t x = c;
+        __syncthreads();
+        for (;;) {
+            uint32_t hit = 0, wait = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
+            for (int w = 0; w < 32; w++) {
+                hit |= a[w] & s_in[w];
+                wait |= a[w] & s_und[w];
+            }
+            const bool out = undec && hit != 0;
+            const bool in = undec && hit == 0 && wait == 0;
+            const uint32_t bi = __ballot_sync(0xffffffffu, in), bo = __ballot_sync(0xffffffffu, out);
+            undec = undec && !in && !out;
+            __syncthreads();  // every thread has read the masks of this round
+            if (lane == 0) {
+                s_in[g] |= bi;
+                s_und[g] &= ~(bi | bo);
+            }
+            if (!__syncthreads_or(undec)) break;
         }
-        s_pre[lane] = x - c;
+        if (g == 0) {  // exclusive prefix of the representatives per group
+            const uint32_t c = __popc(s_in[lane]);
+            uint32_t x = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            s_pre[lane] = x - c;
+        }
+        __syncthreads();
+        const uint32_t mine = s_in[g];
+        if ((mine >> lane) & 1u) {
+            if (p.clusters) p.clusters[found + s_pre[g] + __popc(mine & ((1u << lane) - 1u))] = my_seq;
+            atomicOr(&p.rep[my_seq >> 5], 1u << (my_seq & 31));
+        }
+        found += (int)(s_pre[31] + __popc(s_in[31]));
+        if (lane == 0) s_inprev[g] = mine;
+        __threadfence();
+        __syncthreads();  // also: every thread has read s_in / s_pre before the next block resets them
+        if (t == 0) st_release_gpu(p.resolved, b + 1);
     }
-    __syncthreads();
-    const int c0 = __ldcg(count);
-    const uint32_t mine = s_in[g];
-    if ((mine >> lane) & 1u) {
-        const int v = my_seq;
-        if (clusters) clusters[c0 + s_pre[g] + __popc(mine & ((1u << lane) - 1u))] = v;
-        atomicOr(&rep[v >> 5], 1u << (v & 31));
-    }
-    __syncthreads();  // every thread has read *count
-    if (t == 0) *count = c0 + (int)(s_pre[31] + __popc(s_in[31]));
+    if (t == 0) *p.count = found;
 }
 
-int mis_block() { return MIS_NB; }
-
-// Greedy clustering over the bit matrix (slab layout, n sequences) in the given order; rep
-// (4 * ceil(n / 128) words), alive8 (MIS_NB bytes), adj (MIS_NB * 32 words) and count (1 int)
-// are scratch; rep and count must be zero on entry.
-cudaError_t launch_greedy_clusters(const uint32_t *bits, int n, const int *order, int total,
-                                   uint32_t *rep, uint8_t *alive8, uint32_t *adj, int *clusters,
-                                   int *count, cudaStream_t stream)
+__global__ void __launch_bounds__(1024, 1) k_greedy_clusters(const GreedyParams p)
 {
-    // the 2 x ceil(total / 1024) launches depend on each other one after the other: each is
-    // launched with programmatic stream serialization, so that its launch latency and its
-    // prologue overlap the tail of its predecessor (griddepcontrol.wait inside the kernels)
+    __shared__ int s_ord[2][MIS_NB];
+    __shared__ uint32_t s_hit[MIS_SEQ_PER_CTA][4];
+    __shared__ uint32_t s_masks[4][32];
+    if (blockIdx.x == 0)
+        greedy_resolver(p, s_masks[0], s_masks[1], s_masks[2], s_masks[3]);
+    else
+        greedy_scanner(p, s_ord, s_hit);
+}
+
+// bytes of scratch launch_greedy_clusters needs for n sequences and an order of `total`
+size_t greedy_scratch_bytes(int n, int total)
+{
+    const size_t nslab = ((size_t)n + 127) / 128, nblk = ((size_t)total + MIS_NB - 1) / MIS_NB;
+    auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+    return up(nslab * 16) + up((nblk + 1) * sizeof(int)) + up(2 * MIS_NB) +
+           2 * up((size_t)2 * 32 * MIS_NB * sizeof(uint32_t));
+}
+
+// Greedy clustering over the row-per-sequence bit matrix in the given order (device array of
+// `total` indices); the cluster list goes to `clusters` (may be NULL), its length to *count.
+cudaError_t launch_greedy_clusters(const uint32_t *rows, int n, const int *order, int total,
+                                   void *scratch, int *clusters, int *count, int num_sms,
+                                   cudaStream_t stream)
+{
+    if (total <= 0) return cudaMemsetAsync(count, 0, sizeof(int), stream);
+    const size_t nslab = ((size_t)n + 127) / 128, nblk = ((size_t)total + MIS_NB - 1) / MIS_NB;
+    auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+    uint8_t *q = (uint8_t *)scratch;
+    GreedyParams p{};
+    p.rows = rows;
+    p.pitch_w = brow_pitch_words(n);
+    p.n = n;
+    p.order = order;
+    p.total = total;
+    p.rep = (uint32_t *)q;
+    q += up(nslab * 16);
+    p.scanned = (int *)q;
+    p.resolved = p.scanned + nblk;
+    q += up((nblk + 1) * sizeof(int));
+    const size_t zeroed = (size_t)(q - (uint8_t *)scratch);
+    p.alive8 = q;
+    q += up(2 * MIS_NB);
+    p.adj_own = (uint32_t *)q;
+    q += up((size_t)2 * 32 * MIS_NB * sizeof(uint32_t));
+    p.adj_prev = (uint32_t *)q;
+    p.clusters = clusters;
+    p.count = count;
+    cudaError_t e = cudaMemsetAsync(scratch, 0, zeroed, stream);
+    if (e != cudaSuccess) return e;
+    // every CTA must be resident (the CTAs wait for each other): cooperative launch, at most
+    // one CTA of 1024 threads per SM
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_greedy_clusters, 1024, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1 || num_sms < 2) return cudaErrorLaunchOutOfResources;
+    const int want = (min(total, MIS_NB) + MIS_SEQ_PER_CTA - 1) / MIS_SEQ_PER_CTA;
+    const int nscan = max(1, min(want, num_sms - 1));
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    for (int base = 0; base < total; base += MIS_NB) {
-        const int cnt = min(MIS_NB, total - base);
-        cudaLaunchConfig_t cfg = {};
-        cfg.stream = stream;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        // the very first launch follows copies / memsets / other kernels of the caller: it keeps
-        // the ordinary stream dependency
-        cfg.numAttrs = base == 0 ? 0 : 1;
-        cfg.gridDim = dim3((cnt + 1) / 2);
-        cfg.blockDim = dim3(256);
-        cudaError_t e = cudaLaunchKernelEx(&cfg, k_mis_scan, bits, n, order, base, cnt,
-                                           (const uint32_t *)rep, alive8, adj);
-        if (e != cudaSuccess) return e;
-        cfg.numAttrs = 1;
-        cfg.gridDim = dim3(1);
-        cfg.blockDim = dim3(1024);
-        e = cudaLaunchKernelEx(&cfg, k_mis_resolve, (const uint32_t *)adj, (const uint8_t *)alive8,
-                               order, base, cnt, rep, clusters, count);
-        if (e != cudaSuccess) return e;
-    }
-    return cudaGetLastError();
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cfg.gridDim = dim3(1 + nscan);
+    cfg.blockDim = dim3(1024);
+    return cudaLaunchKernelEx(&cfg, k_greedy_clusters, p);
 }
 
 }  // namespace tcu

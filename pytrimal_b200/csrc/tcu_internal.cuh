@@ -98,7 +98,10 @@ struct Identity2Params {
 // 128 s .. 128 s + 127.  A row-block band of the pair matrix (what one GPU owns) is a
 // contiguous run of slabs, so the bands of several GPUs concatenate without a strided
 // copy.  K1 writes, for the pairs i < j it owns, the bits of row j against the earlier
-// sequences i ("column words"); k_bits_symmetrize then mirrors every 128 x 128 block.
+// sequences i ("column words").  The clustering walk reads whole rows in an arbitrary order,
+// so k_bits_rows then writes the full symmetric matrix with one contiguous row per sequence
+// (brow_*: row r = brow_pitch_words words, bit j of the row = pair (r, j); rows are whole
+// 128-byte lines).
 // ---------------------------------------------------------------------------
 __host__ __device__ inline size_t bits_slab_words(int nk) { return (size_t)nk * 4; }
 __host__ __device__ inline size_t bits_word_index(int nk, int row, int w)
@@ -109,6 +112,11 @@ __host__ __device__ inline size_t bits_total_words(int nk)
 {
     return (size_t)((nk + 127) / 128) * bits_slab_words(nk);
 }
+__host__ __device__ inline size_t brow_pitch_words(int nk)
+{
+    return (size_t)(((nk + 127) / 128 + 7) / 8 * 8) * 4;
+}
+__host__ __device__ inline size_t brow_total_words(int nk) { return (size_t)nk * brow_pitch_words(nk); }
 
 // tiles in super-block rows < sb: each super-block BI pairs with J blocks 2*BI .. nb-1
 __host__ __device__ inline long long tiles_before2(long long sb, long long nb)
@@ -204,15 +212,15 @@ cudaError_t launch_row_hashes(const uint8_t *raw, int nseq, size_t pitch, unsign
                               cudaStream_t stream);
 
 // consumers of the device-resident identity matrix (clusters.cu)
-cudaError_t launch_identity_bits(const float *id, int n, float thr, uint32_t *bits, int row_begin,
+cudaError_t launch_identity_bits(const float *id, int n, float thr, uint32_t *rows, int row_begin,
                                  int row_end, cudaStream_t stream);
-cudaError_t launch_bits_symmetrize(uint32_t *bits, int n, cudaStream_t stream);
+cudaError_t launch_bits_rows(const uint32_t *slab_bits, int n, uint32_t *rows, cudaStream_t stream);
 cudaError_t launch_row_stats(const float *id, int n, bool upper_only, float *row_max,
                              float *row_min, float *row_sum, cudaStream_t stream);
-int mis_block();
-cudaError_t launch_greedy_clusters(const uint32_t *bits, int n, const int *order, int total,
-                                   uint32_t *rep, uint8_t *alive8, uint32_t *adj, int *clusters,
-                                   int *count, cudaStream_t stream);
+size_t greedy_scratch_bytes(int n, int total);
+cudaError_t launch_greedy_clusters(const uint32_t *rows, int n, const int *order, int total,
+                                   void *scratch, int *clusters, int *count, int num_sms,
+                                   cudaStream_t stream);
 
 // ---------------------------------------------------------------------------
 // PTX helpers: mbarrier + 1-D bulk async copy (TMA unit, SASS: UBLKCP)

@@ -7,4 +7,4 @@ m = synthetic_msa(n, L, seed)
 with pb.DeviceAlignment(m) as d:
     for _ in range(2):
         reps = d.representatives(0.8, indet=ord("X"))
-    print(len(reps), d.timings())
+    print(len(reps), d.timings)
