@@ -307,6 +307,16 @@ int tcu_row_hashes(tcu_msa *msa, unsigned long long *hashes);
 int tcu_cluster_order(const int *lengths, int nseq, int *order);
 
 /*
+ * Host only (no device needed).  tcu_representatives never forms the identity ratios: its
+ * identity kernel decides "float(hit) / float(dst) > threshold" (Cleaner.cpp:1435-1440 on
+ * the values of template.h:427-434) for every pair in integers, as
+ *     mode 0: never   mode 1: always   mode 2: hit > (mul * dst) >> shift   (64-bit product)
+ * which is exact for every float threshold and 0 <= hit <= dst < 2^24.  This returns the
+ * rule for a threshold so that it can be checked against the division on any machine.
+ */
+void tcu_threshold_rule(float threshold, int *mode, unsigned *mul, int *shift);
+
+/*
  * Cleaner::calculateRepresentativeSeq (Cleaner.cpp:1398-1466) in one call for an
  * alignment with every row kept: sequence lengths, visiting order, and the greedy
  * clustering at `threshold` (maximumIdent) over the identities of the kept columns

@@ -10,12 +10,13 @@ from ._lib import (LIB_PATH, NoDeviceError, SymbolError, TrimalCudaError, device
 from .alignment import Alignment
 from .matrix import SimilarityMatrix
 from .statistics import (Communicator, DeviceAlignment, cluster_order, gaps_window, get_devices,
-                         set_devices, shard_blocks, shard_range, similarity_window)
+                         set_devices, shard_blocks, shard_range, similarity_window,
+                         threshold_rule)
 
 __version__ = "0.1.0"
 
 __all__ = [
     "Alignment", "SimilarityMatrix", "DeviceAlignment", "Communicator", "cluster_order", "gaps_window",
-    "similarity_window", "shard_blocks", "shard_range", "set_devices", "get_devices",
+    "similarity_window", "threshold_rule", "shard_blocks", "shard_range", "set_devices", "get_devices",
     "device_count", "load", "NoDeviceError", "SymbolError", "TrimalCudaError", "LIB_PATH",
 ]

@@ -108,6 +108,7 @@ PROTOTYPES = {
     "tcu_row_residues": (C.c_int, [_h, _i32p, _i32p]),
     "tcu_row_hashes": (C.c_int, [_h, C.POINTER(C.c_ulonglong)]),
     "tcu_cluster_order": (C.c_int, [_i32p, C.c_int, _i32p]),
+    "tcu_threshold_rule": (None, [C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_uint), C.POINTER(C.c_int)]),
     "tcu_representatives": (C.c_int, [_h, _i32p, C.c_uint8, C.c_float, _i32p, _i32p]),
     "tcu_representatives_all": (C.c_int, [_h, _h, _i32p, C.c_uint8, C.c_float, _i32p, _i32p]),
 }

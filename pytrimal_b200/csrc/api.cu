@@ -612,13 +612,14 @@ static bool peer_prepare(tcu_comm *c, void *buf, std::vector<void *> &peer_base,
         ok = 0;
     }
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    // my handle into my slot, slots all-gathered (tiny), back to the host
+    // my handle into my slot, zeros elsewhere; an integer sum over all ranks is then the
+    // all-gather (one small all-reduce: a fraction of the latency of 2 (world - 1)
+    // point-to-point transfers)
+    memset(c->h_sync, 0, 64 * (size_t)c->world);
     memcpy(c->h_sync + 64 * (size_t)c->rank, &mine, 64);
-    std::vector<size_t> off((size_t)c->world), cnt((size_t)c->world, 64);
-    for (int r = 0; r < c->world; r++) off[r] = 64 * (size_t)r;
-    bool comm_ok = cudaMemcpyAsync(c->d_sync + off[c->rank], c->h_sync + off[c->rank], 64,
-                                   cudaMemcpyHostToDevice, stream) == cudaSuccess &&
-                   comm_allgatherv(c, c->d_sync, off.data(), cnt.data(), stream) == TCU_OK &&
+    bool comm_ok = cudaMemcpyAsync(c->d_sync, c->h_sync, 64 * (size_t)c->world, cudaMemcpyHostToDevice,
+                                   stream) == cudaSuccess &&
+                   comm_allreduce_i32(c, (int *)c->d_sync, 16 * (size_t)c->world, stream) == TCU_OK &&
                    cudaMemcpyAsync(c->h_sync, c->d_sync, 64 * (size_t)c->world, cudaMemcpyDeviceToHost,
                                    stream) == cudaSuccess &&
                    cudaStreamSynchronize(stream) == cudaSuccess;
@@ -745,7 +746,8 @@ static bool is_pinned_host(const void *p)
 // Page-locked source: ONE linear DMA of the whole strided block into scratch (a 2-D copy
 // would issue a descriptor per 1000-byte row), then a device kernel lays the rows out at
 // the device pitch and zero-fills the padding.
-static int upload_strided_pinned(tcu_msa *m, const uint8_t *data, size_t stride, int r0, int r1)
+static int upload_strided_pinned(tcu_msa *m, const uint8_t *data, size_t stride, int r0, int r1,
+                                 const std::vector<uint8_t *> *peer_raw = nullptr)
 {
     CK(cudaSetDevice(m->device));
     m->timings = tcu_timings{};
@@ -756,8 +758,9 @@ static int upload_strided_pinned(tcu_msa *m, const uint8_t *data, size_t stride,
     CK(cudaEventRecord(m->ev[0], m->stream));
     CK(cudaMemcpyAsync(m->d_scratch, data + (size_t)r0 * stride, bytes, cudaMemcpyHostToDevice,
                        m->stream));
-    CK(launch_repitch_rows((const uint8_t *)m->d_scratch, stride, r1 - r0, m->ncol,
-                           m->d_raw + (size_t)r0 * m->pitch, m->pitch, m->stream));
+    CK(launch_repitch_rows((const uint8_t *)m->d_scratch, stride, r1 - r0, m->ncol, m->d_raw, m->pitch,
+                           (size_t)r0 * m->pitch, peer_raw ? peer_raw->data() : nullptr,
+                           peer_raw ? (int)peer_raw->size() : 0, m->stream));
     CK(cudaEventRecord(m->ev[1], m->stream));
     CK(cudaStreamSynchronize(m->stream));
     m->timings.h2d_ms = ev_ms(m->ev[0], m->ev[1]);
@@ -1137,6 +1140,33 @@ extern "C" int tcu_msa_create_all(tcu_comm *comm, const uint8_t *data, int nseq,
     if (rc != TCU_OK) return rc;
     int r0 = 0, r1 = 0;
     tcu_shard_range(nseq, 1, comm->rank, comm->world, &r0, &r1);
+    // A page-locked buffer goes up in one copy and a layout kernel; with peer memory that
+    // kernel writes the rank's rows into every rank's matrix (NVLink) and a one-word
+    // all-reduce is all that is left of the exchange.
+    std::vector<void *> peer_base;
+    if (h.pinned && nseq > 0 && ncol > 0 && comm->world > 1 && comm->world - 1 <= ID2_MAX_PEERS &&
+        peer_prepare(comm, m->d_raw, peer_base, m->stream)) {
+        std::vector<uint8_t *> others;
+        for (int q = 1; q < comm->world; q++)
+            others.push_back((uint8_t *)peer_base[(size_t)((comm->rank + q) % comm->world)]);
+        rc = upload_strided_pinned(m, h.data, h.stride, r0, r1, &others);
+        if (rc == TCU_OK) {
+            cudaEventRecord(m->ev[4], m->stream);
+            rc = comm_allreduce_i32(comm, (int *)(comm->d_sync + 64 * 64 + 64), 1, m->stream);
+            cudaEventRecord(m->ev[5], m->stream);
+            if (rc == TCU_OK && cudaStreamSynchronize(m->stream) != cudaSuccess)
+                rc = cuda_fail(cudaGetLastError(), "row exchange between ranks");
+            if (rc == TCU_OK) m->timings.comm_ms = ev_ms(m->ev[4], m->ev[5]);
+        }
+        if (rc != TCU_OK) {
+            const std::string keep = g_last_error;
+            tcu_msa_destroy(m);
+            g_last_error = keep;
+            return rc;
+        }
+        *out = m;
+        return TCU_OK;
+    }
     rc = upload_range(m, h, r0, r1);
     if (rc == TCU_OK && nseq > 0) {
         std::vector<size_t> off(comm->world), cnt(comm->world);
@@ -1475,7 +1505,9 @@ static int identity_launch(tcu_msa *m, int sb_begin, int sb_end, float *d_out, i
     p.hit_out = d_hit;
     p.dst_out = d_dst;
     p.bits_out = d_bits;
-    p.thr = thr;
+    p.thr = threshold_rule(thr);
+    if (d_bits && (size_t)((m->nk + 127) / 128) * (size_t)m->nk >= 0xFFFFFFFFull)
+        return fail(TCU_ERR_INVALID, "%d sequences: the threshold bit matrix is limited to 2^32 entries", m->nk);
     if (bits_peers) {
         if (bits_peers->size() > (size_t)ID2_MAX_PEERS) return fail(TCU_ERR_INVALID, "too many peer matrices");
         for (uint32_t *q : *bits_peers) p.bits_peer[p.n_bits_peer++] = q;
@@ -2118,6 +2150,14 @@ extern "C" int tcu_cluster_order(const int *lengths, int nseq, int *order)
     }
     for (int i = 0; i < nseq; i++) order[i] = v[nseq - 1 - i].idx;
     return TCU_OK;
+}
+
+extern "C" void tcu_threshold_rule(float threshold, int *mode, unsigned *mul, int *shift)
+{
+    const ThresholdRule r = threshold_rule(threshold);
+    if (mode) *mode = r.mode;
+    if (mul) *mul = r.mul;
+    if (shift) *shift = r.shift;
 }
 
 // Cleaner::calculateRepresentativeSeq in one call.  The walk only ever asks "identity >

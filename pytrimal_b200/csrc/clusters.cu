@@ -105,57 +105,89 @@ cudaError_t launch_identity_bits(const float *id, int n, float thr, uint32_t *bi
 // clustering walk reads, in an order that has nothing to do with the sequence index): output
 // block (R, C) of 128 x 128 bits is slab C's rows of R as they are when R > C, the transpose
 // of slab R's rows of C when R < C, and U | U^T on the diagonal.  One CTA of 128 threads per
-// row block and PAIR of column blocks (a thread's two 16-byte stores fill one 32-byte sector
-// of its row); a transpose is four 32 x 32 butterflies across the warp and a pass through
-// shared memory.  HBM-bound: reads and writes n^2 / 8 bytes each.
+// row block and EIGHT column blocks: all 16-byte loads of a thread are issued first (2 KB
+// contiguous per warp and block), a transpose is four 32 x 32 butterflies across the warp
+// written straight into the shared-memory tile, and the tile leaves as whole 128-byte lines
+// of the rows.  HBM-bound: reads and writes n^2 / 8 bytes each.
 // ---------------------------------------------------------------------------
+constexpr int BR_COLS = 8;               // column blocks per CTA
+constexpr int BR_STRIDE = BR_COLS + 1;   // uint4 per tile row (+1: spreads the banks)
+
 __global__ void __launch_bounds__(128) k_bits_rows(const uint32_t *__restrict__ slab_bits, int n,
                                                    uint32_t *__restrict__ rows)
 {
-    __shared__ uint4 s_out[128];
-    const int R = blockIdx.y;
+    __shared__ uint4 s_tile[128 * BR_STRIDE];
+    const int R = blockIdx.y, C0 = blockIdx.x * BR_COLS;
     const int lane = threadIdx.x & 31, u = threadIdx.x >> 5;
     const int nslab = (n + 127) >> 7;
     const uint4 *slabs = reinterpret_cast<const uint4 *>(slab_bits);
     const size_t pitch4 = brow_pitch_words(n) / 4;
-    const int r = R * 128 + threadIdx.x;  // the row this thread stores
+    const int r = R * 128 + threadIdx.x;  // this thread's row of R
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-    uint32_t *s_words = reinterpret_cast<uint32_t *>(s_out);
-#pragma unroll 1
-    for (int c = 0; c < 2; c++) {
-        const int C = 2 * blockIdx.x + c;
-        if (C >= nslab) break;  // uniform
-        uint4 v = zero;
-        if (C <= R && r < n) v = slabs[(size_t)C * n + r];  // bits (r, i) for i in C, i < r
-        if (C >= R) {
-            // rows of C against the sequences of R, transposed
-            const int x = C * 128 + threadIdx.x;
-            const uint4 own = C == R ? v : (x < n ? slabs[(size_t)R * n + x] : zero);
-            const uint32_t w4[4] = {own.x, own.y, own.z, own.w};
+    uint32_t *s_words = reinterpret_cast<uint32_t *>(s_tile);
+
+    // one load per column block: C <= R the row's own entry (bits against earlier sequences),
+    // C > R the entry of row 128 C + thread against the sequences of R (to be transposed)
+    uint4 v[BR_COLS];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                // 32 x 32 bit transpose across the warp (lane = row): five butterfly stages,
-                // each swapping the off-diagonal j x j blocks with the lane j away; afterwards
-                // lane k holds sequence 128 R + 32 q + k against rows 128 C + 32 u ..
-                uint32_t xw = w4[q];
-                uint32_t low = 0x0000FFFFu;  // columns c with (c & j) == 0
-#pragma unroll
-                for (int j = 16; j >= 1; j >>= 1) {
-                    const uint32_t y = __shfl_xor_sync(0xffffffffu, xw, j);
-                    xw = (lane & j) ? ((xw & ~low) | ((y & ~low) >> j)) : ((xw & low) | ((y & low) << j));
-                    low ^= low << (j >> 1);  // 0x0000FFFF -> 0x00FF00FF -> ... -> 0x55555555
-                }
-                s_words[(32 * q + lane) * 4 + u] = xw;
+    for (int c = 0; c < BR_COLS; c++) {
+        const int C = C0 + c;
+        v[c] = zero;
+        if (C < nslab) {
+            if (C <= R) {
+                if (r < n) v[c] = slabs[(size_t)C * n + r];
+            } else {
+                const int x = C * 128 + threadIdx.x;
+                if (x < n) v[c] = slabs[(size_t)R * n + x];
             }
-            __syncthreads();
-            const uint4 t4 = s_out[threadIdx.x];
-            v.x |= t4.x;
-            v.y |= t4.y;
-            v.z |= t4.z;
-            v.w |= t4.w;
-            __syncthreads();  // s_out is rewritten by the second column block
         }
-        if (r < n) reinterpret_cast<uint4 *>(rows)[(size_t)r * pitch4 + C] = v;
+    }
+    // transposes (C >= R) into the tile
+#pragma unroll
+    for (int c = 0; c < BR_COLS; c++) {
+        const int C = C0 + c;
+        if (C < R || C >= nslab) continue;  // uniform
+        const uint32_t w4[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            // 32 x 32 bit transpose across the warp (lane = row): five butterfly stages, each
+            // swapping the off-diagonal j x j blocks with the lane j away; afterwards lane k
+            // holds sequence 128 R + 32 q + k against rows 128 C + 32 u ..
+            uint32_t xw = w4[q];
+            uint32_t low = 0x0000FFFFu;  // columns with (column & j) == 0
+#pragma unroll
+            for (int j = 16; j >= 1; j >>= 1) {
+                const uint32_t y = __shfl_xor_sync(0xffffffffu, xw, j);
+                xw = (lane & j) ? ((xw & ~low) | ((y & ~low) >> j)) : ((xw & low) | ((y & low) << j));
+                low ^= low << (j >> 1);  // 0x0000FFFF -> 0x00FF00FF -> ... -> 0x55555555
+            }
+            s_words[((32 * q + lane) * BR_STRIDE + c) * 4 + u] = xw;
+        }
+    }
+    __syncthreads();
+    // the rows' own entries (C <= R); on the diagonal they join the transposed half
+#pragma unroll
+    for (int c = 0; c < BR_COLS; c++) {
+        const int C = C0 + c;
+        if (C > R && C < nslab) continue;  // uniform
+        uint4 o = v[c];
+        if (C == R) {
+            const uint4 t4 = s_tile[threadIdx.x * BR_STRIDE + c];
+            o.x |= t4.x;
+            o.y |= t4.y;
+            o.z |= t4.z;
+            o.w |= t4.w;
+        }
+        s_tile[threadIdx.x * BR_STRIDE + c] = o;
+    }
+    __syncthreads();
+    // 128 rows x 128 bytes: eight threads per row
+    uint4 *out = reinterpret_cast<uint4 *>(rows);
+#pragma unroll
+    for (int pass = 0; pass < 8; pass++) {
+        const int row = pass * 16 + (threadIdx.x >> 3), piece = threadIdx.x & 7;
+        const int rr = R * 128 + row;
+        if (rr < n) out[(size_t)rr * pitch4 + C0 + piece] = s_tile[row * BR_STRIDE + piece];
     }
 }
 
@@ -163,7 +195,7 @@ cudaError_t launch_bits_rows(const uint32_t *slab_bits, int n, uint32_t *rows, c
 {
     if (n <= 0) return cudaSuccess;
     const int nsb = (n + 127) / 128;
-    dim3 grid((nsb + 1) / 2, nsb);
+    dim3 grid((nsb + BR_COLS - 1) / BR_COLS, nsb);
     k_bits_rows<<<grid, 128, 0, stream>>>(slab_bits, n, rows);
     return cudaGetLastError();
 }

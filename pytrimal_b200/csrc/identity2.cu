@@ -313,13 +313,19 @@ __global__ void __launch_bounds__(ID2_THREADS, NP <= 5 ? 2 : 1) k_identity2(cons
         const int rowB0 = 32 * wj + lj;               // + 8*b
         const unsigned long long n = (unsigned long long)p.nk;
 
-        // threshold mode: the column entry this thread stores one tile late (see the epilogue)
-        bool have_prev = false;
-        size_t prev_at = 0;
-        int prev_buf = 0;
-        auto flush_bits = [&](size_t at, int kb) {
-            const uint32_t *w = s_xch + (4 * wj) * (32 * ID2_XS) + lane * ID2_XS + 32 + kb;
+        // threshold mode: the 64 column entries of the tile whose words sit in buffer kb, stored
+        // one tile late (see the epilogue): every warp takes eight of them (equal work for
+        // all warps keeps them on the same ring stage), 128 contiguous bytes per warp.  The
+        // entry's position was parked next to the words, so that nothing stays live across
+        // the counting loop.
+        auto flush_bits = [&](int kb) {
+            if (lane >= 8) return;
+            const int col = 8 * warp + lane;  // column of the tile: patch row col % 32 of the warps (.., col / 32)
+            const uint32_t *w = s_xch + (4 * (col >> 5)) * (32 * ID2_XS) + (col & 31) * ID2_XS + 32 + kb;
+            const uint32_t at4 = w[2];  // 16-byte entry index, ~0 for a column beyond nk
+            if (at4 == 0xFFFFFFFFu) return;
             const uint4 v = make_uint4(w[0], w[32 * ID2_XS], w[2 * 32 * ID2_XS], w[3 * 32 * ID2_XS]);
+            const size_t at = (size_t)at4 * 4;
             *reinterpret_cast<uint4 *>(p.bits_out + at) = v;
             for (int q = 0; q < p.n_bits_peer; q++) *reinterpret_cast<uint4 *>(p.bits_peer[q] + at) = v;
         };
@@ -414,6 +420,7 @@ __global__ void __launch_bounds__(ID2_THREADS, NP <= 5 ? 2 : 1) k_identity2(cons
             __syncwarp();
 
             if (p.bits_out != nullptr) {
+                if (k > 0) flush_bits((int)((k - 1) & 1));  // the previous tile's entries
                 // threshold mode (Cleaner.cpp:1435-1440: a pair joins two sequences iff
                 // identity > threshold): the same division, but only its comparison with the
                 // threshold leaves the SM.  ballot(a, b) holds bit (i = li + 4a, j = lj + 8b)
@@ -435,8 +442,11 @@ __global__ void __launch_bounds__(ID2_THREADS, NP <= 5 ? 2 : 1) k_identity2(cons
                                                   : (b < 2 ? (int)(hit[a][b] & 0xFFFFu)
                                                            : (int)(hit[a][b - 2] >> 16));
                             const int d = p.total_bits - (int)patch[(li + 4 * a) * ID2_XS + lj + 8 * b];
-                            const float v = d == 0 ? 0.0f : __fdiv_rn((float)h, (float)d);
-                            const bool bit = i < p.nk && j < p.nk && j > i && v > p.thr;
+                            // fl(h / d) > thr, exactly, without dividing (ThresholdRule)
+                            const uint32_t q =
+                                (uint32_t)(((unsigned long long)p.thr.mul * (uint32_t)d) >> p.thr.shift);
+                            const bool over = p.thr.mode == 2 ? (uint32_t)h > q : p.thr.mode == 1;
+                            const bool bit = i < p.nk && j < p.nk && j > i && over;
                             const uint32_t w = __ballot_sync(0xffffffffu, bit);
                             if ((lane >> 3) == b) mine = w;
                         }
@@ -446,14 +456,13 @@ __global__ void __launch_bounds__(ID2_THREADS, NP <= 5 ? 2 : 1) k_identity2(cons
                 // The four words of a column (wi = 0..3) are 16 contiguous bytes of the slab
                 // layout, held by four warps.  Each warp parks its word in the padding of its
                 // patch (two buffers, by tile parity); one tile later -- the barrier above
-                // has then seen every warp finish this epilogue -- the warps with wi == 0
-                // store whole 16-byte column entries, 1 KB contiguous per tile: to the local
-                // matrix and, in a multi-GPU run, straight into every peer's over NVLink.
-                if (wi == 0 && have_prev) flush_bits(prev_at, prev_buf);
+                // has then seen every warp finish this epilogue -- whole 16-byte column entries
+                // are stored, 1 KB contiguous per tile: to the local matrix and, in a multi-GPU
+                // run, straight into every peer's over NVLink.
                 patch[lane * ID2_XS + 32 + (int)(k & 1)] = colword;
-                have_prev = j0 + lane < p.nk;
-                prev_at = bits_word_index(p.nk, j0 + lane, 4 * BI);
-                prev_buf = (int)(k & 1);
+                if (wi == 0)  // (nslab * nk entries: below 2^32 up to 740 000 sequences)
+                    patch[lane * ID2_XS + 34 + (int)(k & 1)] =
+                        j0 + lane < p.nk ? (uint32_t)((size_t)BI * p.nk + (size_t)(j0 + lane)) : 0xFFFFFFFFu;
                 __syncwarp();  // the patch is rewritten by the next tile
                 continue;
             }
@@ -484,7 +493,7 @@ __global__ void __launch_bounds__(ID2_THREADS, NP <= 5 ? 2 : 1) k_identity2(cons
         }
         if (p.bits_out != nullptr) {  // the last tile's column entries
             asm volatile("bar.sync 1, %0;" ::"n"(ID2_MATH_THREADS) : "memory");
-            if (wi == 0 && have_prev) flush_bits(prev_at, prev_buf);
+            if (k > 0) flush_bits((int)((k - 1) & 1));
         }
     }
 

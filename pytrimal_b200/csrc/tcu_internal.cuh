@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "trimal_cuda.h"
 
@@ -63,6 +64,33 @@ __host__ __device__ constexpr int tile2_bytes(int np) { return tile2_words(np) *
 __host__ __device__ constexpr int role_words(int np) { return KC2 * RB * (1 + rest_words(np)); }
 __host__ __device__ constexpr int role_bytes(int np) { return role_words(np) * 4; }
 
+// "fl(h / d) > thr" without the division (identity2.cu, threshold mode).  The correctly
+// rounded quotient exceeds thr exactly when the exact one exceeds the midpoint between thr
+// and the next float above it (a tie cannot occur: the midpoint is an odd multiple of a power
+// of two below 2^-24, and d < 2^24).  With thr = m 2^e that midpoint is (2m + 1) 2^(e-1), so
+//     fl(h / d) > thr   <=>   h 2^k > (2m + 1) d   <=>   h > ((2m + 1) d) >> k,   k = 1 - e >= 25
+// for 0 <= thr < 1; thr < 0 holds for every pair (also d = 0: the reference's 0 / 0 is 0),
+// thr >= 1 or NaN for none.
+struct ThresholdRule {
+    int mode;       // 0: never, 1: always, 2: h > (mul * d) >> shift
+    uint32_t mul;   // 2m + 1 < 2^25
+    int shift;      // k, clamped to 63 (mul * d < 2^49)
+};
+inline ThresholdRule threshold_rule(float thr)
+{
+    uint32_t b;
+    memcpy(&b, &thr, sizeof b);
+    const uint32_t mag = b & 0x7FFFFFFFu;
+    if (mag > 0x7F800000u) return ThresholdRule{0, 0, 0};            // NaN
+    if ((b >> 31) && mag != 0) return ThresholdRule{1, 0, 0};         // negative
+    if (mag >= 0x3F800000u) return ThresholdRule{0, 0, 0};            // >= 1, +inf
+    const uint32_t E = mag >> 23, F = mag & 0x7FFFFFu;
+    const uint32_t m = E ? (F | 0x800000u) : F;
+    const int e = E ? (int)E - 150 : -149;
+    const int k = 1 - e;
+    return ThresholdRule{2, 2 * m + 1, k > 63 ? 63 : k};
+}
+
 constexpr int ID2_MAX_PEERS = 15;  // other devices whose bit matrix K1 may write
 
 struct Identity2Params {
@@ -83,7 +111,7 @@ struct Identity2Params {
     // threshold mode (bits_out != nullptr): instead of the ratios, identity > thr as one bit per
     // pair in the slab layout below; out / hit_out / dst_out are not touched
     uint32_t *bits_out;
-    float thr;
+    ThresholdRule thr;
     // the same words stored into the bit matrices of other devices as well (peer memory over
     // NVLink: CUDA IPC mappings or peer access inside one process) -- the band exchange of a
     // multi-GPU clustering happens inside the epilogue, tile by tile, under the computation
@@ -171,7 +199,8 @@ __host__ __device__ inline void tile_to_blocks2(long long t, int nb, int sb_begi
 cudaError_t launch_byte_presence(const uint8_t *raw, int nseq, int ncol, size_t pitch,
                                  unsigned int *present256, int num_sms, cudaStream_t stream);
 cudaError_t launch_repitch_rows(const uint8_t *src, size_t stride, int nseq, int ncol, uint8_t *dst,
-                                size_t pitch, cudaStream_t stream);
+                                size_t pitch, size_t dst_offset, uint8_t *const *peer_dst,
+                                int n_peers, cudaStream_t stream);
 cudaError_t launch_byte_histogram(const uint8_t *raw, int nseq, int ncol, size_t pitch,
                                   unsigned long long *hist256, int num_sms, cudaStream_t stream);
 cudaError_t launch_pack_planes(const uint8_t *raw, size_t pitch, int ncol, const int *kept_rows,

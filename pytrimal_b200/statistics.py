@@ -422,6 +422,14 @@ def cluster_order(lengths):
     return out
 
 
+def threshold_rule(threshold):
+    """(mode, mul, shift): the integer form of ``float32(hit) / float32(dst) > threshold`` the
+    identity kernel uses in threshold mode (tcu_threshold_rule); host only."""
+    mode, mul, shift = C.c_int(), C.c_uint(), C.c_int()
+    _lib.load().tcu_threshold_rule(float(np.float32(threshold)), C.byref(mode), C.byref(mul), C.byref(shift))
+    return mode.value, mul.value, shift.value
+
+
 def gaps_window(gaps_in_column, half_window):
     """``Gaps::applyWindow`` (Gaps.cpp:93-153): mirrored integer mean with
     ``utils::roundInt`` (utils.cpp:68-72).  Host side, O(L*w)."""
