@@ -1949,13 +1949,30 @@ static int clusters_impl(tcu_msa *m, const float *id0, const int *order, int cou
                               m->stream));
     CK(cudaEventRecord(m->ev[3], m->stream));
     int found = 0;
-    CK(cudaMemcpyAsync(&found, d_count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
-    CK(cudaStreamSynchronize(m->stream));
-    if (clusters && found > 0)
-        CK(cudaMemcpyAsync(clusters, d_clusters, (size_t)found * 4, cudaMemcpyDeviceToHost,
-                           m->stream));
-    CK(cudaEventRecord(m->ev[4], m->stream));
-    CK(cudaStreamSynchronize(m->stream));
+    void *stage = (size_t)(count + 1) * sizeof(int) <= STAGE_BYTES ? stage_acquire() : nullptr;
+    if (stage) {
+        // one round trip: the counter and the whole candidate list into page-locked memory
+        int *h = (int *)stage;
+        cudaError_t e = cudaMemcpyAsync(h, d_count, sizeof(int), cudaMemcpyDeviceToHost, m->stream);
+        if (e == cudaSuccess && clusters)
+            e = cudaMemcpyAsync(h + 1, d_clusters, (size_t)count * 4, cudaMemcpyDeviceToHost, m->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(m->ev[4], m->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+        if (e == cudaSuccess) {
+            found = h[0];
+            if (clusters && found > 0) memcpy(clusters, h + 1, (size_t)found * 4);
+        }
+        stage_release(stage);
+        if (e != cudaSuccess) return cuda_fail(e, "cluster list download");
+    } else {
+        CK(cudaMemcpyAsync(&found, d_count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+        CK(cudaStreamSynchronize(m->stream));
+        if (clusters && found > 0)
+            CK(cudaMemcpyAsync(clusters, d_clusters, (size_t)found * 4, cudaMemcpyDeviceToHost,
+                               m->stream));
+        CK(cudaEventRecord(m->ev[4], m->stream));
+        CK(cudaStreamSynchronize(m->stream));
+    }
     *n_clusters = found;
     m->timings.h2d_ms = ev_ms(m->ev[0], m->ev[1]);
     m->timings.pack_ms = ev_ms(m->ev[1], m->ev[2]);    // threshold -> bit matrix (K5)
@@ -2152,6 +2169,37 @@ extern "C" int tcu_cluster_order(const int *lengths, int nseq, int *order)
     return TCU_OK;
 }
 
+// The sequence lengths and (if not known yet) the set of byte values that occur, in ONE
+// round trip to the device: both are needed before the identity kernel can be set up.
+static int lengths_and_presence(tcu_msa *m, int *lengths)
+{
+    CK(cudaSetDevice(m->device));
+    m->timings = tcu_timings{};
+    const int n = m->nseq;
+    const size_t len_b = ((size_t)n * sizeof(int) + 255) / 256 * 256;
+    int rc = ensure_dev(m->device, &m->d_scratch, &m->scratch_cap, len_b + 256 * sizeof(unsigned int), m);
+    if (rc != TCU_OK) return rc;
+    unsigned int *d_present = (unsigned int *)((uint8_t *)m->d_scratch + len_b);
+    const bool presence = !m->have_present;
+    CK(cudaEventRecord(m->ev[1], m->stream));
+    if (presence) {
+        CK(cudaMemsetAsync(d_present, 0, 256 * sizeof(unsigned int), m->stream));
+        CK(launch_byte_presence(m->d_raw, m->nseq, m->ncol, m->pitch, d_present, m->num_sms, m->stream));
+    }
+    CK(launch_row_lengths(m->d_raw, n, m->ncol, m->pitch, (int *)m->d_scratch, m->stream));
+    CK(cudaEventRecord(m->ev[2], m->stream));
+    if (presence)
+        CK(cudaMemcpyAsync(m->present, d_present, sizeof m->present, cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaMemcpyAsync(lengths, m->d_scratch, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaEventRecord(m->ev[3], m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    if (presence) m->have_present = true;
+    m->timings.kernel_ms = ev_ms(m->ev[1], m->ev[2]);
+    m->timings.d2h_ms = ev_ms(m->ev[2], m->ev[3]);
+    m->timings.kernel_launches = presence ? 2 : 1;
+    return TCU_OK;
+}
+
 extern "C" void tcu_threshold_rule(float threshold, int *mode, unsigned *mul, int *shift)
 {
     const ThresholdRule r = threshold_rule(threshold);
@@ -2189,8 +2237,27 @@ static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res,
     };
     static const bool trace = getenv("TCU_TRACE") != nullptr;
     const double t_begin = now_ms();
-    std::vector<int> lengths((size_t)n), order((size_t)n);
-    rc = tcu_sequence_lengths(m, lengths.data());
+    // lengths and visiting order live in page-locked memory when they fit a staging buffer
+    // (copies to and from it are asynchronous and run at PCIe speed)
+    struct StageHold {
+        void *p = nullptr;
+        ~StageHold() { stage_release(p); }
+    } hold;
+    std::vector<int> pageable;
+    int *lengths, *order;
+    if ((size_t)n * 2 * sizeof(int) <= STAGE_BYTES && (hold.p = stage_acquire()) != nullptr) {
+        lengths = (int *)hold.p;
+        order = lengths + n;
+    } else {
+        try {
+            pageable.resize((size_t)n * 2);
+        } catch (...) {
+            return fail(TCU_ERR_OOM, "host allocation failed");
+        }
+        lengths = pageable.data();
+        order = lengths + n;
+    }
+    rc = lengths_and_presence(m, lengths);
     if (rc != TCU_OK) return rc;
     add(m->timings);
     const double t_lengths = now_ms();
@@ -2199,7 +2266,7 @@ static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res,
     double sort_ms = 0;
     auto sort = [&]() {
         const double t0 = now_ms();
-        sort_rc = tcu_cluster_order(lengths.data(), n, order.data());
+        sort_rc = tcu_cluster_order(lengths, n, order);
         if (sort_rc != TCU_OK) sort_err = g_last_error;  // thread-local: carry it over
         sort_ms = now_ms() - t0;
     };
@@ -2342,7 +2409,7 @@ static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res,
         if (rc != TCU_OK) return rc;
         add(m->timings);
         if (sort_rc != TCU_OK) return fail(sort_rc, "%s", sort_err.c_str());
-        rc = clusters_impl(m, m->d_ident, order.data(), n, threshold, clusters, n_clusters);
+        rc = clusters_impl(m, m->d_ident, order, n, threshold, clusters, n_clusters);
         if (rc != TCU_OK) return rc;
         add(m->timings);
         m->timings = total;
@@ -2355,7 +2422,7 @@ static int representatives_impl(tcu_msa *m, tcu_comm *comm, const int *save_res,
     if (rc != TCU_OK) return rc;
     add(m->timings);
     if (sort_rc != TCU_OK) return fail(sort_rc, "%s", sort_err.c_str());
-    rc = clusters_impl(m, nullptr, order.data(), n, threshold, clusters, n_clusters);
+    rc = clusters_impl(m, nullptr, order, n, threshold, clusters, n_clusters);
     if (rc != TCU_OK) return rc;
     add(m->timings);
     if (trace)
