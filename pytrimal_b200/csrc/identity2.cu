@@ -483,7 +483,10 @@ __global__ void __launch_bounds__(ID2_THREADS, NP <= 5 ? 2 : 1) k_identity2(cons
                     const int h = !PACKED ? (int)hit[a][b]
                                           : (b < 2 ? (int)(hit[a][b] & 0xFFFFu) : (int)(hit[a][b - 2] >> 16));
                     const int d = p.total_bits - (int)patch[(li + 4 * a) * ID2_XS + lj + 8 * b];
-                    const float v = d == 0 ? 0.0f : __fdiv_rn((float)h, (float)d);
+                    // PACKED: fewer than 65 536 columns, the short exact division applies
+                    const float v = d == 0 ? 0.0f
+                                           : (PACKED ? div_small_counts((float)h, (float)d)
+                                                     : __fdiv_rn((float)h, (float)d));
                     p.out[pos - p.out_base] = v;
                     if (p.hit_out) p.hit_out[pos] = h;
                     if (p.dst_out) p.dst_out[pos] = d;

@@ -255,6 +255,24 @@ cudaError_t launch_greedy_clusters(const uint32_t *rows, int n, const int *order
 // PTX helpers: mbarrier + 1-D bulk async copy (TMA unit, SASS: UBLKCP)
 // ---------------------------------------------------------------------------
 #ifdef __CUDACC__
+// fl(h / d), correctly rounded, for integers 0 <= h <= d and 0 < d < 2^16 (the counts of an
+// alignment of fewer than 65 536 columns): reciprocal estimate, quotient estimate, its EXACT
+// residual (h - d q is a multiple of ulp(q) below 2^17 of them, so the fused multiply-add
+// returns it without rounding) and one correction.  q + r / d is the true quotient; using
+// r * rc for r / d is off by less than 2^-22 ulp(q), while a quotient of such integers that
+// is not a float is at least ulp(q) / 2^17 away from any rounding boundary -- so the single
+// rounding of the last operation is the rounding of the exact quotient.  4 instructions
+// against the 12 + range check + slow-path call of the general division.  Checked against
+// __fdiv_rn for every such pair: tools/fdiv_check.cu, profiles/r03_fdiv_check.txt.
+__device__ __forceinline__ float div_small_counts(float h, float d)
+{
+    float rc;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(d));
+    const float q = __fmul_rn(h, rc);
+    const float r = __fmaf_rn(-d, q, h);
+    return __fmaf_rn(r, rc, q);
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
