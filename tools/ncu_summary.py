@@ -1,7 +1,7 @@
-"""Print the metrics we track from an `ncu --page raw --csv` export (first kernel row)."""
+"""Print the metrics we track from an `ncu --page raw --csv` export (every kernel row)."""
 import csv, sys
 rows = list(csv.reader(open(sys.argv[1])))
-hdr, units, vals = rows[0], rows[1], rows[2]
+hdr, units = rows[0], rows[1]
 want = ['Kernel Name', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
         'launch__shared_mem_per_block_dynamic', 'gpu__time_duration.sum', 'sm__cycles_active.avg',
         'dram__bytes_read.sum', 'dram__bytes_write.sum', 'lts__t_sector_hit_rate.pct',
@@ -18,6 +18,10 @@ want = ['Kernel Name', 'launch__grid_size', 'launch__block_size', 'launch__regis
         'sm__warps_active.avg.pct_of_peak_sustained_active',
         'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'smsp__inst_executed.sum', 'smsp__warps_eligible.avg.per_cycle_active']
-for i, h in enumerate(hdr):
-    if h in want or h.startswith('smsp__average_warps_issue_stalled') and h.endswith('per_issue_active.ratio'):
-        print(f"{h:92s} {units[i]:16s} {vals[i]}")
+for vals in rows[2:]:
+    if len(vals) != len(hdr):
+        continue
+    print("=" * 100)
+    for i, h in enumerate(hdr):
+        if h in want or h.startswith('smsp__average_warps_issue_stalled') and h.endswith('per_issue_active.ratio'):
+            print(f"{h:92s} {units[i]:16s} {vals[i]}")
