@@ -352,6 +352,7 @@ struct GreedyParams {
     uint32_t *adj_prev;  // [2][32][MIS_NB]
     int *clusters;
     int *count;
+    int rep_in_smem;  // the resolver keeps `rep` in (dynamic) shared memory and stores whole words
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int *p)
@@ -363,6 +364,10 @@ __device__ __forceinline__ int ld_acquire_gpu(const int *p)
 __device__ __forceinline__ void st_release_gpu(int *p, int v)
 {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_release_gpu(int *p, int v)
+{
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void group_bar(int id)  // the 128 threads of one sequence
 {
@@ -394,10 +399,21 @@ __device__ void greedy_scanner(const GreedyParams &p, int (*s_ord)[MIS_NB], uint
             const uint32_t *row = p.rows + (size_t)s * p.pitch_w;
             const uint4 *row4 = reinterpret_cast<const uint4 *>(row);
             uint32_t acc = 0;
-            for (int S = lane + 32 * part; S < nslab; S += 128) {
-                const uint4 a = row4[S];             // immutable: may stay in L1 for the gathers
-                const uint4 r = __ldcg(rep4 + S);    // written by the resolver: L2
-                acc |= (a.x & r.x) | (a.y & r.y) | (a.z & r.z) | (a.w & r.w);
+            for (int S0 = lane + 32 * part; S0 < nslab; S0 += 4 * 128) {
+                // eight loads in flight per lane (the row comes from HBM: one latency, not four)
+                uint4 a[4], r[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int S = S0 + 128 * k;
+                    a[k] = r[k] = make_uint4(0u, 0u, 0u, 0u);
+                    if (S < nslab) {
+                        a[k] = row4[S];           // immutable: may stay in L1 for the gathers
+                        r[k] = __ldcg(rep4 + S);  // written by the resolver: L2
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    acc |= (a[k].x & r[k].x) | (a[k].y & r[k].y) | (a[k].z & r[k].z) | (a[k].w & r[k].w);
             }
             const uint32_t any = __any_sync(0xffffffffu, acc != 0) ? 1u : 0u;
             if (lane == 0) s_hit[sub][part] = any;
@@ -442,16 +458,21 @@ __device__ void greedy_scanner(const GreedyParams &p, int (*s_ord)[MIS_NB], uint
             }
             group_bar(1 + sub);  // s_hit is rewritten by the group's next sequence
         }
-        __threadfence();
         __syncthreads();
-        if (tid == 0) atomicAdd(p.scanned + b, 1);
+        // release is cumulative: it publishes what the CTA wrote before the barrier
+        if (tid == 0) red_add_release_gpu(p.scanned + b, 1);
     }
 }
 
 __device__ void greedy_resolver(const GreedyParams &p, uint32_t *s_in, uint32_t *s_und,
-                                uint32_t *s_pre, uint32_t *s_inprev)
+                                uint32_t *s_pre, uint32_t *s_inprev, uint32_t *s_rep)
 {
     const int t = threadIdx.x, lane = t & 31, g = t >> 5;
+    if (p.rep_in_smem) {
+        const int nwords = 4 * ((p.n + 127) >> 7);
+        for (int i = t; i < nwords; i += 1024) s_rep[i] = 0;
+        __syncthreads();
+    }
     const int nscan = gridDim.x - 1;
     const int nblk = (p.total + MIS_NB - 1) / MIS_NB;
     int found = 0;
@@ -465,18 +486,18 @@ __device__ void greedy_resolver(const GreedyParams &p, uint32_t *s_in, uint32_t 
         // the scanners' output: L2 only (this SM's L1 may hold the lines of two blocks ago)
         const uint32_t *own = p.adj_own + (size_t)buf * 32 * MIS_NB;
         const uint32_t *prev = p.adj_prev + (size_t)buf * 32 * MIS_NB;
-        bool undec = t < cnt && __ldcg(p.alive8 + buf * MIS_NB + t) != 0;
+        // all loads of the block are issued at once (one L2 latency, not one per dependency);
+        // the words of a sequence that is not alive were not written and are never used
+        const uint8_t alive = t < cnt ? __ldcg(p.alive8 + buf * MIS_NB + t) : (uint8_t)0;
         uint32_t a[32];
 #pragma unroll
-        for (int w = 0; w < 32; w++) a[w] = (w <= g && undec) ? __ldcg(own + w * MIS_NB + t) : 0u;
-        if (b > 0) {
-            uint32_t hitp = 0;
-            if (undec) {
+        for (int w = 0; w < 32; w++) a[w] = (w <= g && t < cnt) ? __ldcg(own + w * MIS_NB + t) : 0u;
+        uint32_t hitp = 0;
+        if (b > 0 && t < cnt) {
 #pragma unroll
-                for (int w = 0; w < 32; w++) hitp |= __ldcg(prev + w * MIS_NB + t) & s_inprev[w];
-            }
-            undec = undec && hitp == 0;
+            for (int w = 0; w < 32; w++) hitp |= __ldcg(prev + w * MIS_NB + t) & s_inprev[w];
         }
+        bool undec = alive != 0 && hitp == 0;
         {
             const uint32_t bu = __ballot_sync(0xffffffffu, undec);
             if (lane == 0) {
@@ -487,10 +508,14 @@ __device__ void greedy_resolver(const GreedyParams &p, uint32_t *s_in, uint32_t 
         __syncthreads();
         for (;;) {
             uint32_t hit = 0, wait = 0;
+            const uint4 *in4 = reinterpret_cast<const uint4 *>(s_in);
+            const uint4 *und4 = reinterpret_cast<const uint4 *>(s_und);
 #pragma unroll
-            for (int w = 0; w < 32; w++) {
-                hit |= a[w] & s_in[w];
-                wait |= a[w] & s_und[w];
+            for (int w4 = 0; w4 < 8; w4++) {
+                if (4 * w4 > g) break;  // a[w] = 0 beyond the warp's own word (warp-uniform)
+                const uint4 i4 = in4[w4], u4 = und4[w4];
+                hit |= (a[4 * w4] & i4.x) | (a[4 * w4 + 1] & i4.y) | (a[4 * w4 + 2] & i4.z) | (a[4 * w4 + 3] & i4.w);
+                wait |= (a[4 * w4] & u4.x) | (a[4 * w4 + 1] & u4.y) | (a[4 * w4 + 2] & u4.z) | (a[4 * w4 + 3] & u4.w);
             }
             const bool out = undec && hit != 0;
             const bool in = undec && hit == 0 && wait == 0;
@@ -517,12 +542,22 @@ __device__ void greedy_resolver(const GreedyParams &p, uint32_t *s_in, uint32_t 
         const uint32_t mine = s_in[g];
         if ((mine >> lane) & 1u) {
             if (p.clusters) p.clusters[found + s_pre[g] + __popc(mine & ((1u << lane) - 1u))] = my_seq;
-            atomicOr(&p.rep[my_seq >> 5], 1u << (my_seq & 31));
+            if (p.rep_in_smem)
+                atomicOr(&s_rep[my_seq >> 5], 1u << (my_seq & 31));
+            else
+                atomicOr(&p.rep[my_seq >> 5], 1u << (my_seq & 31));
         }
         found += (int)(s_pre[31] + __popc(s_in[31]));
         if (lane == 0) s_inprev[g] = mine;
-        __threadfence();
         __syncthreads();  // also: every thread has read s_in / s_pre before the next block resets them
+        if (p.rep_in_smem) {
+            // the bitset lives in shared memory and goes out as whole lines: ~50 plain stores
+            // for the publishing fence to wait for, instead of ~900 scattered atomics
+            const int nwords = 4 * ((p.n + 127) >> 7);
+            for (int i = t; i < nwords; i += 1024) p.rep[i] = s_rep[i];
+            __syncthreads();
+        }
+        // release is cumulative: it publishes what the CTA wrote to rep / clusters before the barrier
         if (t == 0) st_release_gpu(p.resolved, b + 1);
     }
     if (t == 0) *p.count = found;
@@ -532,9 +567,10 @@ __global__ void __launch_bounds__(1024, 1) k_greedy_clusters(const GreedyParams 
 {
     __shared__ int s_ord[2][MIS_NB];
     __shared__ uint32_t s_hit[MIS_SEQ_PER_CTA][4];
-    __shared__ uint32_t s_masks[4][32];
+    __shared__ __align__(16) uint32_t s_masks[4][32];
+    extern __shared__ __align__(16) uint32_t s_rep[];  // the resolver's copy of `rep` (rep_in_smem)
     if (blockIdx.x == 0)
-        greedy_resolver(p, s_masks[0], s_masks[1], s_masks[2], s_masks[3]);
+        greedy_resolver(p, s_masks[0], s_masks[1], s_masks[2], s_masks[3], s_rep);
     else
         greedy_scanner(p, s_ord, s_hit);
 }
@@ -581,8 +617,13 @@ cudaError_t launch_greedy_clusters(const uint32_t *rows, int n, const int *order
     if (e != cudaSuccess) return e;
     // every CTA must be resident (the CTAs wait for each other): cooperative launch, at most
     // one CTA of 1024 threads per SM
+    const size_t rep_smem = nslab * 16;
+    p.rep_in_smem = rep_smem <= 64 * 1024;  // up to 524 288 sequences
+    const size_t dyn = p.rep_in_smem ? rep_smem : 0;
+    e = cudaFuncSetAttribute(k_greedy_clusters, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_greedy_clusters, 1024, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_greedy_clusters, 1024, dyn);
     if (e != cudaSuccess) return e;
     if (per_sm < 1 || num_sms < 2) return cudaErrorLaunchOutOfResources;
     const int want = (min(total, MIS_NB) + MIS_SEQ_PER_CTA - 1) / MIS_SEQ_PER_CTA;
@@ -596,6 +637,7 @@ cudaError_t launch_greedy_clusters(const uint32_t *rows, int n, const int *order
     cfg.numAttrs = 1;
     cfg.gridDim = dim3(1 + nscan);
     cfg.blockDim = dim3(1024);
+    cfg.dynamicSmemBytes = dyn;
     return cudaLaunchKernelEx(&cfg, k_greedy_clusters, p);
 }
 
