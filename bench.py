@@ -569,8 +569,47 @@ def run_identity(args, env):
                 line["similarity"] = similarity_extra(pb, CONFIGS, synthetic_msa)
             except Exception as exc:  # never lose the headline line over the secondary figure
                 line["similarity"] = {"error": repr(exc)}
+            try:
+                line["overlap"] = overlap_extra(pb, CONFIGS, synthetic_msa)
+            except Exception as exc:
+                line["overlap"] = {"error": repr(exc)}
         print(json.dumps(line), flush=True)
     dev.close()
+
+
+def overlap_extra(pb, CONFIGS, synthetic_msa):
+    """BASELINE.json's configs[4] beside the headline: Overlap::calculateSpuriousVector and the gap
+    counts over C5, host buffers in and out, checked against the reference's stored vector (see
+    --workload C5 for the full line)."""
+    n, L, seed = CONFIGS["C5"]
+    m = synthetic_msa(n, L, seed)
+    X = ord("X")
+    peaks = measured_peaks()
+    with pb.DeviceAlignment(m) as d:
+        best = {"spurious": (1e30, 1e30), "gaps": (1e30, 1e30)}
+        for _ in range(3):
+            t0 = time.perf_counter()
+            sp = d.spurious(0.5, indet=X)
+            best["spurious"] = (min(best["spurious"][0], d.timings["kernel_ms"]),
+                                min(best["spurious"][1], time.perf_counter() - t0))
+            t0 = time.perf_counter()
+            g = d.gaps()[0]
+            best["gaps"] = (min(best["gaps"][0], d.timings["kernel_ms"]),
+                            min(best["gaps"][1], time.perf_counter() - t0))
+    out = {"workload": workload_name("C5", n, L)}
+    gpath = os.path.join(ROOT, "tests", "golden", "full", "C5.npz")
+    if os.path.exists(gpath):
+        ref = np.load(gpath)
+        out["bit_identical_to_reference"] = bool(
+            (sp.view(np.uint32) == ref["spurious_50"].view(np.uint32)).all() and (g == ref["gaps"]).all())
+    for name, byts in (("spurious", 2 * n * L + 4 * n), ("gaps", n * L + 4 * L)):
+        k, w = best[name]
+        out[name] = {"kernel_ms": k, "call_ms_host_buffers": w * 1e3,
+                     "roofline": {"bound": "hbm", "achieved": byts / (k * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                                  "unit": "GB/s", "frac": byts / (k * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
+    out["spurious"]["value"] = n * (n - 1) * L / (best["spurious"][0] * 1e-3)
+    out["spurious"]["unit"] = "ordered " + UNIT
+    return out
 
 
 def similarity_extra(pb, CONFIGS, synthetic_msa):
