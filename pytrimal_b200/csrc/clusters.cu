@@ -1,4 +1,4 @@
-// clusters.cu -- K5..K8: consumers of the device-resident identity matrix
+// clusters.cu -- K5..K7: consumers of the device-resident identity matrix
 // (SURVEY 8f rank 1).
 //
 // The reference computes the packed nseq x nseq identity matrix and then walks it

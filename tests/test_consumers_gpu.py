@@ -107,7 +107,7 @@ def test_select_method_cutpoint_and_representatives(gpu, port, n, L, seed):
                                  (383, 700), (1000, 200), (1025, 64), (2100, 96), (2700, 33)])
 def test_representatives_threshold_epilogue(gpu, port, n, L):
     """tcu_representatives = K1 in threshold mode (one bit per pair, slab layout) + the mirror
-    pass + K7/K8: every tile-edge shape, thresholds at exact identity values (the > must not
+    pass + the clustering kernel (K7): every tile-edge shape, thresholds at exact identity values (the > must not
     become >=), negative and >= 1 thresholds, masked columns."""
     rng = np.random.default_rng(n * 131 + L)
     m = family_msa(n, L, n + L) if n >= 64 else random_msa(rng, n, L)

@@ -92,7 +92,7 @@ def test_c4_identity_matrix_and_representatives_full_size(gpu):
     m = msa_of("C4", g)
     n = m.shape[0]
     with gpu.DeviceAlignment(m) as d:
-        reps = d.representatives(0.8, indet=X)          # K1 threshold mode + K7/K8
+        reps = d.representatives(0.8, indet=X)          # K1 threshold mode + K7
         assert reps.tolist() == g["representatives_80"].tolist()
         assert (d.gaps()[0] == g["gaps"]).all()
         ident = d.identity(X, keep_on_device=True)      # 5 GB of floats to the host
