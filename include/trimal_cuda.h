@@ -377,8 +377,10 @@ int tcu_gaps_all(tcu_msa *msa, tcu_comm *comm, const int *save_seq, int *gaps_in
                  int *num_cols_with_gaps, int *max_gaps);
 int tcu_spurious_all(tcu_msa *msa, tcu_comm *comm, uint8_t indet, uint32_t ovrlap,
                      float *spurious);
-/* tcu_representatives with the identity matrix computed in row bands across the ranks
- * (tcu_identity_all); the clustering itself is sequential and runs on every rank. */
+/* tcu_representatives with the pair matrix split into row bands across the ranks: every
+ * rank's identity kernel thresholds its band and stores the bits into ALL ranks' matrices over
+ * peer memory (NVLink; NCCL transfers when the ranks cannot map each other's memory); the
+ * clustering itself is sequential and runs on every rank. */
 int tcu_representatives_all(tcu_msa *msa, tcu_comm *comm, const int *save_res, uint8_t indet,
                             float threshold, int *clusters, int *n_clusters);
 
