@@ -348,6 +348,16 @@ int tcu_representatives(tcu_msa *msa, const int *save_res, uint8_t indet, float 
 typedef struct tcu_comm tcu_comm;
 #define TCU_COMM_ID_BYTES 128
 
+/*
+ * Environment read by the library (all optional):
+ *   TRIMAL_CUDA_DEVICES          device set of TCU_DEVICE_AUTO handles ("all", "0,1,2,3")
+ *   TRIMAL_CUDA_MULTI_MIN_BYTES  alignments smaller than this stay on one device (default 4 MB)
+ *   TRIMAL_CUDA_NO_PEER=1        ranks never map each other's memory: every exchange of the
+ *                                *_all calls goes through NCCL transfers (must be set on all ranks)
+ *   TRIMAL_CUDA_NVTX=1           NVTX ranges around the entry points
+ *   TCU_TRACE=1                  host-clock phase timings on stderr
+ */
+
 /* Rank 0 creates the 128-byte rendezvous id (ncclGetUniqueId); the caller hands it to the
  * other ranks by any means it has (torch.distributed, MPI, a file). */
 int tcu_comm_id(void *id);

@@ -434,7 +434,9 @@ struct tcu_comm {
     std::mutex mutex;
     uint8_t *d_sync = nullptr;   // handle exchange area + the word of the stream-ordered barriers
     uint8_t *h_sync = nullptr;   // pinned mirror
-    bool ipc_usable = true;      // cleared for good on the first failure (agreed by all ranks)
+    // peer memory between the ranks; cleared for good on the first failure (agreed by all
+    // ranks), or from the start with TRIMAL_CUDA_NO_PEER=1 in the environment (every rank's)
+    bool ipc_usable = getenv("TRIMAL_CUDA_NO_PEER") == nullptr;
 };
 constexpr size_t COMM_SYNC_BYTES = 64 * 64 + 256;  // up to 64 ranks x 64-byte IPC handles + flags
 

@@ -22,13 +22,21 @@ def _free_port():
     return p
 
 
-def test_all_rank_calls_match_single_gpu(gpu):
+@pytest.mark.parametrize("peer_memory", [True, False])
+def test_all_rank_calls_match_single_gpu(gpu, peer_memory):
+    """With peer memory (CUDA IPC: the exchanges are stores from the producing kernels into the
+    other ranks' buffers) and without it (TRIMAL_CUDA_NO_PEER=1: NCCL point-to-point transfers,
+    the path a box takes whose ranks cannot map each other's memory)."""
     if gpu.device_count() < 2:
         pytest.skip("needs two GPUs in the box")
     world = min(gpu.device_count(), 4)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
            f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(ROOT, "tools", "multigpu_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ)
+    env.pop("TRIMAL_CUDA_NO_PEER", None)
+    if not peer_memory:
+        env["TRIMAL_CUDA_NO_PEER"] = "1"
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert '"all_ranks_bit_identical": true' in r.stdout
