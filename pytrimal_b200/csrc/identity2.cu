@@ -487,9 +487,11 @@ __global__ void __launch_bounds__(ID2_THREADS, NP <= 5 ? 2 : 1) k_identity2(cons
                     const float v = d == 0 ? 0.0f
                                            : (PACKED ? div_small_counts((float)h, (float)d)
                                                      : __fdiv_rn((float)h, (float)d));
-                    p.out[pos - p.out_base] = v;
-                    if (p.hit_out) p.hit_out[pos] = h;
-                    if (p.dst_out) p.dst_out[pos] = d;
+                    // streaming stores: 4 * P bytes pass through L2 once and must not evict the
+                    // operand planes every CTA keeps re-reading (40 MB against 5 GB at C4)
+                    __stcs(p.out + (pos - p.out_base), v);
+                    if (p.hit_out) __stcs(p.hit_out + pos, h);
+                    if (p.dst_out) __stcs(p.dst_out + pos, d);
                 }
             }
             __syncwarp();  // the patch is rewritten by the next tile
