@@ -335,6 +335,9 @@ cudaError_t launch_row_stats(const float *id, int n, bool upper_only, float *row
 // see `rep` while the resolver adds block b-1's representatives to it: harmless, those are
 // genuine earlier representatives and the union with the prev check is the same.
 // ---------------------------------------------------------------------------
+#ifndef MIS_FORCE_GLOBAL_REP
+#define MIS_FORCE_GLOBAL_REP 0
+#endif
 constexpr int MIS_NB = 1024;
 constexpr int MIS_SEQ_PER_CTA = 8;  // 1024 threads, four warps per sequence
 
@@ -618,7 +621,9 @@ cudaError_t launch_greedy_clusters(const uint32_t *rows, int n, const int *order
     // every CTA must be resident (the CTAs wait for each other): cooperative launch, at most
     // one CTA of 1024 threads per SM
     const size_t rep_smem = nslab * 16;
-    p.rep_in_smem = rep_smem <= 64 * 1024;  // up to 524 288 sequences
+    // up to 524 288 sequences; beyond, the resolver updates `rep` in global memory (a build with
+    // -DMIS_FORCE_GLOBAL_REP=1 takes that path always: how the test suite was run over it once)
+    p.rep_in_smem = !MIS_FORCE_GLOBAL_REP && rep_smem <= 64 * 1024;
     const size_t dyn = p.rep_in_smem ? rep_smem : 0;
     e = cudaFuncSetAttribute(k_greedy_clusters, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (e != cudaSuccess) return e;
