@@ -33,6 +33,7 @@
 //   warp 9     MMA issuer: one thread, two UMMAs per gap-byte stage, tcgen05.commit
 //              frees the stage / publishes the accumulator (two TMEM buffers)
 #include <algorithm>
+#include <type_traits>
 
 #include "tcu_internal.cuh"
 
@@ -422,78 +423,107 @@ __global__ void __launch_bounds__(ID2_THREADS, NP <= 5 ? 2 : 1) k_identity2(cons
             if (p.bits_out != nullptr) {
                 if (k > 0) flush_bits((int)((k - 1) & 1));  // the previous tile's entries
                 // threshold mode (Cleaner.cpp:1435-1440: a pair joins two sequences iff
-                // identity > threshold): the same division, but only its comparison with the
-                // threshold leaves the SM.  ballot(a, b) holds bit (i = li + 4a, j = lj + 8b)
-                // of the patch at lane position li + 4 lj; lane c assembles the word of patch
-                // column c (sequence j0 + c against the 32 sequences i0 ..): nibble c % 8 of
-                // the ballots with b = c / 8, one nibble per a.  Patches below the diagonal
-                // hold no pair j > i and store zeros (the mirror pass fills them).
+                // identity > threshold): only the comparison with the threshold leaves the SM,
+                // decided in integers (ThresholdRule).  A thread owns the pairs i = li + 4a,
+                // j = lj + 8b of the warp's 32 x 32 patch: its bits of column j go to positions
+                // li + 4a of cw[b], the four lanes that share lj OR their words together (two
+                // shuffles per column instead of a ballot per pair), and lane (lj, li) keeps
+                // the word of patch column c = lj + 8 li (sequence j0 + c against the 32
+                // sequences i0 ..).  Patches below the diagonal hold no pair j > i and store
+                // zeros (the mirror pass fills them); a patch strictly above it and inside the
+                // matrix needs no per-pair bounds.
                 const int i0 = BI * IB + 32 * wi, j0 = bj * RB + 32 * wj;
-                uint32_t colword = 0;
-                if (j0 + 31 > i0) {
+                uint32_t cw[4] = {0u, 0u, 0u, 0u};
+                if (j0 + 31 > i0 && p.thr.mode != 0) {
+                    const bool interior = i0 + 31 < p.nk && j0 + 31 < p.nk && j0 > i0 + 31;
+                    auto fill = [&](auto inside, auto always) {
 #pragma unroll
-                    for (int a = 0; a < 8; a++) {
-                        const int i = i0 + li + 4 * a;
-                        uint32_t mine = 0;
+                        for (int a = 0; a < 8; a++) {
+                            const int i = i0 + li + 4 * a;
 #pragma unroll
-                        for (int b = 0; b < 4; b++) {
-                            const int j = j0 + lj + 8 * b;
-                            const int h = !PACKED ? (int)hit[a][b]
-                                                  : (b < 2 ? (int)(hit[a][b] & 0xFFFFu)
-                                                           : (int)(hit[a][b - 2] >> 16));
-                            const int d = p.total_bits - (int)patch[(li + 4 * a) * ID2_XS + lj + 8 * b];
-                            // fl(h / d) > thr, exactly, without dividing (ThresholdRule)
-                            const uint32_t q =
-                                (uint32_t)(((unsigned long long)p.thr.mul * (uint32_t)d) >> p.thr.shift);
-                            const bool over = p.thr.mode == 2 ? (uint32_t)h > q : p.thr.mode == 1;
-                            const bool bit = i < p.nk && j < p.nk && j > i && over;
-                            const uint32_t w = __ballot_sync(0xffffffffu, bit);
-                            if ((lane >> 3) == b) mine = w;
+                            for (int b = 0; b < 4; b++) {
+                                const int j = j0 + lj + 8 * b;
+                                bool over = true;
+                                if (!decltype(always)::value) {
+                                    const uint32_t h = !PACKED ? hit[a][b]
+                                                               : (b < 2 ? (hit[a][b] & 0xFFFFu)
+                                                                        : (hit[a][b - 2] >> 16));
+                                    const uint32_t d = (uint32_t)p.total_bits -
+                                                       patch[(li + 4 * a) * ID2_XS + lj + 8 * b];
+                                    // fl(h / d) > thr, exactly, without dividing
+                                    over = h > (uint32_t)(((unsigned long long)p.thr.mul * d) >> p.thr.shift);
+                                }
+                                if (!decltype(inside)::value) over = over && i < p.nk && j < p.nk && j > i;
+                                cw[b] |= (uint32_t)over << (li + 4 * a);
+                            }
                         }
-                        colword |= ((mine >> (4 * (lane & 7))) & 0xFu) << (4 * a);
+                    };
+                    using T = std::true_type;
+                    using F = std::false_type;
+                    if (p.thr.mode == 2) {
+                        if (interior) fill(T{}, F{});
+                        else fill(F{}, F{});
+                    } else {  // negative threshold: every pair
+                        if (interior) fill(T{}, T{});
+                        else fill(F{}, T{});
+                    }
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        cw[b] |= __shfl_xor_sync(0xffffffffu, cw[b], 1);
+                        cw[b] |= __shfl_xor_sync(0xffffffffu, cw[b], 2);
                     }
                 }
+                const uint32_t colword = li == 0 ? cw[0] : (li == 1 ? cw[1] : (li == 2 ? cw[2] : cw[3]));
+                const int c = lj + 8 * li;  // this lane's column of the patch
                 // The four words of a column (wi = 0..3) are 16 contiguous bytes of the slab
                 // layout, held by four warps.  Each warp parks its word in the padding of its
                 // patch (two buffers, by tile parity); one tile later -- the barrier above
                 // has then seen every warp finish this epilogue -- whole 16-byte column entries
                 // are stored, 1 KB contiguous per tile: to the local matrix and, in a multi-GPU
                 // run, straight into every peer's over NVLink.
-                patch[lane * ID2_XS + 32 + (int)(k & 1)] = colword;
+                patch[c * ID2_XS + 32 + (int)(k & 1)] = colword;
                 if (wi == 0)  // (nslab * nk entries: below 2^32 up to 740 000 sequences)
-                    patch[lane * ID2_XS + 34 + (int)(k & 1)] =
-                        j0 + lane < p.nk ? (uint32_t)((size_t)BI * p.nk + (size_t)(j0 + lane)) : 0xFFFFFFFFu;
+                    patch[c * ID2_XS + 34 + (int)(k & 1)] =
+                        j0 + c < p.nk ? (uint32_t)((size_t)BI * p.nk + (size_t)(j0 + c)) : 0xFFFFFFFFu;
                 __syncwarp();  // the patch is rewritten by the next tile
                 continue;
             }
+            // a tile strictly above the diagonal and inside the matrix (all but the rim)
+            // needs no per-pair bounds
+            const bool interior = BI * IB + IB - 1 < p.nk && bj * RB + RB - 1 < p.nk &&
+                                  bj * RB > BI * IB + IB - 1;
+            auto store_ratios = [&](auto inside) {
 #pragma unroll
-            for (int a = 0; a < 8; a++) {
-                const int il = 64 * half + rowA0 + 4 * a;  // row inside the super-block
-                const int i = BI * IB + il;
-                if (i >= p.nk) continue;
-                // offset of pair (i, i+1): i*n - i*(i+1)/2 - i - 1 + (i+1)
-                const unsigned long long row_base =
-                    (unsigned long long)i * n - ((unsigned long long)i * (i + 1)) / 2 - i - 1;
+                for (int a = 0; a < 8; a++) {
+                    const int il = 64 * half + rowA0 + 4 * a;  // row inside the super-block
+                    const int i = BI * IB + il;
+                    if (!decltype(inside)::value && i >= p.nk) continue;
+                    // offset of pair (i, i+1): i*n - i*(i+1)/2 - i - 1 + (i+1)
+                    const unsigned long long row_base =
+                        (unsigned long long)i * n - ((unsigned long long)i * (i + 1)) / 2 - i - 1;
 #pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const int jl = rowB0 + 8 * b;
-                    const int j = bj * RB + jl;
-                    if (j >= p.nk || j <= i) continue;
-                    const unsigned long long pos = row_base + j;
-                    const int h = !PACKED ? (int)hit[a][b]
-                                          : (b < 2 ? (int)(hit[a][b] & 0xFFFFu) : (int)(hit[a][b - 2] >> 16));
-                    const int d = p.total_bits - (int)patch[(li + 4 * a) * ID2_XS + lj + 8 * b];
-                    // PACKED: fewer than 65 536 columns, the short exact division applies
-                    const float v = d == 0 ? 0.0f
-                                           : (PACKED ? div_small_counts((float)h, (float)d)
-                                                     : __fdiv_rn((float)h, (float)d));
-                    // streaming stores: 4 * P bytes pass through L2 once and must not evict the
-                    // operand planes every CTA keeps re-reading (40 MB against 5 GB at C4)
-                    __stcs(p.out + (pos - p.out_base), v);
-                    if (p.hit_out) __stcs(p.hit_out + pos, h);
-                    if (p.dst_out) __stcs(p.dst_out + pos, d);
+                    for (int b = 0; b < 4; b++) {
+                        const int jl = rowB0 + 8 * b;
+                        const int j = bj * RB + jl;
+                        if (!decltype(inside)::value && (j >= p.nk || j <= i)) continue;
+                        const unsigned long long pos = row_base + j;
+                        const int h = !PACKED ? (int)hit[a][b]
+                                              : (b < 2 ? (int)(hit[a][b] & 0xFFFFu) : (int)(hit[a][b - 2] >> 16));
+                        const int d = p.total_bits - (int)patch[(li + 4 * a) * ID2_XS + lj + 8 * b];
+                        // PACKED: fewer than 65 536 columns, the short exact division applies
+                        const float v = d == 0 ? 0.0f
+                                               : (PACKED ? div_small_counts((float)h, (float)d)
+                                                         : __fdiv_rn((float)h, (float)d));
+                        // streaming stores: 4 * P bytes pass through L2 once and must not evict
+                        // the operand planes every CTA keeps re-reading (40 MB against 5 GB at C4)
+                        __stcs(p.out + (pos - p.out_base), v);
+                        if (p.hit_out) __stcs(p.hit_out + pos, h);
+                        if (p.dst_out) __stcs(p.dst_out + pos, d);
+                    }
                 }
-            }
+            };
+            if (interior) store_ratios(std::true_type{});
+            else store_ratios(std::false_type{});
             __syncwarp();  // the patch is rewritten by the next tile
         }
         if (p.bits_out != nullptr) {  // the last tile's column entries
