@@ -331,6 +331,10 @@ __global__ void __launch_bounds__(ID2_THREADS, NP <= 5 ? 2 : 1) k_identity2(cons
             for (int q = 0; q < p.n_bits_peer; q++) *reinterpret_cast<uint4 *>(p.bits_peer[q] + at) = v;
         };
 
+        // barrier addresses as plain shared-memory offsets, converted once
+        const uint32_t pfull_a = smem_u32(pfull), pempty_a = smem_u32(pempty);
+        const uint32_t accfull_a = smem_u32(accfull), accempty_a = smem_u32(accempty);
+
         int stage = 0;
         uint32_t phase = 0;
         long long k = 0;
@@ -356,7 +360,7 @@ __global__ void __launch_bounds__(ID2_THREADS, NP <= 5 ? 2 : 1) k_identity2(cons
             // by another one, so neither the XU latency nor its queue stalls the in-order
             // warp (ep / pc are the two pipeline registers per J row).
             for (int c = 0; c < p.nchunks; c++) {
-                mbar_wait(&pfull[stage], phase);
+                mbar_wait_a(pfull_a + 8u * (uint32_t)stage, phase);
                 const uint32_t *base = reinterpret_cast<const uint32_t *>(s_planes + stage * PST_B);
                 const uint32_t *a_rest = base + half * ROLE_W, *a_p0 = a_rest + KC2 * RB * RP;
                 const uint32_t *b_p0 = base + 2 * ROLE_W, *b_rest = b_p0 + p0_words();
@@ -380,7 +384,7 @@ __global__ void __launch_bounds__(ID2_THREADS, NP <= 5 ? 2 : 1) k_identity2(cons
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&pempty[stage]);
+                if (lane == 0) mbar_arrive_a(pempty_a + 8u * (uint32_t)stage);
                 if (++stage == ID2_PSTAGES) {
                     stage = 0;
                     phase ^= 1u;
@@ -398,13 +402,13 @@ __global__ void __launch_bounds__(ID2_THREADS, NP <= 5 ? 2 : 1) k_identity2(cons
             // receives row r; a warp-private shared-memory patch turns that into the
             // (li, lj) ownership of the hit counters -- no CTA-wide barrier.
             const int buf = (int)(k & 1);
-            mbar_wait(&accfull[buf], (uint32_t)((k >> 1) & 1));
+            mbar_wait_a(accfull_a + 8u * (uint32_t)buf, (uint32_t)((k >> 1) & 1));
             tc_fence_after();
             uint32_t both[32];
             tmem_ld32(tmem_base + ((uint32_t)(32 * wi) << 16) + (uint32_t)(buf * RB + 32 * wj), both);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&accempty[buf]);
+            if (lane == 0) mbar_arrive_a(accempty_a + 8u * (uint32_t)buf);
             // not needed for correctness (patches are warp-private): re-aligns the eight
             // warps once per tile so that all of them consume the same ring stage and
             // the other stages stay prefetched

@@ -309,6 +309,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "r"(parity)
         : "memory");
 }
+// The same two on a 32-bit shared-memory address computed once outside a hot loop (the
+// conversion from a generic pointer costs a special-register read each time it is redone).
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar_addr)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "TCU_WAITA:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra TCU_DONEA;\n"
+        "bra TCU_WAITA;\n"
+        "TCU_DONEA:\n"
+        "}\n" ::"r"(bar_addr),
+        "r"(parity)
+        : "memory");
+}
 // One non-blocking probe (about 90 cycles until the result is usable): issue it early,
 // test the result later, fall back to mbar_wait when it is 0.
 __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t *bar, uint32_t parity)
